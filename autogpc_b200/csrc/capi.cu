@@ -1,0 +1,187 @@
+// C ABI of the engine (include/autogpc_b200.h): context, workspace arena, datasets, building-block entry points.
+// The scoring pipeline itself is in score.cu.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "engine.h"
+
+using namespace agpc;
+
+static int fail(agpc_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess) {
+  if (ctx) {
+    char buf[512];
+    if (e != cudaSuccess)
+      snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    else
+      snprintf(buf, sizeof buf, "%s", what);
+    ctx->err = buf;
+  }
+  return code;
+}
+
+#define CK(ctx, expr)                                                  \
+  do {                                                                 \
+    cudaError_t _e = (expr);                                           \
+    if (_e != cudaSuccess) return fail(ctx, AGPC_E_CUDA, #expr, _e);   \
+  } while (0)
+
+int agpc_ctx::ensure_arena(size_t bytes) {
+  if (bytes <= arena_bytes) return AGPC_OK;
+  if (arena) {
+    cudaStreamSynchronize(stream);
+    cudaFree(arena);
+    arena = nullptr;
+    arena_bytes = 0;
+  }
+  cudaError_t e = cudaMalloc(&arena, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(this, AGPC_E_NOMEM, "workspace arena cudaMalloc", e);
+  }
+  arena_bytes = bytes;
+  return AGPC_OK;
+}
+
+size_t agpc_ctx::workspace_budget() {
+  if (limit) return limit;
+  size_t fr = 0, tot = 0;
+  if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return (size_t)8 << 30;
+  return (size_t)((double)(fr + arena_bytes) * 0.80);
+}
+
+extern "C" {
+
+int agpc_version(void) { return AGPC_VERSION; }
+
+int agpc_create(int device, agpc_ctx** out) {
+  if (!out) return AGPC_E_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return AGPC_E_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return AGPC_E_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return AGPC_E_CUDA;
+  if (prop.major != 10) return AGPC_E_UNSUPPORTED;  // sm_100a only: no fallback path exists
+  agpc_ctx* c = new (std::nothrow) agpc_ctx();
+  if (!c) return AGPC_E_NOMEM;
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return AGPC_E_CUDA;
+  }
+  *out = c;
+  return AGPC_OK;
+}
+
+int agpc_destroy(agpc_ctx* ctx) {
+  if (!ctx) return AGPC_E_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& d : ctx->datasets) {
+    if (d.X) cudaFree(d.X);
+    if (d.y) cudaFree(d.y);
+  }
+  if (ctx->arena) cudaFree(ctx->arena);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return AGPC_OK;
+}
+
+const char* agpc_last_error(agpc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int agpc_set_workspace_limit(agpc_ctx* ctx, uint64_t bytes) {
+  if (!ctx) return AGPC_E_ARG;
+  ctx->limit = (size_t)bytes;
+  return AGPC_OK;
+}
+
+int64_t agpc_launch_count(agpc_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int agpc_dataset_create(agpc_ctx* ctx, const double* X_host, const double* y_host, int32_t N, int32_t D,
+                        int32_t* dataset_id) {
+  if (!ctx || !X_host || !y_host || N <= 0 || D <= 0 || !dataset_id) return fail(ctx, AGPC_E_ARG, "dataset_create args");
+  CK(ctx, cudaSetDevice(ctx->device));
+  Dataset d;
+  d.N = N;
+  d.D = D;
+  CK(ctx, cudaMalloc(&d.X, sizeof(double) * (size_t)N * D));
+  CK(ctx, cudaMalloc(&d.y, sizeof(double) * (size_t)N));
+  CK(ctx, cudaMemcpyAsync(d.X, X_host, sizeof(double) * (size_t)N * D, cudaMemcpyHostToDevice, ctx->stream));
+  // labels: 1 -> +1, everything else -> -1 (GPy bernoulli.py moments_match_ep)
+  std::vector<double> ypm(N);
+  for (int i = 0; i < N; ++i) ypm[i] = (y_host[i] == 1.0) ? 1.0 : -1.0;
+  CK(ctx, cudaMemcpyAsync(d.y, ypm.data(), sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  // reuse a free slot if any
+  for (size_t i = 0; i < ctx->datasets.size(); ++i)
+    if (ctx->datasets[i].X == nullptr) {
+      ctx->datasets[i] = d;
+      *dataset_id = (int32_t)i;
+      return AGPC_OK;
+    }
+  ctx->datasets.push_back(d);
+  *dataset_id = (int32_t)ctx->datasets.size() - 1;
+  return AGPC_OK;
+}
+
+int agpc_dataset_destroy(agpc_ctx* ctx, int32_t id) {
+  if (!ctx || id < 0 || id >= (int)ctx->datasets.size() || !ctx->datasets[id].X) return fail(ctx, AGPC_E_ARG, "bad dataset id");
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->datasets[id].X);
+  cudaFree(ctx->datasets[id].y);
+  ctx->datasets[id] = Dataset();
+  return AGPC_OK;
+}
+
+int agpc_gemm_nt(agpc_ctx* ctx, const double* A, const double* B, double* C, int32_t M, int32_t N, int32_t K,
+                 double alpha, double beta, int32_t batch, void* stream) {
+  if (!ctx || !A || !B || !C || M <= 0 || N <= 0 || K <= 0 || batch <= 0 || M % TILE || N % TILE || K % GEMM_BK)
+    return fail(ctx, AGPC_E_ARG, "gemm_nt: M,N must be multiples of 128 and K of 16");
+  CK(ctx, cudaSetDevice(ctx->device));
+  CUtensorMap ma, mb;
+  if (make_tensor_map(&ma, A, K, M, batch, K, (long long)M * K) || make_tensor_map(&mb, B, K, N, batch, K, (long long)N * K))
+    return fail(ctx, AGPC_E_CUDA, "cuTensorMapEncodeTiled failed");
+  GemmArgs g{};
+  g.C = C; g.ldc = N; g.c_batch = (long long)M * N;
+  g.m_tiles = M / TILE; g.n_tiles = N / TILE; g.k_tiles = K / GEMM_BK;
+  g.alpha = alpha; g.beta = beta;
+  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches};
+  CK(ctx, gemm_nt_launch(L, ma, mb, g, g.m_tiles * g.n_tiles, 1, batch));
+  return AGPC_OK;
+}
+
+int agpc_potrf(agpc_ctx* ctx, double* A, int32_t n, int32_t batch, double* Minv, double* Uinv, int32_t* info,
+               void* stream) {
+  if (!ctx || !A || n <= 0 || batch <= 0 || n % TILE) return fail(ctx, AGPC_E_ARG, "potrf: n must be a multiple of 128");
+  CK(ctx, cudaSetDevice(ctx->device));
+  const size_t mat = sizeof(double) * (size_t)n * n * batch;
+  const bool want_inv = (Minv != nullptr) || (Uinv != nullptr);
+  size_t need = 0;
+  if (!Minv) need += mat;
+  if (!Uinv) need += mat;
+  if (want_inv) need += mat;  // T
+  int rc = ctx->ensure_arena(need + 4096);
+  if (rc) return rc;
+  char* p = (char*)ctx->arena;
+  MatSet ms;
+  ms.np = n; ms.batch = batch; ms.stride = (long long)n * n;
+  ms.A = A;
+  ms.M = Minv ? Minv : (double*)p; if (!Minv) p += mat;
+  ms.U = Uinv ? Uinv : (double*)p; if (!Uinv) p += mat;
+  ms.T = want_inv ? (double*)p : nullptr;
+  if (make_tensor_map(&ms.mapA, ms.A, n, n, batch, n, ms.stride) || make_tensor_map(&ms.mapM, ms.M, n, n, batch, n, ms.stride) ||
+      make_tensor_map(&ms.mapU, ms.U, n, n, batch, n, ms.stride) ||
+      (want_inv && make_tensor_map(&ms.mapT, ms.T, n, n, batch, n, ms.stride)))
+    return fail(ctx, AGPC_E_CUDA, "cuTensorMapEncodeTiled failed");
+  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches};
+  if (info) CK(ctx, cudaMemsetAsync(info, 0, sizeof(int32_t) * batch, L.stream));
+  CK(ctx, potrf_blocked(L, ms, nullptr, info));
+  if (want_inv) CK(ctx, trtri_blocked(L, ms, nullptr));
+  return AGPC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,143 @@
+// Shared declarations of the autogpc_b200 CUDA engine (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/autogpc_b200.h"
+
+namespace agpc {
+
+constexpr int TILE = 128;       // factorisation block = GEMM CTA tile edge; every matrix is padded to a multiple
+constexpr int GEMM_BK = 16;     // K-chunk of the GEMM pipeline: 16 doubles = one 128-byte TMA swizzle span
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_CONSUMER_WARPS = 16;
+constexpr int GEMM_THREADS = (GEMM_CONSUMER_WARPS + 1) * 32;
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * 2 * TILE * GEMM_BK * 8 + 1024 /*align slack*/ + 128 /*barriers*/;
+
+// What a GEMM tile's extents / K-range depend on (see gemm_nt.cu).
+enum : int { EXT_FIXED = 0, EXT_H2 = 1 };
+enum : int { KRULE_FULL = 0, KRULE_BEGIN_AT_ROW = 1, KRULE_END_AT_ROW = 2, KRULE_END_AT_COL = 3 };
+
+struct GemmArgs {
+  double* C;                 // output (row-major), element (r, c) of batch b at C + b*c_batch + r*ldc + c
+  double* Ct;                // optional second, transposed output: Ct + b*c_batch + c*ldc + r   (nullptr = none)
+  long long ldc, c_batch;
+  int a_row0, a_col0, b_row0, b_col0, c_row0, c_col0, ct_row0, ct_col0;  // element offsets (group-relative)
+  int m_tiles, n_tiles, k_tiles;  // extents when EXT_FIXED: tiles of 128 x 128 x 16
+  int m_kind, n_kind, k_kind;     // EXT_FIXED or EXT_H2 (right-half size of trtri group g, may be partial)
+  int grp_blocks, half_blocks, nblk;  // trtri grouping: group g covers blocks [g*grp_blocks, ...)
+  int k_rule, lower_only;
+  double alpha, beta;
+  const int* active;  // per-batch-item flag (nullptr = all active)
+};
+
+// Launchers (host).  Every launcher bumps *launch_counter when non-null.
+struct Launch {
+  cudaStream_t stream;
+  long long* counter;
+  void bump(int n = 1) const {
+    if (counter) *counter += n;
+  }
+};
+
+// gemm_nt.cu
+cudaError_t gemm_nt_launch(const Launch& L, const CUtensorMap& mapA, const CUtensorMap& mapB, const GemmArgs& args,
+                           int tiles_x, int groups, int batch);
+// Encodes a 3-D FP64 tensor map {cols, rows, batch} with a {16, 128, 1} box and 128-byte swizzle.
+int make_tensor_map(CUtensorMap* out, const double* base, long long cols, long long rows, long long batch,
+                    long long ld, long long batch_stride);
+
+// One lock-step batch of padded np x np matrices (np % 128 == 0, ld == np, matrix b at base + b*stride) and the
+// tensor maps the GEMM kernel reads them through.
+//   K: kernel matrix            A: B = I + S^1/2 K S^1/2 -> L (lower)        M: L^-1 (lower)
+//   U: L^-T (upper)             T: scratch (trtri) / B^-1 (lauum output)
+struct MatSet {
+  int np = 0, batch = 0;
+  long long stride = 0;
+  double *K = nullptr, *A = nullptr, *M = nullptr, *U = nullptr, *T = nullptr;
+  CUtensorMap mapA, mapM, mapU, mapT;
+};
+
+// chol.cu
+cudaError_t potrf_blocked(const Launch& L, const MatSet& ms, const int* active, int* info);
+cudaError_t trtri_blocked(const Launch& L, const MatSet& ms, const int* active);
+cudaError_t lauum_blocked(const Launch& L, const MatSet& ms, double* dst, const int* active);
+cudaError_t potf2_inv_launch(const Launch& L, double* A, double* M, double* U, long long ld, long long batch_stride,
+                             int diag_block, int batch, const int* active, int* info);
+
+// kbuild.cu
+struct BuildArgs {
+  const agpc_program* progs;   // [batch] (device)
+  const double* theta;         // [batch][theta_stride]
+  int theta_stride;
+  const double* Xa;            // row points  [batch][na_pad][D]
+  const double* Xb;            // col points  [batch][nb_pad][D]
+  const int* na_of;            // [batch] valid rows (nullptr -> na_fixed)
+  const int* nb_of;            // [batch] valid cols (nullptr -> nb_fixed)
+  int na_fixed, nb_fixed;
+  int na_pad, nb_pad, D;
+  long long xa_batch, xb_batch;  // batch strides of Xa / Xb in elements
+  double* out;                   // [batch][na_pad][ld]
+  long long ld, out_batch;
+  double* dK;                    // optional [batch][n_theta][na_pad][ld]
+  double* kdiag;                 // optional [batch][na_pad] (only meaningful when Xa == Xb)
+  const int* active;
+};
+struct GradArgs {
+  const agpc_program* progs;
+  const double* theta;
+  int theta_stride;
+  const double* Xf;    // [batch][np][D]
+  const int* n_of;     // valid n per item (nullptr -> n_fixed)
+  int n_fixed, np, D;
+  const double* G;     // B^-1 lower tiles (mode 0) or a full weight matrix (mode 1): [batch][np][ld]
+  long long ld, g_batch;
+  const double* alpha; // [batch][np]   (mode 0)
+  const double* s;     // [batch][np]   (mode 0)
+  int mode;
+  double* partial;     // [batch][tiles][AGPC_MAX_THETA]
+  int tiles_per_item;
+  const int* active;
+};
+cudaError_t build_K_launch(const Launch& L, const BuildArgs& a, int batch, bool grad);
+cudaError_t kself_launch(const Launch& L, const agpc_program* progs, const double* theta, int theta_stride,
+                         const double* Xs, int m_pad, int D, const int* m_of, int batch, double* kss);
+cudaError_t gather_rows_launch(const Launch& L, const double* X, const double* y, const int* rows,
+                               const long long* row_off, const int* n_of, int D, int np, int batch, double* Xf,
+                               double* yf);
+cudaError_t form_B_launch(const Launch& L, const double* K, const double* s, double* A, int np, long long stride,
+                          int batch, const int* active);
+cudaError_t scale_cols_launch(const Launch& L, double* Ks, const double* s, int rows, int np, int batch);
+cudaError_t grad_contract_launch(const Launch& L, const GradArgs& a, int batch, double scale, double* grad,
+                                 int grad_stride);
+int grad_tiles(int np, int mode);
+
+// ep.cu
+cudaError_t rowdot_launch(const Launch& L, int range, bool sq, const double* A, const double* x, double* y,
+                          double* y2, int nrows, int ncols, long long a_batch, long long x_batch, long long y_batch,
+                          int batch, const int* active);
+cudaError_t sqrt_scale_launch(const Launch& L, const double* tau, const double* w, double* s, double* u, int np,
+                              int batch, const int* active);
+cudaError_t mul_launch(const Launch& L, const double* a, const double* b, double* out, int np, int batch,
+                       const int* active);
+cudaError_t marginals_launch(const Launch& L, const double* tau, const double* dB, const double* w, const double* kv,
+                             const double* kdiag, double* sig, double* mu, const int* n_of, int np, int batch, int cold,
+                             const int* active);
+cudaError_t ep_update_launch(const Launch& L, double* tau, double* nu, const double* sig, const double* mu,
+                             const double* yf, const double* kdiag, const int* n_of, int np, int batch, double eps,
+                             double damping, int* active, int* sweeps, int* status, int* converged, const int* info);
+cudaError_t ep_final_launch(const Launch& L, const double* tau, const double* nu, const double* sig, const double* mu,
+                            const double* yf, const double* s, const double* z, const double* Lmat, long long stride,
+                            const int* n_of, int np, int batch, const agpc_program* progs, double* alpha, double* nlml,
+                            double* nlml_gauss, double* bic, int* status, const int* info);
+cudaError_t predict_prob_launch(const Launch& L, const double* mu_s, const double* kss, const double* vsq, double* p,
+                                double* var, long long total);
+
+}  // namespace agpc
+
+#define AGPC_CUDA_TRY(expr)                         \
+  do {                                              \
+    cudaError_t _e = (expr);                        \
+    if (_e != cudaSuccess) return _e;               \
+  } while (0)

@@ -1,0 +1,29 @@
+// Host-side engine state behind the opaque agpc_ctx handle.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+struct Dataset {
+  double* X = nullptr;  // N x D row-major (device)
+  double* y = nullptr;  // N, +-1 (device)
+  int N = 0, D = 0;
+};
+
+struct agpc_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  long long launches = 0;
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+  size_t limit = 0;
+  void* pinned = nullptr;  // small pinned staging buffer for per-sweep flags
+  size_t pinned_bytes = 0;
+  std::vector<Dataset> datasets;
+
+  int ensure_arena(size_t bytes);
+  size_t workspace_budget();
+};

@@ -1,0 +1,326 @@
+// EP site updates, posterior marginals and the log-marginal reductions (warp-reduction kernels).
+//
+// Stands in for GPy EP.expectation_propagation / Bernoulli.moments_match_ep / EP.inference's scalar algebra
+//  for gpckernel.py:245-246, restated for the *parallel* EP schedule (oracle.ep_parallel):
+//   marginals:  diag(Sigma)_i = (1 - (B^-1)_ii) / tau~_i,   (B^-1)_ii = sum_k U[i,k]^2  (U = L^-T)
+//               mu = w - K (s o z),  w = K nu~,  z = B^-1 (s o w) = U (M (s o w))
+//   sites:      cavity tau_ = 1/Sigma_ii - tau~_i, nu_ = mu_i/Sigma_ii - nu~_i; probit moments via erfcx;
+//               tau~ += damping * (1/sigma^2_hat - 1/Sigma_ii), nu~ += damping * (mu_hat/sigma^2_hat - mu_i/Sigma_ii)
+//   log Z_EP:   R&W (3.65) with (3.73)-(3.75); alpha = nu~ - s o z.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace agpc {
+
+// ---- row-oriented matrix-vector kernels: one warp per row, coalesced along the row ---------------------------
+// y_i = sum_{k in range(i)} A[i,k] x_k ;  optionally y2_i = sum_{k in range(i)} A[i,k]^2
+// range: 0 = all k < np, 1 = k <= i (lower), 2 = k >= i (upper)
+template <int RANGE, bool SQ>
+__global__ void __launch_bounds__(256)
+rowdot_kernel(const double* __restrict__ A, const double* __restrict__ x, double* __restrict__ y,
+              double* __restrict__ y2, int nrows, int ncols, long long a_batch, long long x_batch, long long y_batch,
+              const int* __restrict__ active) {
+  const int b = blockIdx.y;
+  if (active != nullptr && active[b] == 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + warp;
+  if (i >= nrows) return;
+  const double* row = A + (long long)b * a_batch + (long long)i * ncols;
+  const double* xb = x + (long long)b * x_batch;
+  int k0 = 0, k1 = ncols;
+  if (RANGE == 1) k1 = i + 1;
+  if (RANGE == 2) k0 = i;
+  // align the start down to a multiple of 2 so double2 loads are 16-byte aligned (ncols is even)
+  const int ka = k0 & ~1;
+  double s = 0.0, q = 0.0;
+  for (int k = ka + 2 * lane; k < k1; k += 64) {
+    const double2 a2 = *reinterpret_cast<const double2*>(row + k);
+    const double2 x2 = *reinterpret_cast<const double2*>(xb + k);
+    if (k >= k0) {
+      s += a2.x * x2.x;
+      if (SQ) q += a2.x * a2.x;
+    }
+    if (k + 1 < k1) {
+      s += a2.y * x2.y;
+      if (SQ) q += a2.y * a2.y;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (SQ) q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) {
+    y[(long long)b * y_batch + i] = s;
+    if (SQ) y2[(long long)b * y_batch + i] = q;
+  }
+}
+
+// range: 0 full row, 1 lower (k <= i), 2 upper (k >= i); sq: also y2_i = sum A[i,k]^2 over the same range
+cudaError_t rowdot_launch(const Launch& L, int range, bool sq, const double* A, const double* x, double* y,
+                          double* y2, int nrows, int ncols, long long a_batch, long long x_batch, long long y_batch,
+                          int batch, const int* active) {
+  dim3 grid((nrows + 7) / 8, batch);
+#define RD(R, S) rowdot_kernel<R, S><<<grid, 256, 0, L.stream>>>(A, x, y, y2, nrows, ncols, a_batch, x_batch, y_batch, active)
+  if (range == 0 && !sq) RD(0, false);
+  else if (range == 0) RD(0, true);
+  else if (range == 1) RD(1, false);
+  else if (sq) RD(2, true);
+  else RD(2, false);
+#undef RD
+  L.bump();
+  return cudaGetLastError();
+}
+
+// ---- probit helpers (same branches as oracle.log_cdf / pdf_over_cdf) ---------------------------------------------
+__device__ __forceinline__ double pdf_over_cdf(double z) {
+  return 0.79788456080286535588 /* sqrt(2/pi) */ / erfcx(-z * 0.70710678118654752440);
+}
+__device__ __forceinline__ double log_cdf(double z) {
+  const double t = -z * 0.70710678118654752440;
+  if (z > -5.0) return log(0.5 * erfc(t));
+  return log(0.5 * erfcx(t)) - t * t;
+}
+
+// ---- small elementwise steps ---------------------------------------------------------------------------------
+// s = sqrt(tau); u = s * w   (u optional)
+__global__ void sqrt_scale_kernel(const double* __restrict__ tau, const double* __restrict__ w, double* __restrict__ s,
+                                  double* __restrict__ u, int np, const int* __restrict__ active) {
+  const int b = blockIdx.y;
+  if (active != nullptr && active[b] == 0) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= np) return;
+  const long long o = (long long)b * np + i;
+  const double si = sqrt(tau[o]);
+  if (s) s[o] = si;
+  if (u) u[o] = si * w[o];
+}
+// out = a * b (elementwise)
+__global__ void mul_kernel(const double* __restrict__ a, const double* __restrict__ bvec, double* __restrict__ out,
+                           int np, const int* __restrict__ active) {
+  const int b = blockIdx.y;
+  if (active != nullptr && active[b] == 0) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= np) return;
+  const long long o = (long long)b * np + i;
+  out[o] = a[o] * bvec[o];
+}
+// sig = (1 - dB) / tau (or kdiag when tau == 0 everywhere: cold start), mu = w - kv
+__global__ void marginals_kernel(const double* __restrict__ tau, const double* __restrict__ dB,
+                                 const double* __restrict__ w, const double* __restrict__ kv,
+                                 const double* __restrict__ kdiag, double* __restrict__ sig, double* __restrict__ mu,
+                                 const int* __restrict__ n_of, int np, int cold, const int* __restrict__ active) {
+  const int b = blockIdx.y;
+  if (active != nullptr && active[b] == 0) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= np) return;
+  const long long o = (long long)b * np + i;
+  if (i >= n_of[b]) {
+    sig[o] = 1.0;
+    mu[o] = 0.0;
+    return;
+  }
+  if (cold) {
+    sig[o] = kdiag[o];
+    mu[o] = 0.0;
+  } else {
+    sig[o] = (1.0 - dB[o]) / tau[o];
+    mu[o] = w[o] - kv[o];
+  }
+}
+
+cudaError_t sqrt_scale_launch(const Launch& L, const double* tau, const double* w, double* s, double* u, int np,
+                              int batch, const int* active) {
+  dim3 grid((np + 255) / 256, batch);
+  sqrt_scale_kernel<<<grid, 256, 0, L.stream>>>(tau, w, s, u, np, active);
+  L.bump();
+  return cudaGetLastError();
+}
+cudaError_t mul_launch(const Launch& L, const double* a, const double* b, double* out, int np, int batch,
+                       const int* active) {
+  dim3 grid((np + 255) / 256, batch);
+  mul_kernel<<<grid, 256, 0, L.stream>>>(a, b, out, np, active);
+  L.bump();
+  return cudaGetLastError();
+}
+cudaError_t marginals_launch(const Launch& L, const double* tau, const double* dB, const double* w, const double* kv,
+                             const double* kdiag, double* sig, double* mu, const int* n_of, int np, int batch, int cold,
+                             const int* active) {
+  dim3 grid((np + 255) / 256, batch);
+  marginals_kernel<<<grid, 256, 0, L.stream>>>(tau, dB, w, kv, kdiag, sig, mu, n_of, np, cold, active);
+  L.bump();
+  return cudaGetLastError();
+}
+
+// ---- block reduction helper (fixed order -> deterministic) -----------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void block_reduce(double (&v)[NV], double* red /* [32][NV] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+    if (lane == 0) red[warp * NV + q] = v[q];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      double t = (lane < nw) ? red[lane * NV + q] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      v[q] = t;
+    }
+  }
+  __syncthreads();
+}
+
+// ---- EP site update: one CTA per item ------------------------------------------------------------------------
+// Reads marginals (sig, mu), updates (tau, nu) in place, decides convergence of the item.
+// active[b] <- 0 when converged (or failed); sweeps[b]++.
+__global__ void __launch_bounds__(1024)
+ep_update_kernel(double* __restrict__ tau, double* __restrict__ nu, const double* __restrict__ sig,
+                 const double* __restrict__ mu, const double* __restrict__ yf, const double* __restrict__ kdiag,
+                 const int* __restrict__ n_of, int np, double eps, double damping, int* __restrict__ active,
+                 int* __restrict__ sweeps, int* __restrict__ status, int* __restrict__ converged,
+                 const int* __restrict__ info) {
+  const int b = blockIdx.x;
+  if (active[b] == 0) return;
+  if (info[b] != 0) {  // the factorisation behind these marginals failed
+    if (threadIdx.x == 0) {
+      status[b] = info[b];
+      active[b] = 0;
+    }
+    return;
+  }
+  __shared__ double red[32 * 3];
+  const int n = n_of[b];
+  double acc[3] = {0.0, 0.0, 0.0};  // sum d_tau^2, sum d_nu^2, non-finite count
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const long long o = (long long)b * np + i;
+    const double sg = sig[o], m = mu[o], tt = tau[o], vt = nu[o], y = yf[o];
+    const double tau_cav = 1.0 / sg - tt;
+    const double v_cav = m / sg - vt;
+    const double den2 = tau_cav * tau_cav + tau_cav;
+    const double den = sqrt(den2);
+    const double z = y * v_cav / den;
+    const double N = pdf_over_cdf(z);
+    const double mu_hat = v_cav / tau_cav + y * N / den;
+    const double s2_hat = 1.0 / tau_cav - N * (z + N) / den2;
+    double d_tau = damping * (1.0 / s2_hat - 1.0 / sg);
+    const double d_v = damping * (mu_hat / s2_hat - m / sg);
+    double new_tau = tt + d_tau;
+    const double floor_tau = 1e-10 / kdiag[o];  // keeps (1 - Binv_ii)/tau well defined; see DESIGN.md
+    if (!(new_tau >= floor_tau)) new_tau = isnan(new_tau) ? new_tau : floor_tau;
+    d_tau = new_tau - tt;
+    const double new_v = vt + d_v;
+    tau[o] = new_tau;
+    nu[o] = new_v;
+    acc[0] += d_tau * d_tau;
+    acc[1] += d_v * d_v;
+    if (!isfinite(new_tau) || !isfinite(new_v)) acc[2] += 1.0;
+  }
+  block_reduce<3>(acc, red);
+  if (threadIdx.x == 0) {
+    const int sw = sweeps[b] + 1;
+    sweeps[b] = sw;
+    if (acc[2] > 0.0) {
+      status[b] = AGPC_ST_NONFINITE;
+      active[b] = 0;
+    } else if (sw > 1 && acc[0] / n <= eps && acc[1] / n <= eps) {
+      converged[b] = 1;
+      active[b] = 0;
+    }
+  }
+}
+
+cudaError_t ep_update_launch(const Launch& L, double* tau, double* nu, const double* sig, const double* mu,
+                             const double* yf, const double* kdiag, const int* n_of, int np, int batch, double eps,
+                             double damping, int* active, int* sweeps, int* status, int* converged, const int* info) {
+  ep_update_kernel<<<batch, 1024, 0, L.stream>>>(tau, nu, sig, mu, yf, kdiag, n_of, np, eps, damping, active, sweeps,
+                                                  status, converged, info);
+  L.bump();
+  return cudaGetLastError();
+}
+
+// ---- final reductions: log Z_EP, alpha, Gaussian-only value, BIC ----------------------------------------------
+__global__ void __launch_bounds__(1024)
+ep_final_kernel(const double* __restrict__ tau, const double* __restrict__ nu, const double* __restrict__ sig,
+                const double* __restrict__ mu, const double* __restrict__ yf, const double* __restrict__ s,
+                const double* __restrict__ z /* B^-1 (s o w) */, const double* __restrict__ Lmat, long long stride,
+                const int* __restrict__ n_of, int np, const agpc_program* __restrict__ progs,
+                double* __restrict__ alpha, double* __restrict__ nlml, double* __restrict__ nlml_gauss,
+                double* __restrict__ bic, int* __restrict__ status, const int* __restrict__ info) {
+  const int b = blockIdx.x;
+  __shared__ double red[32 * 4];
+  const int n = n_of[b];
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};  // site terms + 1/2 nu~.mu ; sum log L_ii ; gauss extras ; nonfinite
+  const double* Lb = Lmat + (long long)b * stride;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) {
+    const long long o = (long long)b * np + i;
+    if (i >= n) {
+      alpha[o] = 0.0;
+      continue;
+    }
+    const double sg = sig[o], m = mu[o], tt = tau[o], vt = nu[o], y = yf[o];
+    const double tau_cav = 1.0 / sg - tt;
+    const double v_cav = m / sg - vt;
+    const double zz = y * v_cav / sqrt(tau_cav * tau_cav + tau_cav);
+    const double tsum = tau_cav + tt;
+    const double site = log_cdf(zz) + 0.5 * log1p(tt / tau_cav) - 0.5 * vt * vt / tsum +
+                        0.5 * v_cav * ((tt / tau_cav) * v_cav - 2.0 * vt) / tsum;
+    const double a = vt - s[o] * z[o];
+    alpha[o] = a;
+    const double lii = Lb[(long long)i * np + i];
+    acc[0] += site + 0.5 * vt * m;
+    acc[1] += log(lii);
+    if (tt > 0.0) acc[2] += -log(tt) + (vt / tt) * a;
+    if (!isfinite(site) || !isfinite(a) || !(lii > 0.0)) acc[3] += 1.0;
+  }
+  block_reduce<4>(acc, red);
+  if (threadIdx.x == 0) {
+    const double log_z = -acc[1] + acc[0];
+    const double v = -log_z;
+    nlml[b] = v;
+    nlml_gauss[b] = 0.5 * (n * 1.8378770664093454836 /* ln 2 pi */ + 2.0 * acc[1] + acc[2]);
+    bic[b] = 2.0 * v + progs[b].p_eff * log((double)n);
+    if (info[b] != 0) status[b] = info[b];
+    else if ((acc[3] > 0.0 || !isfinite(v)) && status[b] != AGPC_ST_NOT_PD) status[b] = AGPC_ST_NONFINITE;
+    if (status[b] == AGPC_ST_NOT_PD || status[b] == AGPC_ST_NONFINITE) {
+      nlml[b] = CUDART_INF;
+      nlml_gauss[b] = CUDART_INF;
+      bic[b] = CUDART_INF;
+    }
+  }
+}
+
+cudaError_t ep_final_launch(const Launch& L, const double* tau, const double* nu, const double* sig, const double* mu,
+                            const double* yf, const double* s, const double* z, const double* Lmat, long long stride,
+                            const int* n_of, int np, int batch, const agpc_program* progs, double* alpha, double* nlml,
+                            double* nlml_gauss, double* bic, int* status, const int* info) {
+  ep_final_kernel<<<batch, 1024, 0, L.stream>>>(tau, nu, sig, mu, yf, s, z, Lmat, stride, n_of, np, progs, alpha, nlml,
+                                                 nlml_gauss, bic, status, info);
+  L.bump();
+  return cudaGetLastError();
+}
+
+// ---- predictive probability p* = Phi(mu* / sqrt(1 + v*)) -------------------------------------------------------
+__global__ void predict_prob_kernel(const double* __restrict__ mu_s, const double* __restrict__ kss,
+                                    const double* __restrict__ vsq, double* __restrict__ p, double* __restrict__ var,
+                                    long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const double v = kss[i] - vsq[i];
+  if (var) var[i] = v;
+  p[i] = 0.5 * erfc(-(mu_s[i] / sqrt(1.0 + v)) * 0.70710678118654752440);
+}
+
+cudaError_t predict_prob_launch(const Launch& L, const double* mu_s, const double* kss, const double* vsq, double* p,
+                                double* var, long long total) {
+  predict_prob_kernel<<<(unsigned)((total + 255) / 256), 256, 0, L.stream>>>(mu_s, kss, vsq, p, var, total);
+  L.bump();
+  return cudaGetLastError();
+}
+
+}  // namespace agpc

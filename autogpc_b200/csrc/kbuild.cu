@@ -1,0 +1,412 @@
+// Pairwise kernel-matrix kernels: K(X, X'), materialised dK/dtheta, and the fused gradient contraction.
+//
+// Stands in for GPy kern.K / kern.update_gradients_full of RBF, StdPeriodic, Bias, Add, Prod (+ the Linear extension)
+// -- SURVEY 8a G1/G2 -- as reached from GPClassification's constructor and optimize() (gpckernel.py:245-246) and
+// from predict (gpckernel.py:832).  Leaf formulas (theta order = gpss2gpy, gpckernel.py:535-565):
+//   SE    k = v exp(-r^2 / 2l^2)                     dk/dv = k/v   dk/dl = k r^2 / l^3
+//   PER   k = v exp(-sin^2(pi r / T) / 2l^2)         dk/dv = k/v   dk/dT = k sin b cos b (b/T) / l^2   dk/dl = k sin^2 b / l^3
+//   LIN   k = v (x - c)(x' - c)                      dk/dv = k/v   dk/dc = -v (x + x' - 2c)
+//   CONST k = v                                      dk/dv = 1
+// A product term is evaluated as (prod of scale factors) * exp(sum of exponents): one exp per term, not per leaf.
+//
+// Layout: one CTA = 32 rows x 128 columns; a warp writes 32 consecutive doubles (256 B) per store, the point
+// coordinates of the tile live in shared memory (dimension-major, so column reads are conflict-free and row reads
+// broadcast).  HBM-write-bound for light programs, FP64-ALU-bound once a term carries sin/cos.
+#include "common.cuh"
+
+namespace agpc {
+
+constexpr int KB_ROWS = 32, KB_COLS = 128, KB_THREADS = 256;
+
+struct LeafConst {
+  int type, dim;
+  double var, a, b, c, d;
+};
+
+struct ProgShared {
+  int n_leaves, n_terms, n_theta;
+  int term_len[AGPC_MAX_TERMS];
+  int term_leaf[AGPC_MAX_TERMS][AGPC_MAX_TERM_LEN];
+  int leaf_off[AGPC_MAX_LEAVES];
+  LeafConst leaf[AGPC_MAX_LEAVES];
+};
+
+__device__ void load_program(ProgShared& P, const agpc_program& g, const double* __restrict__ theta) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    P.n_leaves = g.n_leaves;
+    P.n_terms = g.n_terms;
+    P.n_theta = g.n_theta;
+  }
+  if (tid < AGPC_MAX_TERMS) P.term_len[tid] = g.term_len[tid];
+  if (tid < AGPC_MAX_TERMS * AGPC_MAX_TERM_LEN) (&P.term_leaf[0][0])[tid] = (&g.term_leaf[0][0])[tid];
+  if (tid < AGPC_MAX_LEAVES && tid < g.n_leaves) {
+    LeafConst lc;
+    lc.type = g.leaf_type[tid];
+    lc.dim = g.leaf_dim[tid];
+    const int o = g.leaf_off[tid];
+    P.leaf_off[tid] = o;
+    lc.var = theta[o];
+    lc.a = lc.b = lc.c = lc.d = 0.0;
+    if (lc.type == AGPC_LEAF_SE) {
+      const double l = theta[o + 1];
+      lc.a = 1.0 / (l * l);
+      lc.b = 1.0 / (l * l * l);
+    } else if (lc.type == AGPC_LEAF_PER) {
+      const double T = theta[o + 1], l = theta[o + 2];
+      lc.a = 1.0 / T;
+      lc.b = 1.0 / (l * l);
+      lc.d = 1.0 / (l * l * l);
+    } else if (lc.type == AGPC_LEAF_LIN) {
+      lc.a = theta[o + 1];
+    }
+    P.leaf[tid] = lc;
+  }
+}
+
+// K(x, x') and (GRAD) its partials w.r.t. theta accumulated into dk[0..n_theta) with weight w.
+// xi(d) = xa[d * sa], xj(d) = xb[d * sb].
+template <bool GRAD>
+__device__ __forceinline__ double eval_pair(const ProgShared& P, const double* xa, int sa, const double* xb, int sb,
+                                            double* dk, double w) {
+  double K = 0.0;
+  for (int t = 0; t < P.n_terms; ++t) {
+    const int len = P.term_len[t];
+    double arg = 0.0, mult = 1.0;
+    bool has_exp = false;
+    double sc[AGPC_MAX_TERM_LEN][2];
+    double fac[AGPC_MAX_TERM_LEN];
+    for (int p = 0; p < len; ++p) {
+      const LeafConst& lc = P.leaf[P.term_leaf[t][p]];
+      double f = lc.var;
+      if (lc.type == AGPC_LEAF_SE) {
+        const double r = xa[lc.dim * sa] - xb[lc.dim * sb];
+        arg -= 0.5 * r * r * lc.a;
+        has_exp = true;
+      } else if (lc.type == AGPC_LEAF_PER) {
+        const double r = xa[lc.dim * sa] - xb[lc.dim * sb];
+        double s, c;
+        sincos(M_PI * r * lc.a, &s, &c);  // GPy: np.sin(np.pi * r / T)
+        arg -= 0.5 * s * s * lc.b;
+        has_exp = true;
+        if (GRAD) {
+          sc[p][0] = s;
+          sc[p][1] = c;
+        }
+      } else if (lc.type == AGPC_LEAF_LIN) {
+        f *= (xa[lc.dim * sa] - lc.a) * (xb[lc.dim * sb] - lc.a);
+      }
+      mult *= f;
+      if (GRAD) fac[p] = f;
+    }
+    const double e = has_exp ? exp(arg) : 1.0;
+    const double v = mult * e;
+    K += v;
+    if (GRAD) {
+      const double wv = w * v;
+      for (int p = 0; p < len; ++p) {
+        const int l = P.term_leaf[t][p];
+        const LeafConst& lc = P.leaf[l];
+        const int o = P.leaf_off[l];
+        if (lc.type == AGPC_LEAF_SE) {
+          const double r = xa[lc.dim * sa] - xb[lc.dim * sb];
+          dk[o] += wv / lc.var;
+          dk[o + 1] += wv * r * r * lc.b;
+        } else if (lc.type == AGPC_LEAF_PER) {
+          const double r = xa[lc.dim * sa] - xb[lc.dim * sb];
+          const double s = sc[p][0], c = sc[p][1];
+          const double bb = M_PI * r * lc.a;
+          dk[o] += wv / lc.var;
+          dk[o + 1] += wv * s * c * (bb * lc.a) * lc.b;
+          dk[o + 2] += wv * s * s * lc.d;
+        } else if (lc.type == AGPC_LEAF_LIN) {
+          double excl = e;
+          for (int q = 0; q < len; ++q)
+            if (q != p) excl *= fac[q];
+          const double xi = xa[lc.dim * sa], xj = xb[lc.dim * sb];
+          dk[o] += w * excl * (xi - lc.a) * (xj - lc.a);
+          dk[o + 1] += w * excl * (-lc.var * (xi + xj - 2.0 * lc.a));
+        } else {
+          // CONST: dk/dv = (term without the constant) = v / var
+          dk[o] += wv / lc.var;
+        }
+      }
+    }
+  }
+  return K;
+}
+
+// ---- gather fold rows ------------------------------------------------------------------------------------
+// Xf[b][i][d] = X[rows[off_b + i]][d], yf[b][i] = y[...]; padding rows: x = 0, y = +1.
+__global__ void gather_rows_kernel(const double* __restrict__ X, const double* __restrict__ y,
+                                   const int* __restrict__ rows, const long long* __restrict__ row_off,
+                                   const int* __restrict__ n_of, int D, int np, double* __restrict__ Xf,
+                                   double* __restrict__ yf) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= np) return;
+  const int n = n_of[b];
+  double* xo = Xf + ((long long)b * np + i) * D;
+  if (i < n) {
+    const int r = rows[row_off[b] + i];
+    for (int d = 0; d < D; ++d) xo[d] = X[(long long)r * D + d];
+    yf[(long long)b * np + i] = y[r];
+  } else {
+    for (int d = 0; d < D; ++d) xo[d] = 0.0;
+    yf[(long long)b * np + i] = 1.0;
+  }
+}
+
+// ---- K build ---------------------------------------------------------------------------------------------
+// out[b][i][j] = K(xa_i, xb_j) for i < na, j < nb, zero in the padding; optional kdiag (when xa == xb) and
+// materialised dK slabs dK[b][theta][i][j].
+template <bool GRAD>
+__global__ void __launch_bounds__(KB_THREADS)
+build_K_kernel(const BuildArgs a) {
+  const int b = blockIdx.z;
+  if (a.active != nullptr && a.active[b] == 0) return;
+  extern __shared__ double smem[];
+  __shared__ ProgShared P;
+  const int D = a.D;
+  double* xr = smem;                 // [D][KB_ROWS]
+  double* xc = smem + D * KB_ROWS;   // [D][KB_COLS]
+  const int row0 = blockIdx.y * KB_ROWS, col0 = blockIdx.x * KB_COLS;
+  const int na = a.na_of ? a.na_of[b] : a.na_fixed, nb = a.nb_of ? a.nb_of[b] : a.nb_fixed;
+  load_program(P, a.progs[b], a.theta + (long long)b * a.theta_stride);
+  const double* Xa = a.Xa + (long long)b * a.xa_batch;
+  const double* Xb = a.Xb + (long long)b * a.xb_batch;
+  for (int idx = threadIdx.x; idx < KB_ROWS * D; idx += KB_THREADS) {
+    const int r = idx / D, d = idx % D;
+    xr[d * KB_ROWS + r] = (row0 + r < a.na_pad) ? Xa[(long long)(row0 + r) * D + d] : 0.0;
+  }
+  for (int idx = threadIdx.x; idx < KB_COLS * D; idx += KB_THREADS) {
+    const int c = idx / D, d = idx % D;
+    xc[d * KB_COLS + c] = (col0 + c < a.nb_pad) ? Xb[(long long)(col0 + c) * D + d] : 0.0;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 column lanes x 4 row groups
+  double* out = a.out + (long long)b * a.out_batch;
+  const int n_theta = P.n_theta;
+  for (int rr = ty; rr < KB_ROWS; rr += 4) {
+    const int i = row0 + rr;
+    if (i >= a.na_pad) break;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int cc = tx + 64 * h, j = col0 + cc;
+      if (j >= a.ld) continue;
+      const bool valid = (i < na) && (j < nb);
+      double dk[GRAD ? AGPC_MAX_THETA : 1];
+      if (GRAD)
+        for (int q = 0; q < n_theta; ++q) dk[q] = 0.0;
+      double k = 0.0;
+      if (valid) k = eval_pair<GRAD>(P, xr + rr, KB_ROWS, xc + cc, KB_COLS, dk, 1.0);
+      out[(long long)i * a.ld + j] = k;
+      if (GRAD) {
+        double* dKb = a.dK + (long long)b * n_theta * a.out_batch;
+        for (int q = 0; q < n_theta; ++q) dKb[(long long)q * a.out_batch + (long long)i * a.ld + j] = valid ? dk[q] : 0.0;
+      }
+      if (a.kdiag != nullptr && i == j) a.kdiag[(long long)b * a.na_pad + i] = k;
+    }
+  }
+}
+
+cudaError_t build_K_launch(const Launch& L, const BuildArgs& a, int batch, bool grad) {
+  dim3 grid((unsigned)((a.ld + KB_COLS - 1) / KB_COLS), (unsigned)((a.na_pad + KB_ROWS - 1) / KB_ROWS), batch);
+  const size_t smem = sizeof(double) * a.D * (KB_ROWS + KB_COLS);
+  if (grad)
+    build_K_kernel<true><<<grid, KB_THREADS, smem, L.stream>>>(a);
+  else
+    build_K_kernel<false><<<grid, KB_THREADS, smem, L.stream>>>(a);
+  L.bump();
+  return cudaGetLastError();
+}
+
+cudaError_t gather_rows_launch(const Launch& L, const double* X, const double* y, const int* rows,
+                               const long long* row_off, const int* n_of, int D, int np, int batch, double* Xf,
+                               double* yf) {
+  dim3 grid((np + 255) / 256, batch);
+  gather_rows_kernel<<<grid, 256, 0, L.stream>>>(X, y, rows, row_off, n_of, D, np, Xf, yf);
+  L.bump();
+  return cudaGetLastError();
+}
+
+// ---- B = I + S^1/2 K S^1/2 (lower tiles only) ---------------------------------------------------------------
+__global__ void form_B_kernel(const double* __restrict__ K, const double* __restrict__ s, double* __restrict__ A,
+                              int np, long long stride, const int* __restrict__ active) {
+  const int b = blockIdx.z;
+  if (active != nullptr && active[b] == 0) return;
+  const int ti = blockIdx.y, tj = blockIdx.x;  // 32 x 128 tiles
+  const int row0 = ti * 32, col0 = tj * 128;
+  if (col0 > row0 + 31) return;  // strictly above the diagonal
+  const double* Kb = K + (long long)b * stride;
+  double* Ab = A + (long long)b * stride;
+  const double* sb = s + (long long)b * np;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  for (int rr = ty; rr < 32; rr += 4) {
+    const int i = row0 + rr;
+    const double si = sb[i];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = col0 + tx + 64 * h;
+      const long long o = (long long)i * np + j;
+      double v = si * Kb[o] * sb[j];
+      if (i == j) v += 1.0;
+      Ab[o] = v;
+    }
+  }
+}
+
+cudaError_t form_B_launch(const Launch& L, const double* K, const double* s, double* A, int np, long long stride,
+                          int batch, const int* active) {
+  dim3 grid(np / 128, np / 32, batch);
+  form_B_kernel<<<grid, 256, 0, L.stream>>>(K, s, A, np, stride, active);
+  L.bump();
+  return cudaGetLastError();
+}
+
+// ---- fused gradient contraction ---------------------------------------------------------------------------
+// partial[b][tile][q] = sum over the tile's pairs of  w_ik * dK_ik/dtheta_q, where
+//   mode 0 (EP):   w_ik = c_ik * 1/2 (alpha_i alpha_k - s_i Binv_ik s_k), lower triangle, c = 2 off-diagonal, 1 on it
+//   mode 1 (raw):  w_ik = G_ik (full matrix)
+constexpr int GT = 64;  // gradient tile edge
+
+__global__ void __launch_bounds__(256)
+grad_contract_kernel(const GradArgs a) {
+  const int b = blockIdx.y;
+  if (a.active != nullptr && a.active[b] == 0) return;
+  __shared__ ProgShared P;
+  extern __shared__ double smem[];
+  const int D = a.D;
+  double* xr = smem;             // [D][GT]
+  double* xc = smem + D * GT;    // [D][GT]
+  double* red = xc + D * GT;     // [8 warps][AGPC_MAX_THETA]
+  const int nt = a.np / GT;
+  int ti, tj;
+  if (a.mode == 0) {
+    const int t = blockIdx.x;
+    ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while (ti * (ti + 1) / 2 > t) --ti;
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    tj = t - ti * (ti + 1) / 2;
+  } else {
+    ti = blockIdx.x / nt;
+    tj = blockIdx.x % nt;
+  }
+  const int n = a.n_of ? a.n_of[b] : a.n_fixed;
+  load_program(P, a.progs[b], a.theta + (long long)b * a.theta_stride);
+  const double* Xf = a.Xf + (long long)b * a.np * D;
+  const int row0 = ti * GT, col0 = tj * GT;
+  for (int idx = threadIdx.x; idx < GT * D; idx += 256) {
+    const int r = idx / D, d = idx % D;
+    xr[d * GT + r] = Xf[(long long)(row0 + r) * D + d];
+    xc[d * GT + r] = Xf[(long long)(col0 + r) * D + d];
+  }
+  __syncthreads();
+  const int n_theta = P.n_theta;
+  double acc[AGPC_MAX_THETA];
+  for (int q = 0; q < n_theta; ++q) acc[q] = 0.0;
+  const double* Gb = a.G + (long long)b * a.g_batch;
+  const double* al = a.alpha ? a.alpha + (long long)b * a.np : nullptr;
+  const double* sv = a.s ? a.s + (long long)b * a.np : nullptr;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int j = col0 + tx;
+  for (int rr = ty; rr < GT; rr += 4) {
+    const int i = row0 + rr;
+    if (i >= n || j >= n) continue;
+    double w;
+    if (a.mode == 0) {
+      if (j > i) continue;
+      const double g = Gb[(long long)i * a.ld + j];
+      w = 0.5 * (al[i] * al[j] - sv[i] * g * sv[j]);
+      if (j < i) w *= 2.0;
+    } else {
+      w = Gb[(long long)i * a.ld + j];
+    }
+    eval_pair<true>(P, xr + rr, GT, xc + tx, GT, acc, w);
+  }
+  // deterministic block reduction: shuffle within warps, fixed-order sum across the 8 warps
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int q = 0; q < n_theta; ++q) {
+    double v = acc[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp * AGPC_MAX_THETA + q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < n_theta) {
+    double v = 0.0;
+    for (int w8 = 0; w8 < 8; ++w8) v += red[w8 * AGPC_MAX_THETA + threadIdx.x];
+    a.partial[((long long)b * a.tiles_per_item + blockIdx.x) * AGPC_MAX_THETA + threadIdx.x] = v;
+  }
+}
+
+// grad[b][q] = scale * sum_tiles partial[b][tile][q]   (one warp per (b, q), fixed summation order)
+__global__ void grad_finalize_kernel(const double* __restrict__ partial, int tiles, const agpc_program* progs,
+                                     double scale, double* __restrict__ grad, int grad_stride,
+                                     const int* __restrict__ active) {
+  const int b = blockIdx.x;
+  if (active != nullptr && active[b] == 0) return;
+  const int q = blockIdx.y, lane = threadIdx.x & 31;
+  if (q >= progs[b].n_theta) return;
+  double v = 0.0;
+  for (int t = lane; t < tiles; t += 32) v += partial[((long long)b * tiles + t) * AGPC_MAX_THETA + q];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) grad[(long long)b * grad_stride + q] = scale * v;
+}
+
+cudaError_t grad_contract_launch(const Launch& L, const GradArgs& a, int batch, double scale, double* grad,
+                                 int grad_stride) {
+  const int nt = a.np / GT;
+  const int tiles = a.mode == 0 ? nt * (nt + 1) / 2 : nt * nt;
+  const size_t smem = sizeof(double) * (2 * a.D * GT + 8 * AGPC_MAX_THETA);
+  dim3 grid(tiles, batch);
+  grad_contract_kernel<<<grid, 256, smem, L.stream>>>(a);
+  L.bump();
+  AGPC_CUDA_TRY(cudaGetLastError());
+  grad_finalize_kernel<<<dim3(batch, AGPC_MAX_THETA), 32, 0, L.stream>>>(a.partial, tiles, a.progs, scale, grad, grad_stride,
+                                                                     a.active);
+  L.bump();
+  return cudaGetLastError();
+}
+
+// ---- k(x*, x*) per test point, and column scaling Ks[:, k] *= s_k --------------------------------------------
+__global__ void kself_kernel(const agpc_program* __restrict__ progs, const double* __restrict__ theta,
+                             int theta_stride, const double* __restrict__ Xs, int m_pad, int D,
+                             const int* __restrict__ m_of, double* __restrict__ kss) {
+  const int b = blockIdx.y;
+  __shared__ ProgShared P;
+  load_program(P, progs[b], theta + (long long)b * theta_stride);
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m_pad) return;
+  const double* x = Xs + ((long long)b * m_pad + i) * D;
+  double dummy[1];
+  kss[(long long)b * m_pad + i] = (i < m_of[b]) ? eval_pair<false>(P, x, 1, x, 1, dummy, 0.0) : 0.0;
+}
+cudaError_t kself_launch(const Launch& L, const agpc_program* progs, const double* theta, int theta_stride,
+                         const double* Xs, int m_pad, int D, const int* m_of, int batch, double* kss) {
+  dim3 grid((m_pad + 255) / 256, batch);
+  kself_kernel<<<grid, 256, 0, L.stream>>>(progs, theta, theta_stride, Xs, m_pad, D, m_of, kss);
+  L.bump();
+  return cudaGetLastError();
+}
+__global__ void scale_cols_kernel(double* __restrict__ Ks, const double* __restrict__ s, int rows, int np) {
+  const int b = blockIdx.z;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= np || i >= rows) return;
+  Ks[((long long)b * rows + i) * np + j] *= s[(long long)b * np + j];
+}
+cudaError_t scale_cols_launch(const Launch& L, double* Ks, const double* s, int rows, int np, int batch) {
+  dim3 grid((np + 255) / 256, rows, batch);
+  scale_cols_kernel<<<grid, 256, 0, L.stream>>>(Ks, s, rows, np);
+  L.bump();
+  return cudaGetLastError();
+}
+
+int grad_tiles(int np, int mode) {
+  const int nt = np / GT;
+  return mode == 0 ? nt * (nt + 1) / 2 : nt * nt;
+}
+
+}  // namespace agpc
