@@ -85,6 +85,7 @@ int agpc_destroy(agpc_ctx* ctx) {
   }
   if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->scratch) cudaFree(ctx->scratch);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return AGPC_OK;
@@ -181,6 +182,70 @@ int agpc_potrf(agpc_ctx* ctx, double* A, int32_t n, int32_t batch, double* Minv,
   if (info) CK(ctx, cudaMemsetAsync(info, 0, sizeof(int32_t) * batch, L.stream));
   CK(ctx, potrf_blocked(L, ms, nullptr, info));
   if (want_inv) CK(ctx, trtri_blocked(L, ms, nullptr));
+  return AGPC_OK;
+}
+
+
+// small persistent device scratch for a program + theta (building-block entry points)
+static int param_scratch(agpc_ctx* ctx, const agpc_program* prog, const double* theta_host, cudaStream_t st,
+                         agpc_program** d_prog, double** d_theta) {
+  if (!ctx->scratch) {
+    if (cudaMalloc(&ctx->scratch, 1 << 16) != cudaSuccess) return fail(ctx, AGPC_E_NOMEM, "scratch cudaMalloc");
+  }
+  *d_prog = (agpc_program*)ctx->scratch;
+  *d_theta = (double*)((char*)ctx->scratch + 4096);
+  if (prog->n_theta <= 0 || prog->n_theta > AGPC_MAX_THETA || prog->n_leaves <= 0 || prog->n_leaves > AGPC_MAX_LEAVES ||
+      prog->n_terms <= 0 || prog->n_terms > AGPC_MAX_TERMS)
+    return fail(ctx, AGPC_E_ARG, "malformed kernel program");
+  CK(ctx, cudaMemcpyAsync(*d_prog, prog, sizeof(agpc_program), cudaMemcpyHostToDevice, st));
+  CK(ctx, cudaMemcpyAsync(*d_theta, theta_host, sizeof(double) * prog->n_theta, cudaMemcpyHostToDevice, st));
+  return AGPC_OK;
+}
+
+int agpc_build_K(agpc_ctx* ctx, const agpc_program* program, const double* theta_host, const double* X_dev, int32_t n,
+                 int32_t D, double* K_dev, double* dK_dev, int64_t ld, void* stream) {
+  if (!ctx || !program || !theta_host || !X_dev || !K_dev || n <= 0 || D <= 0 || ld < n || (ld & 1))
+    return fail(ctx, AGPC_E_ARG, "build_K: bad argument (ld must be even and >= n)");
+  CK(ctx, cudaSetDevice(ctx->device));
+  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches};
+  agpc_program* d_prog;
+  double* d_theta;
+  int rc = param_scratch(ctx, program, theta_host, L.stream, &d_prog, &d_theta);
+  if (rc) return rc;
+  BuildArgs a{};
+  a.progs = d_prog; a.theta = d_theta; a.theta_stride = AGPC_MAX_THETA;
+  a.Xa = X_dev; a.Xb = X_dev; a.na_fixed = n; a.nb_fixed = n; a.na_pad = n; a.nb_pad = n; a.D = D;
+  a.out = K_dev; a.ld = ld; a.out_batch = (long long)n * ld; a.dK = dK_dev;
+  CK(ctx, build_K_launch(L, a, 1, dK_dev != nullptr));
+  return AGPC_OK;
+}
+
+int agpc_kernel_grad(agpc_ctx* ctx, const agpc_program* program, const double* theta_host, const double* X_dev,
+                     int32_t n, int32_t D, const double* G_dev, int64_t ld, double* grad_host, void* stream) {
+  if (!ctx || !program || !theta_host || !X_dev || !G_dev || !grad_host || n <= 0 || D <= 0 || ld < n)
+    return fail(ctx, AGPC_E_ARG, "kernel_grad: bad argument");
+  CK(ctx, cudaSetDevice(ctx->device));
+  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches};
+  agpc_program* d_prog;
+  double* d_theta;
+  int rc = param_scratch(ctx, program, theta_host, L.stream, &d_prog, &d_theta);
+  if (rc) return rc;
+  const int np = (n + 63) / 64 * 64;
+  const int tiles = grad_tiles(np, 1);
+  const size_t need = sizeof(double) * ((size_t)np * D + (size_t)tiles * AGPC_MAX_THETA + AGPC_MAX_THETA) + 8192;
+  rc = ctx->ensure_arena(need);
+  if (rc) return rc;
+  double* Xp = (double*)ctx->arena;
+  double* partial = Xp + (((size_t)np * D + 127) / 128) * 128;
+  double* g_dev = partial + (size_t)tiles * AGPC_MAX_THETA;
+  CK(ctx, cudaMemsetAsync(Xp, 0, sizeof(double) * (size_t)np * D, L.stream));
+  CK(ctx, cudaMemcpyAsync(Xp, X_dev, sizeof(double) * (size_t)n * D, cudaMemcpyDeviceToDevice, L.stream));
+  GradArgs ga{};
+  ga.progs = d_prog; ga.theta = d_theta; ga.theta_stride = AGPC_MAX_THETA; ga.Xf = Xp; ga.n_fixed = n; ga.np = np; ga.D = D;
+  ga.G = G_dev; ga.ld = ld; ga.g_batch = 0; ga.mode = 1; ga.partial = partial; ga.tiles_per_item = tiles;
+  CK(ctx, grad_contract_launch(L, ga, 1, 1.0, g_dev, AGPC_MAX_THETA));
+  CK(ctx, cudaMemcpyAsync(grad_host, g_dev, sizeof(double) * program->n_theta, cudaMemcpyDeviceToHost, L.stream));
+  CK(ctx, cudaStreamSynchronize(L.stream));
   return AGPC_OK;
 }
 

@@ -112,6 +112,8 @@ cudaError_t scale_cols_launch(const Launch& L, double* Ks, const double* s, int 
 cudaError_t grad_contract_launch(const Launch& L, const GradArgs& a, int batch, double scale, double* grad,
                                  int grad_stride);
 int grad_tiles(int np, int mode);
+cudaError_t dmu_dx_launch(const Launch& L, const agpc_program* prog, const double* theta, const double* Xs, int m,
+                          const double* Xf, int n, int D, const double* alpha, double* out);
 
 // ep.cu
 cudaError_t rowdot_launch(const Launch& L, int range, bool sq, const double* A, const double* x, double* y,

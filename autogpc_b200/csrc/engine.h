@@ -22,6 +22,7 @@ struct agpc_ctx {
   size_t limit = 0;
   void* pinned = nullptr;  // small pinned staging buffer for per-sweep flags
   size_t pinned_bytes = 0;
+  void* scratch = nullptr;  // 64 KB device scratch: program + theta of the building-block entry points
   std::vector<Dataset> datasets;
 
   int ensure_arena(size_t bytes);

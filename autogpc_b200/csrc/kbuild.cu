@@ -404,6 +404,80 @@ cudaError_t scale_cols_launch(const Launch& L, double* Ks, const double* s, int 
   return cudaGetLastError();
 }
 
+// ---- d mu*/d x* = sum_i alpha_i dk(x*, x_i)/dx*  (m.predictive_gradients, gpckernel.py:431) ---------------------
+// dk/dx for a product term v = prod f_l * exp(arg):  SE: -v r / l^2;  PER: -v sin b cos b (pi/T) / l^2;
+// LIN: (v without the leaf) * var (x' - c);  CONST: 0.  One warp per test point.
+constexpr int MAX_D = 32;
+__device__ __forceinline__ void eval_pair_dx(const ProgShared& P, const double* xa, const double* xb, double w,
+                                             double* gx) {
+  for (int t = 0; t < P.n_terms; ++t) {
+    const int len = P.term_len[t];
+    double arg = 0.0, mult = 1.0;
+    double fac[AGPC_MAX_TERM_LEN], dlog[AGPC_MAX_TERM_LEN];
+    for (int p = 0; p < len; ++p) {
+      const LeafConst& lc = P.leaf[P.term_leaf[t][p]];
+      double f = lc.var, dl = 0.0;
+      if (lc.type == AGPC_LEAF_SE) {
+        const double r = xa[lc.dim] - xb[lc.dim];
+        arg -= 0.5 * r * r * lc.a;
+        dl = -r * lc.a;
+      } else if (lc.type == AGPC_LEAF_PER) {
+        const double r = xa[lc.dim] - xb[lc.dim];
+        double s, c;
+        sincos(M_PI * r * lc.a, &s, &c);
+        arg -= 0.5 * s * s * lc.b;
+        dl = -s * c * (M_PI * lc.a) * lc.b;
+      } else if (lc.type == AGPC_LEAF_LIN) {
+        f *= (xa[lc.dim] - lc.a) * (xb[lc.dim] - lc.a);
+      }
+      mult *= f;
+      fac[p] = f;
+      dlog[p] = dl;
+    }
+    const double e = exp(arg);
+    const double v = mult * e;
+    for (int p = 0; p < len; ++p) {
+      const LeafConst& lc = P.leaf[P.term_leaf[t][p]];
+      if (lc.type == AGPC_LEAF_SE || lc.type == AGPC_LEAF_PER) {
+        gx[lc.dim] += w * v * dlog[p];
+      } else if (lc.type == AGPC_LEAF_LIN) {
+        double excl = e;
+        for (int q = 0; q < len; ++q)
+          if (q != p) excl *= fac[q];
+        gx[lc.dim] += w * excl * lc.var * (xb[lc.dim] - lc.a);
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(256)
+dmu_dx_kernel(const agpc_program* __restrict__ prog, const double* __restrict__ theta, const double* __restrict__ Xs,
+              int m, const double* __restrict__ Xf, int n, int D, const double* __restrict__ alpha,
+              double* __restrict__ out) {
+  __shared__ ProgShared P;
+  load_program(P, *prog, theta);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + warp;
+  if (j >= m) return;
+  double gx[MAX_D];
+  for (int d = 0; d < D; ++d) gx[d] = 0.0;
+  const double* xa = Xs + (long long)j * D;
+  for (int i = lane; i < n; i += 32) eval_pair_dx(P, xa, Xf + (long long)i * D, alpha[i], gx);
+  for (int d = 0; d < D; ++d) {
+    double v = gx[d];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) out[(long long)j * D + d] = v;
+  }
+}
+cudaError_t dmu_dx_launch(const Launch& L, const agpc_program* prog, const double* theta, const double* Xs, int m,
+                          const double* Xf, int n, int D, const double* alpha, double* out) {
+  if (D > MAX_D) return cudaErrorInvalidValue;
+  dmu_dx_kernel<<<(m + 7) / 8, 256, 0, L.stream>>>(prog, theta, Xs, m, Xf, n, D, alpha, out);
+  L.bump();
+  return cudaGetLastError();
+}
+
 int grad_tiles(int np, int mode) {
   const int nt = np / GT;
   return mode == 0 ? nt * (nt + 1) / 2 : nt * nt;

@@ -382,15 +382,17 @@ int agpc_score_batch(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, const a
 }
 
 
-int agpc_predict_batch(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, const agpc_program* programs,
-                       const double* theta, int32_t theta_stride, const int32_t* rows, const int64_t* row_off,
-                       const double* tau, const double* nu, int32_t site_stride, const int32_t* test_rows,
-                       const int64_t* test_off, double* p_out, double* mu_out, double* var_out, int32_t* status) {
+static int predict_impl(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, const agpc_program* programs,
+                        const double* theta, int32_t theta_stride, const int32_t* rows, const int64_t* row_off,
+                        const double* tau, const double* nu, int32_t site_stride, const int32_t* test_rows,
+                        const int64_t* test_off, const double* Xstar_host, double* p_out, double* mu_out,
+                        double* var_out, int32_t* status, double* dmu_dx) {
   if (!ctx) return AGPC_E_ARG;
   if (dataset_id < 0 || dataset_id >= (int)ctx->datasets.size() || !ctx->datasets[dataset_id].X)
     return fail(ctx, AGPC_E_ARG, "predict_batch: bad dataset id");
-  if (n_items <= 0 || !programs || !theta || !rows || !row_off || !tau || !nu || !test_rows || !test_off || !p_out)
-    return fail(ctx, AGPC_E_ARG, "predict_batch: null argument");
+  if (n_items <= 0 || !programs || !theta || !rows || !row_off || !tau || !nu || (!test_rows && !Xstar_host) || !test_off || !p_out)
+    return fail(ctx, AGPC_E_ARG, "predict: null argument");
+  if (Xstar_host && n_items != 1) return fail(ctx, AGPC_E_ARG, "predict_points: one item only");
   const Dataset& ds = ctx->datasets[dataset_id];
   CK(cudaSetDevice(ctx->device));
   Launch L{ctx->stream, &ctx->launches};
@@ -458,11 +460,16 @@ int agpc_predict_batch(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, const
     CK(cudaMemcpyAsync(c.progs, programs + first, sizeof(agpc_program) * nb, cudaMemcpyHostToDevice, L.stream));
     CK(cudaMemcpyAsync(c.theta, theta + (size_t)first * theta_stride, sizeof(double) * (size_t)nb * theta_stride, cudaMemcpyHostToDevice, L.stream));
     CK(cudaMemcpyAsync(c.rows, rows + row_off[first], sizeof(int) * nrows_chunk, cudaMemcpyHostToDevice, L.stream));
-    CK(cudaMemcpyAsync(trows, test_rows + test_off[first], sizeof(int) * ntest_chunk, cudaMemcpyHostToDevice, L.stream));
+    if (!Xstar_host) CK(cudaMemcpyAsync(trows, test_rows + test_off[first], sizeof(int) * ntest_chunk, cudaMemcpyHostToDevice, L.stream));
     CK(cudaMemsetAsync(c.status, 0, sizeof(int) * nb, L.stream));
     CK(cudaMemsetAsync(c.info, 0, sizeof(int) * nb, L.stream));
     CK(gather_rows_launch(L, ds.X, ds.y, c.rows, c.row_off, c.n_of, ds.D, np, nb, c.Xf, c.yf));
-    CK(gather_rows_launch(L, ds.X, ds.y, trows, toff_dev, m_dev, ds.D, mp, nb, Xs, ys));
+    if (!Xstar_host) {
+      CK(gather_rows_launch(L, ds.X, ds.y, trows, toff_dev, m_dev, ds.D, mp, nb, Xs, ys));
+    } else {
+      CK(cudaMemsetAsync(Xs, 0, sizeof(double) * (size_t)mp * ds.D, L.stream));
+      CK(cudaMemcpyAsync(Xs, Xstar_host, sizeof(double) * (size_t)m_of[0] * ds.D, cudaMemcpyHostToDevice, L.stream));
+    }
     BuildArgs ba{};
     ba.progs = c.progs; ba.theta = c.theta; ba.theta_stride = theta_stride;
     ba.Xa = c.Xf; ba.Xb = c.Xf; ba.na_of = c.n_of; ba.nb_of = c.n_of;
@@ -495,6 +502,11 @@ int agpc_predict_batch(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, const
     CK(gemm_nt_launch(L, mapKs, c.ms.mapM, g, g.m_tiles * g.n_tiles, 1, nb));
     CK(rowdot_launch(L, 0, true, V, c.alpha, pbuf /*unused dot*/, vsq, mp, np, (long long)mp * np, np, mp, nb, nullptr));
     CK(predict_prob_launch(L, mu_s, kss, vsq, pbuf, varbuf, (long long)nb * mp));
+    if (dmu_dx) {
+      // V is free again: use it as the m x D output buffer
+      CK(dmu_dx_launch(L, c.progs, c.theta, Xs, m_of[0], c.Xf, n_of[0], ds.D, c.alpha, V));
+      CK(cudaMemcpyAsync(dmu_dx, V, sizeof(double) * (size_t)m_of[0] * ds.D, cudaMemcpyDeviceToHost, L.stream));
+    }
     CK(cudaStreamSynchronize(L.stream));
     for (int b = 0; b < nb; ++b) {
       const size_t o = (size_t)test_off[first + b];
@@ -506,6 +518,28 @@ int agpc_predict_batch(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, const
     CK(cudaStreamSynchronize(L.stream));
   }
   return AGPC_OK;
+}
+
+int agpc_predict_batch(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, const agpc_program* programs,
+                       const double* theta, int32_t theta_stride, const int32_t* rows, const int64_t* row_off,
+                       const double* tau, const double* nu, int32_t site_stride, const int32_t* test_rows,
+                       const int64_t* test_off, double* p_out, double* mu_out, double* var_out, int32_t* status) {
+  if (!test_rows) return ctx ? fail(ctx, AGPC_E_ARG, "predict_batch: null test_rows") : AGPC_E_ARG;
+  return predict_impl(ctx, dataset_id, n_items, programs, theta, theta_stride, rows, row_off, tau, nu, site_stride,
+                      test_rows, test_off, nullptr, p_out, mu_out, var_out, status, nullptr);
+}
+
+int agpc_predict_points(agpc_ctx* ctx, int32_t dataset_id, const agpc_program* program, const double* theta,
+                        const int32_t* rows, int32_t n_rows, const double* tau, const double* nu,
+                        const double* Xstar_host, int32_t m, double* p_out, double* mu_out, double* var_out,
+                        double* dmu_dx) {
+  if (!ctx) return AGPC_E_ARG;
+  if (!program || !Xstar_host || m <= 0 || n_rows <= 0) return fail(ctx, AGPC_E_ARG, "predict_points: bad argument");
+  const int64_t row_off[2] = {0, n_rows};
+  const int64_t test_off[2] = {0, m};
+  int32_t status = 0;
+  return predict_impl(ctx, dataset_id, 1, program, theta, program->n_theta, rows, row_off, tau, nu, n_rows, nullptr,
+                      test_off, Xstar_host, p_out, mu_out, var_out, &status, dmu_dx);
 }
 
 }  // extern "C"

@@ -223,3 +223,62 @@ class Engine:
         if want_latent:
             return split(p), split(mu), split(var), status
         return split(p), status
+
+    def predict_points(self, dataset: int, program: Program, theta, rows, tau, nu, Xstar, want_gradients: bool = False):
+        """(p*, mu*, var*[, d mu*/d x*]) at arbitrary points Xstar (m x D) for one item trained on ``rows``."""
+        Xs = np.ascontiguousarray(Xstar, dtype=np.float64)
+        m, D = Xs.shape
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        tau = np.ascontiguousarray(tau, dtype=np.float64)
+        nu = np.ascontiguousarray(nu, dtype=np.float64)
+        p, mu, var = np.zeros(m), np.zeros(m), np.zeros(m)
+        g = np.zeros((m, D)) if want_gradients else None
+        self._check(self._L.agpc_predict_points(self._ctx, int(dataset), C.byref(program), _dp(th), _ip(rows), len(rows),
+                                                _dp(tau), _dp(nu), _dp(Xs), m, _dp(p), _dp(mu), _dp(var), _dp(g)))
+        return (p, mu, var, g) if want_gradients else (p, mu, var)
+
+    # ---- building blocks on device tensors (micro-benchmarks, unit parity tests) ----
+    def build_K(self, program: Program, theta, X_dev_ptr: int, n: int, D: int, K_dev_ptr: int, ld: int,
+                dK_dev_ptr: int = 0, stream: int = 0):
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        self._check(self._L.agpc_build_K(self._ctx, C.byref(program), _dp(th), C.c_void_p(X_dev_ptr), n, D,
+                                         C.c_void_p(K_dev_ptr), C.c_void_p(dK_dev_ptr) if dK_dev_ptr else None,
+                                         C.c_int64(ld), C.c_void_p(stream) if stream else None))
+
+    def kernel_grad(self, program: Program, theta, X_dev_ptr: int, n: int, D: int, G_dev_ptr: int, ld: int):
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        out = np.zeros(program.n_theta)
+        self._check(self._L.agpc_kernel_grad(self._ctx, C.byref(program), _dp(th), C.c_void_p(X_dev_ptr), n, D,
+                                             C.c_void_p(G_dev_ptr), C.c_int64(ld), _dp(out), None))
+        return out
+
+    def potrf(self, A_dev_ptr: int, n: int, batch: int = 1, Minv_ptr: int = 0, Uinv_ptr: int = 0, info_ptr: int = 0,
+              stream: int = 0):
+        self._check(self._L.agpc_potrf(self._ctx, C.c_void_p(A_dev_ptr), n, batch,
+                                       C.c_void_p(Minv_ptr) if Minv_ptr else None,
+                                       C.c_void_p(Uinv_ptr) if Uinv_ptr else None,
+                                       C.c_void_p(info_ptr) if info_ptr else None,
+                                       C.c_void_p(stream) if stream else None))
+
+    def gemm_nt(self, A_ptr: int, B_ptr: int, C_ptr: int, M: int, N: int, K: int, alpha=1.0, beta=0.0, batch=1,
+                stream: int = 0):
+        self._check(self._L.agpc_gemm_nt(self._ctx, C.c_void_p(A_ptr), C.c_void_p(B_ptr), C.c_void_p(C_ptr), M, N, K,
+                                         C.c_double(alpha), C.c_double(beta), batch,
+                                         C.c_void_p(stream) if stream else None))
+
+
+_default: Optional[Engine] = None
+
+
+def default_engine() -> Engine:
+    """Process-wide engine on this rank's GPU (LOCAL_RANK under torchrun, else device 0)."""
+    global _default
+    if _default is None:
+        _default = Engine(int(os.environ.get("LOCAL_RANK", "0")))
+    return _default
+
+
+def set_default_engine(e) -> None:
+    global _default
+    _default = e

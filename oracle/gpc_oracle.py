@@ -310,7 +310,8 @@ def ep_sequential(K, y, eps=1e-6, max_sweeps=100, rng: Optional[np.random.Genera
     return EPResult(tau_t, v_t, it, not (tau_diff > eps or v_diff > eps), jit_used)
 
 
-TAU_FLOOR = 1e-300   # probit sites have tau~ > 0 in exact arithmetic; the floor only guards rounding to <= 0
+TAU_FLOOR_REL = 1e-10   # tau~_i >= 1e-10 / K_ii: probit sites are > 0 in exact arithmetic; the floor keeps the
+                        # device's diag(Sigma)_i = (1 - (B^-1)_ii) / tau~_i well defined (effect on log Z < 1e-10 / site)
 
 
 def ep_parallel(K, y, eps=1e-6, max_sweeps=100, damping=1.0, tau0=None, v0=None):
@@ -334,7 +335,7 @@ def ep_parallel(K, y, eps=1e-6, max_sweeps=100, damping=1.0, tau0=None, v0=None)
         _, mu_hat, s2_hat, _ = moments_match(ypm, tau_cav, v_cav)
         d_tau = damping * (1.0 / s2_hat - 1.0 / sig)
         d_v = damping * (mu_hat / s2_hat - mu / sig)
-        new_tau = np.maximum(tau_t + d_tau, TAU_FLOOR)
+        new_tau = np.maximum(tau_t + d_tau, TAU_FLOOR_REL / np.diag(K))
         d_tau = new_tau - tau_t
         tau_t, v_t = new_tau, v_t + d_v
         it += 1

@@ -1,0 +1,163 @@
+"""Host-side structure tests (CPU): the reference's only assertions (gpckerneltest.py:84-107) plus the shapes its
+print-driven scripts exercise (gpss2gpy / gpy2gpss / expand), ported to asserts."""
+import numpy as np
+import pytest
+
+from autogpc_b200 import flexible_function as ff
+from autogpc_b200 import gpckernel, grammar
+from autogpc_b200 import gpy_compat as GPy
+from autogpc_b200.gpcdata import GPCData
+from tests.util import synth
+
+
+@pytest.fixture()
+def data():
+    X, y = synth(60, 3, 1)
+    return GPCData(X, y.reshape(-1, 1))
+
+
+def test_is_kernel_equal_truth_table():
+    # gpckerneltest.py:86-107, assertion for assertion
+    k1, k2 = ff.NoneKernel(), ff.NoneKernel()
+    assert gpckernel.isKernelEqual(k1, k2)
+    k2 = ff.SqExpKernel(dimension=0, lengthscale=1.5, sf=0.5)
+    assert not gpckernel.isKernelEqual(k1, k2)
+    k1 = ff.SqExpKernel(dimension=0, lengthscale=1, sf=0.5)
+    assert gpckernel.isKernelEqual(k1, k2)
+    assert not gpckernel.isKernelEqual(k1, k2, compare_params=True)
+    assert gpckernel.isKernelEqual(k1, k1.copy(), compare_params=True)
+    k2 = ff.SqExpKernel(dimension=1, lengthscale=1, sf=0.5)
+    assert not gpckernel.isKernelEqual(k1, k2)
+    k1 = ff.SqExpKernel(dimension=0, lengthscale=1, sf=0.5)
+    k2 = ff.SqExpKernel(dimension=1, lengthscale=1, sf=0.5)
+    k3, k4 = ff.SumKernel([k1, k2]), ff.SumKernel([k2, k1])
+    assert gpckernel.isKernelEqual(k3, k4)
+    k4 = ff.SumKernel([k1, k1])
+    assert not gpckernel.isKernelEqual(k3, k4)
+
+
+def test_gpss2gpy_shapes_and_bounds(data):
+    # gpckerneltest.py:32-56 / gpckernel.py:535-565
+    se = gpckernel.gpss2gpy(ff.SqExpKernel(dimension=1, lengthscale=1.5, sf=0.5), data=data)
+    assert isinstance(se, GPy.kern.RBF) and list(se.active_dims) == [1]
+    assert se.variance[0] == pytest.approx(0.25) and se.lengthscale[0] == pytest.approx(1.5)
+    lo, hi = np.ravel(data.getLengthscaleBounds(dims=1))
+    assert se["lengthscale"].kind == "bounded" and (se["lengthscale"].lo, se["lengthscale"].hi) == (lo, hi)
+    per = gpckernel.gpss2gpy(ff.PeriodicKernel(dimension=0, lengthscale=5, period=4, sf=1.5), data=data)
+    assert [p.name for p in per.parameters] == ["variance", "period", "lengthscale"]
+    assert per["period"].kind == "bounded" and per["lengthscale"].kind == "bounded"
+    c = gpckernel.gpss2gpy(ff.ConstKernel(sf=2.0), data=data)
+    assert isinstance(c, GPy.kern.Bias) and list(c.active_dims) == [0, 1, 2] and c.variance[0] == 4.0
+    s = gpckernel.gpss2gpy(ff.SumKernel([ff.SqExpKernel(0, 1.0, 1.0), ff.PeriodicKernel(2, 1.0, 1.0, 1.0)]), data=data)
+    assert isinstance(s, GPy.kern.Add) and list(s.active_dims) == [0, 2]
+    p = gpckernel.gpss2gpy(ff.ProductKernel([ff.SqExpKernel(0, 1.0, 1.0), s_ := ff.SqExpKernel(1, 1.0, 1.0)]), data=data)
+    assert isinstance(p, GPy.kern.Prod) and len(p.parts) == 2
+    with pytest.raises(NotImplementedError):
+        gpckernel.gpss2gpy(ff.NoneKernel(), data=data)
+
+
+def test_gpy2gpss_roundtrip(data):
+    # gpckerneltest.py:58-69
+    kk = GPy.kern.Add([GPy.kern.RBF(1, variance=2, lengthscale=3, active_dims=np.array([3])),
+                       GPy.kern.RBF(1, variance=4, lengthscale=6, active_dims=np.array([1]))])
+    g = gpckernel.gpy2gpss(kk)
+    assert isinstance(g, ff.SumKernel)
+    assert (g.operands[0].dimension, g.operands[0].lengthscale, g.operands[0].sf) == (3, 3.0, pytest.approx(np.sqrt(2)))
+    c = gpckernel.gpy2gpss(GPy.kern.Bias(3, variance=3, active_dims=np.array([0, 1, 2])))
+    assert isinstance(c, ff.ConstKernel) and c.sf == pytest.approx(np.sqrt(3))
+    k = ff.ProductKernel([ff.SqExpKernel(0, 1.25, 0.5), ff.SumKernel([ff.PeriodicKernel(1, 0.5, 2.0, 1.5), ff.ConstKernel(2.0)])])
+    back = gpckernel.gpy2gpss(gpckernel.gpss2gpy(k, data=data))
+    assert gpckernel.isKernelEqual(k, back, compare_params=False)
+    assert np.allclose(back.param_vector, k.param_vector)
+
+
+def test_expand_se0_in_2d():
+    # gpckerneltest.py:71-77: expected set from grammar.py:20-21 after canonical + simplified
+    X, y = synth(40, 2, 0)
+    d = GPCData(X, y.reshape(-1, 1))
+    ks = gpckernel.GPCKernel(ff.SqExpKernel(dimension=0, lengthscale=1.5, sf=0.5), d, 1).expand()
+    assert sorted(k.kernel.structure() for k in ks) == ["SE0", "SE0*SE1", "SE0+SE0", "SE0+SE1"]
+    assert all(k.depth == 2 and k.parent is not None for k in ks)
+
+
+def test_grammar_counts_d8_three_bases():
+    # depth-0 = 24 (NoneKernel + B and NoneKernel x B both canonicalise to B), 48 raw
+    g = grammar.MultiDGrammar(8, "SE,Lin,Per")
+    raw = grammar.expand(ff.NoneKernel(), g)
+    assert len(raw) == 48
+    uniq = [k for k in ff.remove_duplicates([k.canonical() for k in raw]) if not isinstance(k, ff.NoneKernel)]
+    assert len(uniq) == 24
+    raw1 = grammar.expand(ff.SqExpKernel(0, 1.0, 1.0), g)
+    assert len(raw1) == 48
+
+
+def test_canonical_additive_and_peff():
+    a, b, c = ff.SqExpKernel(0, 1.0, 1.0), ff.SqExpKernel(1, 1.0, 1.0), ff.PeriodicKernel(2, 1.0, 1.0, 1.0)
+    k = ff.ProductKernel([a, ff.SumKernel([b, c])])
+    assert k.effective_params == 2 + (2 + 3) - 1                           # flexible_function.py:1647
+    add = k.additive_form()
+    assert isinstance(add, ff.SumKernel) and sorted(o.structure() for o in add.operands) == ["Per2*SE0", "SE0*SE1"]
+    nested = ff.SumKernel([ff.SumKernel([b, a]), ff.NoneKernel(), c])
+    assert nested.canonical().structure() == "Per2+SE0+SE1"
+    assert ff.SumKernel([ff.NoneKernel()]).canonical().structure() == "None"
+    # SE x SE on one dimension collapses; constants fold into the first factor
+    prod = ff.ProductKernel([ff.SqExpKernel(0, 0.1, 0.2), ff.SqExpKernel(0, 0.3, 0.4), ff.ConstKernel(0.5)])
+    assert prod.simplified().structure() == "SE0"
+    assert ff.repr_to_model.__doc__ and repr(eval(repr(k), vars(ff))) == repr(k)
+
+
+def test_compile_program_theta_order_and_terms(data):
+    k = ff.ProductKernel([ff.SqExpKernel(0, 1.5, 0.5), ff.SumKernel([ff.PeriodicKernel(1, 0.5, 2.0, 1.5), ff.ConstKernel(2.0)])])
+    gk = gpckernel.gpss2gpy(k, data=data)
+    prog = GPy.compile_program(gk)
+    # depth-first leaf order, GPy parameter order per leaf (gpckernel.py:535-565)
+    assert [prog.leaf_type[i] for i in range(prog.n_leaves)] == [0, 1, 3]
+    assert [prog.leaf_off[i] for i in range(prog.n_leaves)] == [0, 2, 5]
+    assert prog.n_theta == 6 and prog.p_eff == k.effective_params == 5
+    assert prog.terms() == [[0, 1], [0, 2]]
+    assert np.allclose(gk.param_array, [0.25, 1.5, 2.25, 2.0, 0.5, 4.0])
+
+
+def test_reset_params_in_bounds_and_seeded(data):
+    k = ff.SumKernel([ff.SqExpKernel(0), ff.PeriodicKernel(1), ff.ConstKernel(), ff.LinearKernel(2)])
+    gpckernel.set_rng(123)
+    gpckernel.resetGpssParams(k, data=data)
+    first = k.param_vector.copy()
+    lo, hi = np.ravel(data.getLengthscaleBounds(dims=0))
+    assert lo <= k.operands[0].lengthscale <= hi
+    lo, hi = np.ravel(data.getPeriodBounds(dims=1))
+    assert lo <= k.operands[1].period <= hi and k.operands[1].lengthscale > 0
+    assert all(o.sf > 0 for o in k.operands)
+    gpckernel.set_rng(123)
+    gpckernel.resetGpssParams(k, data=data)
+    assert np.array_equal(first, k.param_vector)
+
+
+def test_gpcdata_bounds_and_folds():
+    X, y = synth(103, 2, 5)
+    d = GPCData(X, y.reshape(-1, 1), seed=7)
+    b = d.getLengthscaleBounds()
+    assert b.shape == (2, 2) and np.all(b[0] > 0) and np.allclose(b[1], 2 * (X.max(0) - X.min(0)))
+    folds = d.kFoldIndices(5)
+    assert [len(te) for _, te in folds] == [21, 21, 21, 20, 20]        # sklearn KFold sizes
+    assert sorted(np.concatenate([te for _, te in folds]).tolist()) == list(range(103))
+    assert all(len(set(tr) & set(te)) == 0 and len(tr) + len(te) == 103 for tr, te in folds)
+    assert d.kFoldIndices(5) is folds                                   # cached (gpcdata.py:163-164)
+    Xs, Ys, XT, YT = d.kFoldSplits(5)
+    assert Xs[0].shape == (82, 2) and YT[4].shape == (20, 1)
+    one = d.kFoldIndices(1)
+    assert len(one) == 1 and np.array_equal(one[0][0], one[0][1])
+
+
+def test_param_transforms_roundtrip_and_gradfactor():
+    p = GPy.Param("v", 0.7)
+    assert p.from_x(p.to_x()) == pytest.approx(0.7)
+    h = 1e-6
+    fd = (p.from_x(p.to_x() + h) - p.from_x(p.to_x() - h)) / (2 * h)
+    assert p.gradfactor() == pytest.approx(fd, rel=1e-7)
+    q = GPy.Param("l", 5.0).constrain_bounded(0.1, 3.0)
+    assert q[0] == pytest.approx(1.55)                                  # out-of-bounds start -> midpoint
+    q.values[0] = 2.0
+    assert q.from_x(q.to_x()) == pytest.approx(2.0)
+    fd = (q.from_x(q.to_x() + h) - q.from_x(q.to_x() - h)) / (2 * h)
+    assert q.gradfactor() == pytest.approx(fd, rel=1e-6)
