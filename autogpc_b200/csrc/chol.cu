@@ -15,79 +15,138 @@ namespace agpc {
 
 constexpr int POTF2_THREADS = 512;
 constexpr int POTF2_LD = TILE + 1;
-constexpr int POTF2_SMEM = TILE * POTF2_LD * 8;
+constexpr int POTF2_SMEM = (TILE * POTF2_LD + 2 * TILE + TILE + 16) * 8;
 
-// One CTA per (batch item): S (smem) holds the lower triangle of the diagonal block (-> L) and, transposed into
-// the strict upper part shifted by one column, the running inverse W (W[i][c] at S[c][i+1]).
+// One CTA per batch item factors the 128 x 128 diagonal block AND inverts its factor, entirely in registers.
+//
+// The square S (thread (ty, tx) of a 32 x 16 grid owns rows ty + 32a, columns tx + 16b: cyclic, so every thread
+// stays busy as the active region shrinks) holds the lower triangle of A (-> L) and, transposed into its strict
+// upper triangle, the strict lower triangle of the running inverse W (W[i][c] at S[c][i]); diag(W) = 1 / diag(L) is
+// kept aside.  With that packing the right-looking Cholesky step and the forward-substitution step of W = L^-1 are
+// ONE masked rank-1 update per column j:
+//     v = S[:, j]  (A[j:, j] below the diagonal, W'[j, :j] above it),  u = v with u_j = 1
+//     S[r][q] -= u_r v_q / a_jj     for q > j and (r <= j  or  r >= q)
+//     S[:, j] *= 1 / sqrt(a_jj)     (final: columns <= j are never touched again)
+// Column j is broadcast through a double-buffered shared-memory vector, one __syncthreads per step; the owners of
+// column j + 1 update and publish it (and the pivot's reciprocal square root) before the bulk of step j, so the
+// sqrt / divide latency of the pivot sits off the critical path.
 __global__ void __launch_bounds__(POTF2_THREADS, 1)
 potf2_inv_kernel(double* __restrict__ A, double* __restrict__ M, double* __restrict__ U, long long ld,
                  long long batch_stride, int diag_block, const int* __restrict__ active, int* __restrict__ info) {
-  const int b = blockIdx.x;
-  if (active != nullptr && active[b] == 0) return;
-  extern __shared__ double S[];
-  const long long base = (long long)b * batch_stride + (long long)diag_block * TILE * ld + (long long)diag_block * TILE;
+  const int bi = blockIdx.x;
+  if (active != nullptr && active[bi] == 0) return;
+  extern __shared__ double smem[];
+  double* stage = smem;                      // [128][129] output transposition buffer
+  double* vbuf = smem + TILE * POTF2_LD;     // [2][128]   broadcast column
+  double* winv = vbuf + 2 * TILE;            // [128]      1 / L_jj
+  double* ibuf = winv + TILE;                // [2][4]     {1/a_jj, 1/sqrt(a_jj), sqrt(a_jj)}
+  int* badflag = reinterpret_cast<int*>(ibuf + 8);
+  const long long base = (long long)bi * batch_stride + (long long)diag_block * TILE * ld + (long long)diag_block * TILE;
   double* Ab = A + base;
-  const int tid = threadIdx.x;
-  // load lower triangle; W = I
-  for (int idx = tid; idx < TILE * TILE; idx += POTF2_THREADS) {
-    const int i = idx / TILE, j = idx % TILE;
-    if (j <= i) S[i * POTF2_LD + j] = Ab[(long long)i * ld + j];
-  }
-  __syncthreads();
-  for (int idx = tid; idx < TILE * TILE; idx += POTF2_THREADS) {
-    const int c = idx / TILE, i = idx % TILE;
-    if (i >= c) S[c * POTF2_LD + i + 1] = (i == c) ? 1.0 : 0.0;
-  }
-  __syncthreads();
-  bool bad = false;
-  for (int j = 0; j < TILE; ++j) {
-    __syncthreads();  // updates of step j-1 are complete
-    double d = S[j * POTF2_LD + j];
-    if (!(d > 0.0) || !isfinite(d)) {
-      bad = true;
-      d = 1.0;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  if (tid == 0) *badflag = 0;
+
+  double s[4][8];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int r = ty + 32 * a, q = tx + 16 * b;
+      s[a][b] = (q <= r) ? Ab[(long long)r * ld + q] : 0.0;
     }
-    const double piv = sqrt(d);
-    const double rinv = 1.0 / piv;
-    // scale column j of A (rows > j) and row j of W (cols <= j); nobody reads those entries before the barrier
-    if (tid < TILE) {
-      const int i = tid;
-      if (i > j) S[i * POTF2_LD + j] *= rinv;
-    } else if (tid < 2 * TILE) {
-      const int c = tid - TILE;
-      if (c <= j) S[c * POTF2_LD + j + 1] *= rinv;
-    }
-    __syncthreads();
-    if (tid == 0) S[j * POTF2_LD + j] = piv;  // a_jj is not read again during this step
-    const int m = TILE - 1 - j;
-    if (m > 0) {
-      // A part: m x m (k fastest), W part: (j+1) x m (i fastest)
-      const int nA = m * m, nW = (j + 1) * m;
-      for (int idx = tid; idx < nA + nW; idx += POTF2_THREADS) {
-        if (idx < nA) {
-          const int i = j + 1 + idx / m, k = j + 1 + idx % m;
-          if (k <= i) S[i * POTF2_LD + k] -= S[i * POTF2_LD + j] * S[k * POTF2_LD + j];
-        } else {
-          const int r = idx - nA;
-          const int c = r / m, i = j + 1 + r % m;
-          S[c * POTF2_LD + i + 1] -= S[i * POTF2_LD + j] * S[c * POTF2_LD + j + 1];
+
+  // publishes column jn (held in s[.][B] by the threads with tx == jn % 16) and its pivot terms
+#define POTF2_PUBLISH(B, jn)                                            \
+  {                                                                     \
+    double* vb_ = vbuf + ((jn)&1) * TILE;                               \
+    _Pragma("unroll") for (int a = 0; a < 4; ++a) {                     \
+      const int r = ty + 32 * a;                                        \
+      vb_[r] = s[a][B];                                                 \
+      if (r == (jn)) {                                                  \
+        double d = s[a][B];                                             \
+        if (!(d > 0.0) || !isfinite(d)) {                               \
+          *badflag = 1;                                                 \
+          d = 1.0;                                                      \
+        }                                                               \
+        const double piv = sqrt(d);                                     \
+        const double rinv = 1.0 / piv;                                  \
+        double* ib_ = ibuf + ((jn)&1) * 4;                              \
+        ib_[0] = rinv * rinv;                                           \
+        ib_[1] = rinv;                                                  \
+        ib_[2] = piv;                                                   \
+        winv[(jn)] = rinv;                                              \
+      }                                                                 \
+    }                                                                   \
+  }
+
+  if (tx == 0) POTF2_PUBLISH(0, 0)
+  __syncthreads();
+
+#pragma unroll
+  for (int bj = 0; bj < 8; ++bj) {
+#pragma unroll 1
+    for (int jj = 0; jj < 16; ++jj) {
+      const int j = 16 * bj + jj;
+      const double* v = vbuf + (j & 1) * TILE;
+      const double* ib = ibuf + (j & 1) * 4;
+      const double inv = ib[0];
+      double u[4];
+      bool low[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int r = ty + 32 * a;
+        const double vr = v[r];
+        u[a] = (r == j) ? -1.0 : -vr;
+        low[a] = r <= j;
+      }
+      // column j is final
+      if (tx == jj) {
+        const double rinv = ib[1], piv = ib[2];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) s[a][bj] = (ty + 32 * a == j) ? piv : s[a][bj] * rinv;
+      }
+      // columns of this 16-group first, so that column j + 1 can be published early
+      {
+        const int q = tx + 16 * bj;
+        const double t = v[q] * inv;
+        if (tx > jj) {
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            if (low[a] || ty + 32 * a >= q) s[a][bj] = fma(u[a], t, s[a][bj]);
         }
       }
+      if (jj < 15 && tx == jj + 1) POTF2_PUBLISH(bj, j + 1)
+#pragma unroll
+      for (int b = bj + 1; b < 8; ++b) {
+        const int q = tx + 16 * b;
+        const double t = v[q] * inv;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          if (low[a] || ty + 32 * a >= q) s[a][b] = fma(u[a], t, s[a][b]);
+      }
+      if (jj == 15 && bj < 7 && tx == 0) POTF2_PUBLISH((bj < 7 ? bj + 1 : 7), j + 1)
+      __syncthreads();
     }
   }
+#undef POTF2_PUBLISH
+
+  // transpose through shared memory so that L, W and W^T all leave with coalesced row writes
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) stage[(ty + 32 * a) * POTF2_LD + tx + 16 * b] = s[a][b];
   __syncthreads();
-  // write back: L (lower) to A; W (lower, zeros above) to M; W^T (upper, zeros below) to U
   double* Mb = M + base;
   double* Ub = U + base;
   for (int idx = tid; idx < TILE * TILE; idx += POTF2_THREADS) {
-    const int i = idx / TILE, j = idx % TILE;
-    if (j <= i) Ab[(long long)i * ld + j] = S[i * POTF2_LD + j];
-    const double w_ij = (j <= i) ? S[j * POTF2_LD + i + 1] : 0.0;  // W[i][j]
-    const double w_ji = (i <= j) ? S[i * POTF2_LD + j + 1] : 0.0;  // W[j][i] = U[i][j]
-    Mb[(long long)i * ld + j] = w_ij;
-    Ub[(long long)i * ld + j] = w_ji;
+    const int i = idx / TILE, jx = idx % TILE;
+    const double sij = stage[i * POTF2_LD + jx];
+    if (jx <= i) Ab[(long long)i * ld + jx] = sij;
+    const double wd = winv[i];
+    Mb[(long long)i * ld + jx] = (jx < i) ? stage[jx * POTF2_LD + i] : (jx == i ? wd : 0.0);  // W[i][jx]
+    Ub[(long long)i * ld + jx] = (jx > i) ? sij : (jx == i ? wd : 0.0);                       // W[jx][i]
   }
-  if (bad && tid == 0 && info != nullptr) info[b] = AGPC_ST_NOT_PD;
+  if (tid == 0 && *badflag != 0 && info != nullptr) info[bi] = AGPC_ST_NOT_PD;
 }
 
 cudaError_t potf2_inv_launch(const Launch& L, double* A, double* M, double* U, long long ld, long long batch_stride,
