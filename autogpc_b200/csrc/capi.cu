@@ -86,6 +86,10 @@ int agpc_destroy(agpc_ctx* ctx) {
   if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->scratch) cudaFree(ctx->scratch);
+  for (auto& r : ctx->prof.recs) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return AGPC_OK;
@@ -100,6 +104,38 @@ int agpc_set_workspace_limit(agpc_ctx* ctx, uint64_t bytes) {
 }
 
 int64_t agpc_launch_count(agpc_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int agpc_profile_enable(agpc_ctx* ctx, int32_t on) {
+  if (!ctx) return AGPC_E_ARG;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  Profiler& p = ctx->prof;
+  p.enabled = on != 0;
+  p.used = 0;
+  for (int c = 0; c < CLS_COUNT; ++c) {
+    p.work[c] = 0.0;
+    p.count[c] = 0;
+  }
+  return AGPC_OK;
+}
+
+int agpc_profile_read(agpc_ctx* ctx, double* ms, double* work, int64_t* launches) {
+  if (!ctx || !ms || !work || !launches) return AGPC_E_ARG;
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaDeviceSynchronize());
+  Profiler& p = ctx->prof;
+  for (int c = 0; c < CLS_COUNT; ++c) {
+    ms[c] = 0.0;
+    work[c] = p.work[c];
+    launches[c] = p.count[c];
+  }
+  for (size_t i = 0; i < p.used; ++i) {
+    float t = 0.f;
+    CK(ctx, cudaEventElapsedTime(&t, p.recs[i].e0, p.recs[i].e1));
+    ms[p.recs[i].cls] += (double)t;
+  }
+  return AGPC_OK;
+}
 
 int agpc_dataset_create(agpc_ctx* ctx, const double* X_host, const double* y_host, int32_t N, int32_t D,
                         int32_t* dataset_id) {
@@ -150,7 +186,7 @@ int agpc_gemm_nt(agpc_ctx* ctx, const double* A, const double* B, double* C, int
   g.C = C; g.ldc = N; g.c_batch = (long long)M * N;
   g.m_tiles = M / TILE; g.n_tiles = N / TILE; g.k_tiles = K / GEMM_BK;
   g.alpha = alpha; g.beta = beta;
-  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches};
+  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches, &ctx->prof};
   CK(ctx, gemm_nt_launch(L, ma, mb, g, g.m_tiles * g.n_tiles, 1, batch));
   return AGPC_OK;
 }
@@ -178,7 +214,7 @@ int agpc_potrf(agpc_ctx* ctx, double* A, int32_t n, int32_t batch, double* Minv,
       make_tensor_map(&ms.mapU, ms.U, n, n, batch, n, ms.stride) ||
       (want_inv && make_tensor_map(&ms.mapT, ms.T, n, n, batch, n, ms.stride)))
     return fail(ctx, AGPC_E_CUDA, "cuTensorMapEncodeTiled failed");
-  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches};
+  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches, &ctx->prof};
   if (info) CK(ctx, cudaMemsetAsync(info, 0, sizeof(int32_t) * batch, L.stream));
   CK(ctx, potrf_blocked(L, ms, nullptr, info));
   if (want_inv) CK(ctx, trtri_blocked(L, ms, nullptr));
@@ -207,7 +243,7 @@ int agpc_build_K(agpc_ctx* ctx, const agpc_program* program, const double* theta
   if (!ctx || !program || !theta_host || !X_dev || !K_dev || n <= 0 || D <= 0 || ld < n || (ld & 1))
     return fail(ctx, AGPC_E_ARG, "build_K: bad argument (ld must be even and >= n)");
   CK(ctx, cudaSetDevice(ctx->device));
-  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches};
+  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches, &ctx->prof};
   agpc_program* d_prog;
   double* d_theta;
   int rc = param_scratch(ctx, program, theta_host, L.stream, &d_prog, &d_theta);
@@ -225,7 +261,7 @@ int agpc_kernel_grad(agpc_ctx* ctx, const agpc_program* program, const double* t
   if (!ctx || !program || !theta_host || !X_dev || !G_dev || !grad_host || n <= 0 || D <= 0 || ld < n)
     return fail(ctx, AGPC_E_ARG, "kernel_grad: bad argument");
   CK(ctx, cudaSetDevice(ctx->device));
-  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches};
+  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches, &ctx->prof};
   agpc_program* d_prog;
   double* d_theta;
   int rc = param_scratch(ctx, program, theta_host, L.stream, &d_prog, &d_theta);

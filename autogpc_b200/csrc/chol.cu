@@ -68,8 +68,9 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ M, double* __restr
           *badflag = 1;                                                 \
           d = 1.0;                                                      \
         }                                                               \
-        const double piv = sqrt(d);                                     \
-        const double rinv = 1.0 / piv;                                  \
+        double rinv = rsqrt(d); /* MUFU.RSQ64H + Newton: short chain */ \
+        rinv = fma(fma(-d * rinv, rinv, 1.0), 0.5 * rinv, rinv);        \
+        const double piv = d * rinv;                                    \
         double* ib_ = ibuf + ((jn)&1) * 4;                              \
         ib_[0] = rinv * rinv;                                           \
         ib_[1] = rinv;                                                  \
@@ -151,6 +152,7 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ M, double* __restr
 
 cudaError_t potf2_inv_launch(const Launch& L, double* A, double* M, double* U, long long ld, long long batch_stride,
                              int diag_block, int batch, const int* active, int* info) {
+  ProfScope prof_scope(L, CLS_POTF2);
   static bool configured = false;
   if (!configured) {
     AGPC_CUDA_TRY(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM));
@@ -164,6 +166,8 @@ cudaError_t potf2_inv_launch(const Launch& L, double* A, double* M, double* U, l
 // ---- drivers -----------------------------------------------------------------------------------------------
 cudaError_t potrf_blocked(const Launch& L, const MatSet& ms, const int* active, int* info) {
   const int nblk = ms.np / TILE;
+  const double wn = L.work_n > 0.0 ? L.work_n : (double)ms.np;
+  L.add_work(CLS_GEMM, (double)L.work_items * wn * wn * wn / 3.0);  // LAPACK dpotrf count
   for (int k = 0; k < nblk; ++k) {
     AGPC_CUDA_TRY(potf2_inv_launch(L, ms.A, ms.M, ms.U, ms.np, ms.stride, k, ms.batch, active, info));
     const int below = nblk - k - 1;
@@ -191,6 +195,8 @@ cudaError_t potrf_blocked(const Launch& L, const MatSet& ms, const int* active, 
 // M = L^-1 (lower), U = M^T (upper); diagonal 128-blocks already written by potf2_inv.
 cudaError_t trtri_blocked(const Launch& L, const MatSet& ms, const int* active) {
   const int nblk = ms.np / TILE;
+  const double wn = L.work_n > 0.0 ? L.work_n : (double)ms.np;
+  L.add_work(CLS_GEMM, (double)L.work_items * wn * wn * wn / 3.0);  // dtrtri
   for (int h = 1; h < nblk; h *= 2) {
     const int G = 2 * h;
     const int groups = (nblk + G - 1) / G;
@@ -224,6 +230,8 @@ cudaError_t trtri_blocked(const Launch& L, const MatSet& ms, const int* active) 
 // dst (lower tiles) = U U^T = B^-1
 cudaError_t lauum_blocked(const Launch& L, const MatSet& ms, double* dst, const int* active) {
   const int nblk = ms.np / TILE;
+  const double wn = L.work_n > 0.0 ? L.work_n : (double)ms.np;
+  L.add_work(CLS_GEMM, (double)L.work_items * wn * wn * wn / 3.0);  // dlauum
   GemmArgs a{};
   a.C = dst; a.Ct = nullptr; a.ldc = ms.np; a.c_batch = ms.stride;
   a.m_tiles = nblk; a.n_tiles = nblk; a.k_tiles = nblk * (TILE / GEMM_BK);

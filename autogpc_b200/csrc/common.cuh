@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "../../include/autogpc_b200.h"
 
 namespace agpc {
@@ -32,12 +34,60 @@ struct GemmArgs {
   const int* active;  // per-batch-item flag (nullptr = all active)
 };
 
+// Kernel classes of the optional per-launch event timing (agpc_profile_*): bench.py's roofline and the share table.
+enum : int { CLS_KBUILD = 0, CLS_GEMM, CLS_POTF2, CLS_MATVEC, CLS_EP, CLS_GRAD, CLS_FORMB, CLS_MISC, CLS_COUNT };
+
+// When enabled, every launcher brackets its kernel with a cudaEvent pair on the launching stream; the pairs are
+// summed per class by agpc_profile_read.  `work` is the ALGORITHMIC work the drivers attribute to a class
+// (flops for CLS_GEMM / CLS_POTF2, bytes for the others), not what the kernels happen to execute.
+struct Profiler {
+  struct Rec {
+    cudaEvent_t e0, e1;
+    int cls;
+  };
+  bool enabled = false;
+  std::vector<Rec> recs;
+  size_t used = 0;
+  double work[CLS_COUNT] = {0};
+  long long count[CLS_COUNT] = {0};
+  int open(int cls, cudaStream_t st) {
+    if (used == recs.size()) {
+      Rec r;
+      if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return -1;
+      recs.push_back(r);
+    }
+    recs[used].cls = cls;
+    cudaEventRecord(recs[used].e0, st);
+    return (int)used++;
+  }
+  void close(int idx, cudaStream_t st) { cudaEventRecord(recs[idx].e1, st); }
+};
+
 // Launchers (host).  Every launcher bumps *launch_counter when non-null.
 struct Launch {
   cudaStream_t stream;
   long long* counter;
+  Profiler* prof = nullptr;
+  int work_items = 1;     // items still active in the batch      } algorithmic work accounting only
+  double work_n = 0.0;    // mean true n of the batch's items     }
   void bump(int n = 1) const {
     if (counter) *counter += n;
+  }
+  void add_work(int cls, double w) const {
+    if (prof && prof->enabled) prof->work[cls] += w;
+  }
+};
+struct ProfScope {
+  const Launch& L;
+  int idx = -1;
+  ProfScope(const Launch& l, int cls) : L(l) {
+    if (L.prof && L.prof->enabled) {
+      idx = L.prof->open(cls, L.stream);
+      L.prof->count[cls] += 1;
+    }
+  }
+  ~ProfScope() {
+    if (idx >= 0) L.prof->close(idx, L.stream);
   }
 };
 

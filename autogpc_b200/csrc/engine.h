@@ -24,6 +24,7 @@ struct agpc_ctx {
   size_t pinned_bytes = 0;
   void* scratch = nullptr;  // 64 KB device scratch: program + theta of the building-block entry points
   std::vector<Dataset> datasets;
+  agpc::Profiler prof;
 
   int ensure_arena(size_t bytes);
   size_t workspace_budget();

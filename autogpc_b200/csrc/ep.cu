@@ -61,6 +61,7 @@ rowdot_kernel(const double* __restrict__ A, const double* __restrict__ x, double
 cudaError_t rowdot_launch(const Launch& L, int range, bool sq, const double* A, const double* x, double* y,
                           double* y2, int nrows, int ncols, long long a_batch, long long x_batch, long long y_batch,
                           int batch, const int* active) {
+  ProfScope prof_scope(L, CLS_MATVEC);
   dim3 grid((nrows + 7) / 8, batch);
 #define RD(R, S) rowdot_kernel<R, S><<<grid, 256, 0, L.stream>>>(A, x, y, y2, nrows, ncols, a_batch, x_batch, y_batch, active)
   if (range == 0 && !sq) RD(0, false);
@@ -132,6 +133,7 @@ __global__ void marginals_kernel(const double* __restrict__ tau, const double* _
 
 cudaError_t sqrt_scale_launch(const Launch& L, const double* tau, const double* w, double* s, double* u, int np,
                               int batch, const int* active) {
+  ProfScope prof_scope(L, CLS_EP);
   dim3 grid((np + 255) / 256, batch);
   sqrt_scale_kernel<<<grid, 256, 0, L.stream>>>(tau, w, s, u, np, active);
   L.bump();
@@ -139,6 +141,7 @@ cudaError_t sqrt_scale_launch(const Launch& L, const double* tau, const double* 
 }
 cudaError_t mul_launch(const Launch& L, const double* a, const double* b, double* out, int np, int batch,
                        const int* active) {
+  ProfScope prof_scope(L, CLS_EP);
   dim3 grid((np + 255) / 256, batch);
   mul_kernel<<<grid, 256, 0, L.stream>>>(a, b, out, np, active);
   L.bump();
@@ -147,6 +150,7 @@ cudaError_t mul_launch(const Launch& L, const double* a, const double* b, double
 cudaError_t marginals_launch(const Launch& L, const double* tau, const double* dB, const double* w, const double* kv,
                              const double* kdiag, double* sig, double* mu, const int* n_of, int np, int batch, int cold,
                              const int* active) {
+  ProfScope prof_scope(L, CLS_EP);
   dim3 grid((np + 255) / 256, batch);
   marginals_kernel<<<grid, 256, 0, L.stream>>>(tau, dB, w, kv, kdiag, sig, mu, n_of, np, cold, active);
   L.bump();
@@ -238,6 +242,7 @@ ep_update_kernel(double* __restrict__ tau, double* __restrict__ nu, const double
 cudaError_t ep_update_launch(const Launch& L, double* tau, double* nu, const double* sig, const double* mu,
                              const double* yf, const double* kdiag, const int* n_of, int np, int batch, double eps,
                              double damping, int* active, int* sweeps, int* status, int* converged, const int* info) {
+  ProfScope prof_scope(L, CLS_EP);
   ep_update_kernel<<<batch, 1024, 0, L.stream>>>(tau, nu, sig, mu, yf, kdiag, n_of, np, eps, damping, active, sweeps,
                                                   status, converged, info);
   L.bump();
@@ -299,6 +304,7 @@ cudaError_t ep_final_launch(const Launch& L, const double* tau, const double* nu
                             const double* yf, const double* s, const double* z, const double* Lmat, long long stride,
                             const int* n_of, int np, int batch, const agpc_program* progs, double* alpha, double* nlml,
                             double* nlml_gauss, double* bic, int* status, const int* info) {
+  ProfScope prof_scope(L, CLS_EP);
   ep_final_kernel<<<batch, 1024, 0, L.stream>>>(tau, nu, sig, mu, yf, s, z, Lmat, stride, n_of, np, progs, alpha, nlml,
                                                  nlml_gauss, bic, status, info);
   L.bump();
@@ -318,6 +324,7 @@ __global__ void predict_prob_kernel(const double* __restrict__ mu_s, const doubl
 
 cudaError_t predict_prob_launch(const Launch& L, const double* mu_s, const double* kss, const double* vsq, double* p,
                                 double* var, long long total) {
+  ProfScope prof_scope(L, CLS_MISC);
   predict_prob_kernel<<<(unsigned)((total + 255) / 256), 256, 0, L.stream>>>(mu_s, kss, vsq, p, var, total);
   L.bump();
   return cudaGetLastError();

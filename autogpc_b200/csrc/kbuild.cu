@@ -211,6 +211,7 @@ build_K_kernel(const BuildArgs a) {
 }
 
 cudaError_t build_K_launch(const Launch& L, const BuildArgs& a, int batch, bool grad) {
+  ProfScope prof_scope(L, CLS_KBUILD);
   dim3 grid((unsigned)((a.ld + KB_COLS - 1) / KB_COLS), (unsigned)((a.na_pad + KB_ROWS - 1) / KB_ROWS), batch);
   const size_t smem = sizeof(double) * a.D * (KB_ROWS + KB_COLS);
   if (grad)
@@ -224,6 +225,7 @@ cudaError_t build_K_launch(const Launch& L, const BuildArgs& a, int batch, bool 
 cudaError_t gather_rows_launch(const Launch& L, const double* X, const double* y, const int* rows,
                                const long long* row_off, const int* n_of, int D, int np, int batch, double* Xf,
                                double* yf) {
+  ProfScope prof_scope(L, CLS_MISC);
   dim3 grid((np + 255) / 256, batch);
   gather_rows_kernel<<<grid, 256, 0, L.stream>>>(X, y, rows, row_off, n_of, D, np, Xf, yf);
   L.bump();
@@ -258,6 +260,7 @@ __global__ void form_B_kernel(const double* __restrict__ K, const double* __rest
 
 cudaError_t form_B_launch(const Launch& L, const double* K, const double* s, double* A, int np, long long stride,
                           int batch, const int* active) {
+  ProfScope prof_scope(L, CLS_FORMB);
   dim3 grid(np / 128, np / 32, batch);
   form_B_kernel<<<grid, 256, 0, L.stream>>>(K, s, A, np, stride, active);
   L.bump();
@@ -357,6 +360,7 @@ __global__ void grad_finalize_kernel(const double* __restrict__ partial, int til
 
 cudaError_t grad_contract_launch(const Launch& L, const GradArgs& a, int batch, double scale, double* grad,
                                  int grad_stride) {
+  ProfScope prof_scope(L, CLS_GRAD);
   const int nt = a.np / GT;
   const int tiles = a.mode == 0 ? nt * (nt + 1) / 2 : nt * nt;
   const size_t smem = sizeof(double) * (2 * a.D * GT + 8 * AGPC_MAX_THETA);
@@ -386,6 +390,7 @@ __global__ void kself_kernel(const agpc_program* __restrict__ progs, const doubl
 }
 cudaError_t kself_launch(const Launch& L, const agpc_program* progs, const double* theta, int theta_stride,
                          const double* Xs, int m_pad, int D, const int* m_of, int batch, double* kss) {
+  ProfScope prof_scope(L, CLS_MISC);
   dim3 grid((m_pad + 255) / 256, batch);
   kself_kernel<<<grid, 256, 0, L.stream>>>(progs, theta, theta_stride, Xs, m_pad, D, m_of, kss);
   L.bump();
@@ -398,6 +403,7 @@ __global__ void scale_cols_kernel(double* __restrict__ Ks, const double* __restr
   Ks[((long long)b * rows + i) * np + j] *= s[(long long)b * np + j];
 }
 cudaError_t scale_cols_launch(const Launch& L, double* Ks, const double* s, int rows, int np, int batch) {
+  ProfScope prof_scope(L, CLS_MISC);
   dim3 grid((np + 255) / 256, rows, batch);
   scale_cols_kernel<<<grid, 256, 0, L.stream>>>(Ks, s, rows, np);
   L.bump();
@@ -472,6 +478,7 @@ dmu_dx_kernel(const agpc_program* __restrict__ prog, const double* __restrict__ 
 }
 cudaError_t dmu_dx_launch(const Launch& L, const agpc_program* prog, const double* theta, const double* Xs, int m,
                           const double* Xf, int n, int D, const double* alpha, double* out) {
+  ProfScope prof_scope(L, CLS_MISC);
   if (D > MAX_D) return cudaErrorInvalidValue;
   dmu_dx_kernel<<<(m + 7) / 8, 256, 0, L.stream>>>(prog, theta, Xs, m, Xf, n, D, alpha, out);
   L.bump();

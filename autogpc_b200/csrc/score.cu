@@ -121,6 +121,11 @@ __global__ void mark_unconverged_kernel(const int* __restrict__ active, int* __r
 cudaError_t posterior(const Launch& L, Chunk& c, const int* active) {
   const int np = c.np, nb = c.nb;
   const long long st = c.ms.stride;
+  {
+    const double wn = L.work_n > 0.0 ? L.work_n : (double)np, n2 = 8.0 * wn * wn * L.work_items;
+    L.add_work(CLS_FORMB, n2);          // read lower K, write lower B
+    L.add_work(CLS_MATVEC, 3.0 * n2);   // two full K passes, two triangular passes over M and U
+  }
   AGPC_CUDA_TRY(sqrt_scale_launch(L, c.tau, nullptr, c.s, nullptr, np, nb, active));
   AGPC_CUDA_TRY(form_B_launch(L, c.ms.K, c.s, c.ms.A, np, st, nb, active));
   AGPC_CUDA_TRY(potrf_blocked(L, c.ms, active, c.info));
@@ -198,7 +203,7 @@ int agpc_score_batch_dev(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, con
   if ((opt->warm_start || opt->max_sweeps == 0) && (!tau_dev || !nu_dev))
     return fail(ctx, AGPC_E_ARG, "score_batch: warm start / frozen sites need tau and nu");
   CK(cudaSetDevice(ctx->device));
-  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches};
+  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches, &ctx->prof};
 
   // chunking: consecutive items, as many as the arena budget allows at the padded size of the largest item
   const int np_all = (int)align_up((size_t)n_max, TILE);
@@ -228,6 +233,12 @@ int agpc_score_batch_dev(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, con
     if (c.make_maps()) return fail(ctx, AGPC_E_CUDA, "cuTensorMapEncodeTiled failed");
     const int tb = 256;
     dim3 gvec((np + tb - 1) / tb, nb);
+    {
+      double m3 = 0.0;
+      for (int b = 0; b < nb; ++b) m3 += (double)n_of[b] * n_of[b] * n_of[b];
+      L.work_n = cbrt(m3 / nb);
+      L.work_items = nb;
+    }
 
     CK(cudaMemcpyAsync(c.n_of, n_of.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, L.stream));
     CK(cudaMemcpyAsync(c.row_off, off.data(), sizeof(long long) * (nb + 1), cudaMemcpyHostToDevice, L.stream));
@@ -248,6 +259,7 @@ int agpc_score_batch_dev(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, con
     ba.Xa = c.Xf; ba.Xb = c.Xf; ba.na_of = c.n_of; ba.nb_of = c.n_of;
     ba.na_pad = np; ba.nb_pad = np; ba.D = ds.D; ba.xa_batch = (long long)np * ds.D; ba.xb_batch = ba.xa_batch;
     ba.out = c.ms.K; ba.ld = np; ba.out_batch = c.ms.stride; ba.dK = nullptr; ba.kdiag = c.kdiag; ba.active = nullptr;
+    L.add_work(CLS_KBUILD, 8.0 * L.work_n * L.work_n * nb);
     CK(build_K_launch(L, ba, nb, false));
 
     const bool frozen = opt->max_sweeps <= 0;
@@ -275,7 +287,9 @@ int agpc_score_batch_dev(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, con
       rc = poll_active(ctx, L, c.active, nb, &n_active);
       if (rc) return rc;
       if (n_active == 0) break;
+      L.work_items = n_active;
     }
+    L.work_items = nb;
     if (!frozen) {
       mark_unconverged_kernel<<<(nb + 255) / 256, 256, 0, L.stream>>>(c.active, c.status, nb);
       L.bump();
@@ -293,6 +307,7 @@ int agpc_score_batch_dev(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, con
       ga.np = np; ga.D = ds.D; ga.G = c.ms.T; ga.ld = np; ga.g_batch = c.ms.stride; ga.alpha = c.alpha; ga.s = c.s;
       ga.mode = 0; ga.partial = c.partial; ga.tiles_per_item = grad_tiles(np, 0); ga.active = nullptr;
       // d nlml / d theta = - sum dL_dK * dK/dtheta
+      L.add_work(CLS_GRAD, 4.0 * L.work_n * L.work_n * nb);  // lower triangle of B^-1 read once
       CK(cudaMemsetAsync(c.grad, 0, sizeof(double) * (size_t)nb * theta_stride, L.stream));
       CK(grad_contract_launch(L, ga, nb, -1.0, c.grad, theta_stride));
       CK(cudaMemcpyAsync(grad_dev + (size_t)first * theta_stride, c.grad, sizeof(double) * (size_t)nb * theta_stride,
@@ -395,7 +410,7 @@ static int predict_impl(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, cons
   if (Xstar_host && n_items != 1) return fail(ctx, AGPC_E_ARG, "predict_points: one item only");
   const Dataset& ds = ctx->datasets[dataset_id];
   CK(cudaSetDevice(ctx->device));
-  Launch L{ctx->stream, &ctx->launches};
+  Launch L{ctx->stream, &ctx->launches, &ctx->prof};
   int n_max = 0, m_max = 0;
   for (int b = 0; b < n_items; ++b) {
     n_max = std::max<int>(n_max, (int)(row_off[b + 1] - row_off[b]));

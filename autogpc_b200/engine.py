@@ -189,6 +189,31 @@ class Engine:
                     tau=[tau_a[b, :len(rows[b])].copy() for b in range(B)],
                     nu=[nu_a[b, :len(rows[b])].copy() for b in range(B)])
 
+    def score_batch_dev(self, dataset: int, progs_array, n_items: int, theta_ptr: int, theta_stride: int, rows_ptr: int,
+                        row_off: np.ndarray, opt: "EPOptions", tau_ptr: int, nu_ptr: int, site_stride: int,
+                        nlml_ptr: int, grad_ptr: int, bic_ptr: int, gauss_ptr: int, sweeps_ptr: int, status_ptr: int,
+                        stream: int = 0):
+        """``agpc_score_batch_dev``: theta / rows / sites / outputs are DEVICE pointers (e.g. ``tensor.data_ptr()``);
+        ``progs_array`` is a ctypes ``Program`` array and ``row_off`` a host int64 array of n_items + 1 offsets."""
+        vp = lambda p: C.c_void_p(p) if p else None
+        self._check(self._L.agpc_score_batch_dev(self._ctx, int(dataset), int(n_items), progs_array, vp(theta_ptr),
+                                                 int(theta_stride), vp(rows_ptr), _lp(row_off), C.byref(opt),
+                                                 vp(tau_ptr), vp(nu_ptr), int(site_stride), vp(nlml_ptr), vp(grad_ptr),
+                                                 vp(bic_ptr), vp(gauss_ptr), vp(sweeps_ptr), vp(status_ptr),
+                                                 vp(stream)))
+
+    # ---- per-launch event timing (bench.py roofline) ----
+    CLASSES = ("kbuild", "gemm", "potf2", "matvec", "ep", "grad", "formB", "misc")
+
+    def profile_enable(self, on: bool = True):
+        self._check(self._L.agpc_profile_enable(self._ctx, 1 if on else 0))
+
+    def profile_read(self) -> dict:
+        n = len(self.CLASSES)
+        ms, work, cnt = np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.int64)
+        self._check(self._L.agpc_profile_read(self._ctx, _dp(ms), _dp(work), _lp(cnt)))
+        return {c: dict(ms=float(ms[i]), work=float(work[i]), launches=int(cnt[i])) for i, c in enumerate(self.CLASSES)}
+
     def predict_batch(self, dataset: int, programs: Sequence[Program], thetas: Sequence[np.ndarray],
                       rows: Sequence[np.ndarray], tau: Sequence[np.ndarray], nu: Sequence[np.ndarray],
                       test_rows: Sequence[np.ndarray], want_latent: bool = False):

@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""Headline benchmark of the candidate-scoring hot path (BASELINE.json metric, configs[2]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a engine
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU arm: the oracle (NumPy/LAPACK restatement of the
+                                                             # GPy path -- GPy itself cannot be installed)
+
+Workload (weak scaling, synthetic): N = 8000 points, D = 8, 5 folds (n = 6400 training points per model).  The
+candidate pool is what gpcsearch generates with SE/LIN/PER bases: the depth-1 expansion followed by the depth-2
+expansion of its first member; every rank owns `--cands` candidates x 5 folds = 40 items by default (round-robin
+by global item id, autogpc_b200/sharding.py).  One STEP = every item of the rank taken through one full cold-start
+evaluation -- K build, parallel EP to epsilon = 1e-6, blocked FP64 Cholesky / triangular inverse per sweep, log Z_EP,
+gradient, BIC -- followed (N > 1) by the NCCL all-gather of the (score, theta) records.  A candidate counts as scored
+when its 5 fold models have been evaluated: value = candidates / s over all ranks.
+
+`value`: inputs (dataset, theta, row lists) resident in HBM, device outputs, CUDA-event timed, max over ranks.
+`e2e`  : the same step through the public host API (Engine.dataset + Engine.score_batch, the call GPCKernel.train
+         makes) with pinned HOST buffers: X, y, theta, rows up; nlml, grad, bic, sites down -- inside the timed region.
+`roofline`: the dominant kernel (gemm_nt_kernel: TMA + FP64 DMMA tile GEMM behind potrf / trtri / lauum), achieved =
+         algorithmic flops (n^3/3 per potrf, trtri, lauum) / summed CUDA-event durations of its launches
+         inside the timed region; peak = cuBLAS DGEMM measured live in this process (MEASURED_PEAKS.json has no FP64
+         entry).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_POINTS, N_DIM, N_FOLDS = 8000, 8, 5
+METRIC = "candidate kernels scored/sec at n=8k D=8"
+UNIT = "candidates/s"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def synth(N, D, seed=0):
+    """SURVEY 8(d) generator: X ~ U(-3,3)^{N x D}, analytic latent, balanced {0,1} labels."""
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-3, 3, (N, D))
+    f = np.sin(2 * X[:, 0]) * np.cos(X[:, 1]) + 0.5 * X[:, 2] + np.sin(2 * np.pi * X[:, 3] / 1.5)
+    if D > 5:
+        f = f + 0.3 * X[:, 4] * X[:, 5]
+    f = f + 0.3 * rng.standard_normal(N)
+    return X, (f > np.median(f)).astype(float)
+
+
+def build_workload(world: int, cands_per_gpu: int, n_points: int = N_POINTS):
+    """Global item list [(candidate index, fold, gpy-shaped kernel, theta0)] in canonical order + the data."""
+    from autogpc_b200 import flexible_function as ff
+    from autogpc_b200 import gpckernel as gk
+    from autogpc_b200.gpcdata import GPCData
+    X, y = synth(n_points, N_DIM, 0)
+    data = GPCData(X, y.reshape(-1, 1), seed=0)
+    gk.set_rng(0)
+    root = gk.GPCKernel(ff.NoneKernel(), data, depth=0)
+    depth1 = root.expand(base_kernels="SE,Lin,Per")
+    depth2 = [k for k in depth1[0].expand(base_kernels="SE,Lin,Per") if len(k.getActiveDims()) > 1]
+    pool = depth1 + depth2
+    need = cands_per_gpu * world
+    while len(pool) < need:  # only for very large worlds: further depth-2 expansions
+        pool += [k for k in depth1[len(pool) % len(depth1)].expand(base_kernels="SE,Lin,Per") if len(k.getActiveDims()) > 1]
+    cands = pool[:need]
+    folds = data.kFoldIndices(N_FOLDS)
+    items = []
+    for ci, c in enumerate(cands):
+        for f in range(N_FOLDS):
+            k = c.kernel.copy()
+            gk.resetGpssParams(k, data=data)  # one random restart per fold (gpckernel.py:241-243)
+            items.append((ci, f, gk.gpss2gpy(k, data=data)))
+    return data, cands, folds, items
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+
+    def __init__(self, device: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def window(self, t0, t1):
+        sm, mx, reasons = [], 0.0, set()
+        for t, c in self.rows:
+            if t0 <= t <= t1 and len(c) >= 7:
+                try:
+                    sm.append(float(c[0]))
+                    mx = max(mx, float(c[1]))
+                except ValueError:
+                    continue
+                for name, v in zip(self.NAMES, c[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+
+def measure_dgemm_peak(torch, seconds=2.0):
+    """cuBLAS DGEMM 8192^3: best-of-5 burst and a back-to-back `seconds`-long loop (sustained) in TFLOP/s."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    c = torch.empty_like(a)
+    for _ in range(2):
+        torch.matmul(a, b, out=c)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    reps = max(3, int(seconds * 1e3 / best))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        torch.matmul(a, b, out=c)
+    e1.record()
+    torch.cuda.synchronize()
+    sustained = 2.0 * n ** 3 * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    del a, b, c
+    torch.cuda.empty_cache()
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12, sustained
+
+
+def oracle_item_seconds(data, folds, item):
+    """One item through the CPU oracle (parallel-EP mode: BLAS/LAPACK-bound, all host threads)."""
+    from oracle import gpc_oracle as orc  # the checker, used here only as the CPU baseline leg
+    from autogpc_b200 import gpy_compat as GPy
+    ci, f, kern = item
+    eprog = GPy.compile_program(kern)
+    prog = orc.KernelProgram(list(eprog.leaf_type[:eprog.n_leaves]), list(eprog.leaf_dim[:eprog.n_leaves]),
+                             list(eprog.leaf_off[:eprog.n_leaves]), eprog.terms(), eprog.n_theta)
+    tr = folds[f][0]
+    y = data.Y.reshape(-1)
+    t = time.perf_counter()
+    o = orc.score(prog, kern.param_array, data.X[tr], y[tr])
+    return time.perf_counter() - t, o
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """CPU arm: the oracle on the box's host cores, one item of the same workload per step."""
+    if rank != 0:
+        return
+    data, cands, folds, items = build_workload(world, args.cands, args.points)
+    times = []
+    for s in range(args.warmup + args.steps):
+        dt, _ = oracle_item_seconds(data, folds, items[s % len(items)])
+        if s >= args.warmup:
+            times.append(dt)
+    total = float(np.sum(times))
+    value = (len(times) / N_FOLDS) / total
+    cores = host_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, world, len(items)),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "1 item (one fold model, n=%d, cold-start EP + NLML + gradient) per step; NumPy/"
+                                   "LAPACK oracle in parallel-EP mode on %d host threads; GPy itself is not installable "
+                                   "(SURVEY 8c)" % (len(folds[0][0]), cores)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world, n_items):
+    return {"workload": "configs[2]: gpcsearch candidate scoring on synthetic D=8 N=%d, 5-fold (n=%d per model), "
+                        "SE/LIN/PER bases; step = every candidate x fold item of the rank through one cold-start "
+                        "evaluation (K build, parallel EP eps=1e-6, FP64 potrf+trtri per sweep, logZ, gradient, BIC)"
+                        % (args.points, args.points - args.points // N_FOLDS),
+            "candidates_per_gpu": args.cands, "folds": N_FOLDS, "items_total": n_items,
+            "parallelism": "items sharded round-robin over %d GPU(s); all-gather of (score, theta) records per step" % world,
+            "l2": "inputs larger than L2 (per-step working set >> 126 MB: %d x 5 n^2 FP64 matrices per rank)" % (args.cands * N_FOLDS)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cands", type=int, default=8, help="candidate structures per GPU (x5 folds = items per step)")
+    ap.add_argument("--points", type=int, default=N_POINTS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from autogpc_b200 import gpy_compat as GPy
+    from autogpc_b200 import sharding
+    from autogpc_b200.engine import Engine, EPOptions, Program
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- autogpc_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    data, cands, folds, items = build_workload(world, args.cands, args.points)
+    mine = sharding.shard_indices(len(items), rank, world)
+    eng = Engine(local_rank)
+    progs = [GPy.compile_program(items[i][2]) for i in mine]
+    thetas = [items[i][2].param_array for i in mine]
+    rows = [folds[items[i][1]][0] for i in mine]
+    B = len(mine)
+    stride = max(p.n_theta for p in progs)
+    n_max = max(len(r) for r in rows)
+
+    # ---- device-resident inputs / outputs for `value` ----
+    th_h = np.zeros((B, stride))
+    for b, t in enumerate(thetas):
+        th_h[b, :len(t)] = t
+    row_off = np.zeros(B + 1, dtype=np.int64)
+    row_off[1:] = np.cumsum([len(r) for r in rows])
+    rows_cat = np.concatenate(rows).astype(np.int32)
+    th_d = torch.from_numpy(th_h).to(dev)
+    rows_d = torch.from_numpy(rows_cat).to(dev)
+    tau_d = torch.zeros((B, n_max), dtype=torch.float64, device=dev)
+    nu_d = torch.zeros_like(tau_d)
+    nlml_d = torch.zeros(B, dtype=torch.float64, device=dev)
+    grad_d = torch.zeros((B, stride), dtype=torch.float64, device=dev)
+    bic_d = torch.zeros_like(nlml_d)
+    gauss_d = torch.zeros_like(nlml_d)
+    sweeps_d = torch.zeros(B, dtype=torch.int32, device=dev)
+    status_d = torch.zeros(B, dtype=torch.int32, device=dev)
+    prog_arr = (Program * B)(*progs)
+    opt = EPOptions(1e-6, 1.0, 100, 0)
+    did = eng.dataset(data.X, data.Y)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def exchange(nlml_np, bic_np, status_np):
+        if world == 1:
+            return
+        local = np.zeros((B, sharding.RECORD_WIDTH))
+        for j, i in enumerate(mine):
+            local[j] = sharding.pack_record(i, nlml_np[j], bic_np[j], 0.0, int(status_np[j]), thetas[j])
+        sharding.allgather_records(local, len(items))
+
+    def step_device():
+        eng.score_batch_dev(did, prog_arr, B, th_d.data_ptr(), stride, rows_d.data_ptr(), row_off, opt,
+                            tau_d.data_ptr(), nu_d.data_ptr(), n_max, nlml_d.data_ptr(), grad_d.data_ptr(),
+                            bic_d.data_ptr(), gauss_d.data_ptr(), sweeps_d.data_ptr(), status_d.data_ptr(), stream)
+        if world > 1:
+            exchange(nlml_d.cpu().numpy(), bic_d.cpu().numpy(), status_d.cpu().numpy())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peak_burst, peak_sustained = measure_dgemm_peak(torch)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    eng.profile_enable(True)
+    launches0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launches - launches0
+    prof = eng.profile_read()
+    eng.profile_enable(False)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    sweeps_mean = float(sweeps_d.float().mean().item())
+    status_ok = int((status_d == 0).sum().item())
+    n_cands_total = len(cands)
+    value = n_cands_total * args.steps / (ms * 1e-3)
+
+    # ---- e2e: the host API with pinned host buffers, copies inside the timed region ----
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    Xp, yp = pin(data.X), pin(data.Y.reshape(-1))
+    thetas_p = [pin(t) for t in thetas]
+    rows_p = [pin(r.astype(np.int32)) for r in rows]
+
+    def step_host():
+        d = eng.dataset(Xp, yp)
+        r = eng.score_batch(d, progs, thetas_p, rows_p)
+        eng.dataset_free(d)
+        exchange(r["nlml"], r["bic"], r["status"])
+        return r
+
+    h2d = Xp.nbytes + yp.nbytes + B * stride * 8 + rows_cat.nbytes + B * 8 + B * 784
+    d2h = B * (8 * 3 + 4 * 2 + stride * 8) + 2 * B * n_max * 8
+    e2e_steps = max(1, min(args.steps, 3))
+    r = step_host()  # warm-up of the host path (staging allocations)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        r = step_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = n_cands_total * e2e_steps / e2e_s
+    same = bool(np.allclose(r["nlml"], nlml_d.cpu().numpy(), rtol=1e-9, atol=0, equal_nan=True))
+
+    clocks = None
+    if sampler is not None:
+        clocks = sampler.window(t_wall0, t_wall1)
+        sampler.stop()
+
+    if rank == 0:
+        g = prof["gemm"]
+        total_kernel_ms = sum(v["ms"] for v in prof.values()) or 1.0
+        achieved = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+        chol_ms = g["ms"] + prof["potf2"]["ms"]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, world, len(items)),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps, "matches_device_path": same},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "gemm_nt_kernel (TMA + FP64 DMMA; potrf trailing/panel updates, "
+                                                     "trtri, lauum)",
+                         "achieved": achieved, "peak": peak_sustained, "unit": "TFLOP/s",
+                         "frac": achieved / peak_sustained if peak_sustained else None, "traffic": None,
+                         "peak_source": "cuBLAS DGEMM 8192^3 measured live, sustained %.1f / burst %.1f TFLOP/s "
+                                        "(MEASURED_PEAKS.json has no FP64 entry; DMMA issue ceiling 37.1 TFLOP/s, "
+                                        "profiles/r01_fp64_peak.md)" % (peak_sustained, peak_burst),
+                         "algorithmic_flops": g["work"], "kernel_ms": g["ms"], "launches": g["launches"],
+                         "share_of_kernel_time": g["ms"] / total_kernel_ms},
+            "cholesky": {"tflops": g["work"] / (chol_ms * 1e-3) / 1e12 if chol_ms > 0 else None,
+                         "note": "potrf+trtri+lauum algorithmic flops / (gemm_nt + potf2_inv) event time"},
+            "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
+            "evals_per_s": len(items) * args.steps / (ms * 1e-3),
+            "ep_sweeps_mean": sweeps_mean, "items_ok": status_ok, "items_per_gpu": B,
+        }
+        kb = prof["kbuild"]
+        if kb["ms"] > 0:
+            line["kbuild_gbs"] = kb["work"] / (kb["ms"] * 1e-3) / 1e9
+        if not args.no_cpu_baseline:
+            dt, o = oracle_item_seconds(data, folds, items[0])
+            cores = host_threads()
+            line["cpu_baseline"] = {"value": (1.0 / N_FOLDS) / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "1 of the step's %d items (one fold model, n=%d, %d EP sweeps), NumPy/"
+                                              "LAPACK oracle, parallel-EP mode, %d host threads: %.1f s"
+                                              % (B, len(rows[0]), o["sweeps"], cores, dt)}
+            gn = float(nlml_d[0].item())
+            line["cpu_baseline"]["nlml_rel_diff_vs_gpu"] = abs(gn - o["nlml"]) / abs(o["nlml"])
+        print(json.dumps(line), flush=True)
+    eng.dataset_free(did)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

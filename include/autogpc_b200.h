@@ -84,6 +84,23 @@ int agpc_set_workspace_limit(agpc_ctx* ctx, uint64_t bytes);
 /* number of kernels launched by this context so far (bench.py's gpu_launches) */
 int64_t agpc_launch_count(agpc_ctx* ctx);
 
+/* Optional per-launch event timing (bench.py's roofline; SURVEY 5 "tracing / profiling": the reference only has the
+ * @timing wall-clock decorator, gpcexperiment.py:13-20).  enable(1) resets and starts bracketing every kernel launch
+ * with a cudaEvent pair on its stream; read() synchronises and returns, per kernel class (AGPC_CLS_*), the summed
+ * device time in ms, the ALGORITHMIC work attributed to the class (flops for GEMM, bytes otherwise) and the launch
+ * count.  Arrays have AGPC_CLS_COUNT entries. */
+#define AGPC_CLS_KBUILD 0
+#define AGPC_CLS_GEMM 1
+#define AGPC_CLS_POTF2 2
+#define AGPC_CLS_MATVEC 3
+#define AGPC_CLS_EP 4
+#define AGPC_CLS_GRAD 5
+#define AGPC_CLS_FORMB 6
+#define AGPC_CLS_MISC 7
+#define AGPC_CLS_COUNT 8
+int agpc_profile_enable(agpc_ctx* ctx, int32_t on);
+int agpc_profile_read(agpc_ctx* ctx, double* ms, double* work, int64_t* launches);
+
 /* ---- dataset: GPCData.X / .Y handed to GPy.models.GPClassification(X, Y, kernel) (gpckernel.py:126,245,322) - */
 /* X: N x D row-major FP64; y: N labels, 1 -> +1, anything else (0 / -1) -> -1 (bernoulli.py).  Copied to device. */
 int agpc_dataset_create(agpc_ctx* ctx, const double* X_host, const double* y_host, int32_t N, int32_t D,
