@@ -148,3 +148,146 @@ def test_not_pd_is_per_item_status(engine):
     o = orc.score(prog, good, X, y)
     assert g["status"][0] == 0 and abs(g["nlml"][0] - o["nlml"]) <= 1e-9 * abs(o["nlml"])
     assert g["status"][1] in (2, 4) and not np.isfinite(g["nlml"][1])
+
+
+# ---- committed golden fixtures (tests/golden/*.npz, generated by tests/golden/make_golden.py from the oracle) ----
+import ast
+import glob
+import os
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden_fixtures_through_c_abi(engine, path):
+    """The five BASELINE configs at reduced n + edge cases (constant-only kernel, n = 129 not a tile multiple)."""
+    g = np.load(path)
+    prog = orc.KernelProgram.from_tree(ast.literal_eval(str(g["tree"])))
+    X, y, N = g["X"], g["y"], g["X"].shape[0]
+    Xall = np.vstack([X, g["Xstar"]])
+    yall = np.concatenate([y, np.zeros(len(g["Xstar"]))])
+    did = engine.dataset(Xall, yall)
+    ep = to_engine_program(prog)
+    rows = [np.arange(N, dtype=np.int32)]
+    r = engine.score_batch(did, [ep], [g["theta"]], rows)
+    p, mu, var, _ = engine.predict_batch(did, [ep], [g["theta"]], rows, r["tau"], r["nu"],
+                                         [np.arange(N, len(Xall), dtype=np.int32)], want_latent=True)
+    engine.dataset_free(did)
+    assert r["status"][0] == int(g["status"]) and r["sweeps"][0] == int(g["sweeps"])
+    assert abs(r["nlml"][0] - g["nlml"]) <= 1e-9 * abs(g["nlml"])
+    assert abs(r["bic"][0] - g["bic"]) <= 1e-9 * abs(g["bic"])
+    assert abs(r["nlml_gauss"][0] - g["nlml_gauss"]) <= 1e-8 * abs(g["nlml_gauss"])
+    scale = np.maximum(np.abs(g["grad"]), 1e-3 * np.abs(g["grad"]).max())
+    assert np.all(np.abs(r["grad"][0, :prog.n_theta] - g["grad"]) <= 1e-7 * scale)
+    assert np.allclose(r["tau"][0], g["tau"], rtol=1e-7, atol=1e-12)
+    assert np.allclose(p[0], g["pstar"], rtol=1e-8, atol=1e-12)
+    assert np.allclose(mu[0], g["mustar"], rtol=1e-8, atol=1e-10)
+    assert np.allclose(var[0], g["varstar"], rtol=1e-7, atol=1e-10)
+
+
+# ---- building blocks on device buffers (agpc_build_K / agpc_kernel_grad / agpc_potrf / agpc_gemm_nt) --------------
+def _torch():
+    import torch
+    return torch
+
+
+@pytest.mark.parametrize("name", ["se0xse1+per3+se2", "mix", "const"])
+@pytest.mark.parametrize("n", [130, 512])
+def test_build_K_dK_and_fused_gradient(engine, name, n):
+    """kern.K, materialised dK/dtheta and the fused <G, dK/dtheta> contraction against the oracle (abs 1e-13)."""
+    torch = _torch()
+    X, _ = synth(n, 4, 21)
+    prog = orc.KernelProgram.from_tree(TREES[name])
+    th = random_theta(prog, np.random.default_rng(4))
+    ep = to_engine_program(prog)
+    Xd = torch.from_numpy(X).cuda()
+    ld = n + (n & 1)
+    K = torch.zeros((n, ld), dtype=torch.float64, device="cuda")
+    dK = torch.zeros((prog.n_theta, n, ld), dtype=torch.float64, device="cuda")
+    engine.build_K(ep, th, Xd.data_ptr(), n, 4, K.data_ptr(), ld, dK.data_ptr())
+    torch.cuda.synchronize()
+    Ko = orc.kern_K(prog, th, X)
+    dKo = orc.kern_dK(prog, th, X)
+    assert np.abs(K.cpu().numpy()[:, :n] - Ko).max() <= 1e-13 * max(1.0, np.abs(Ko).max())
+    for q in range(prog.n_theta):
+        assert np.abs(dK[q].cpu().numpy()[:, :n] - dKo[q]).max() <= 1e-12 * max(1.0, np.abs(dKo[q]).max())
+    K2 = torch.zeros_like(K)
+    engine.build_K(ep, th, Xd.data_ptr(), n, 4, K2.data_ptr(), ld)      # K-only path (symmetric tiles)
+    torch.cuda.synchronize()
+    assert np.abs(K2.cpu().numpy()[:, :n] - Ko).max() <= 1e-13 * max(1.0, np.abs(Ko).max())
+    assert torch.equal(K2[:, :n], K2[:, :n].T.contiguous())             # exactly symmetric
+    G = np.random.default_rng(5).standard_normal((n, n))
+    Gd = torch.from_numpy(G).cuda()
+    g = engine.kernel_grad(ep, th, Xd.data_ptr(), n, 4, Gd.data_ptr(), n)
+    go = orc.kern_grad(prog, th, X, G)
+    assert np.all(np.abs(g - go) <= 1e-10 * np.maximum(np.abs(go), 1e-3 * np.abs(go).max() + 1e-30))
+
+
+@pytest.mark.parametrize("n,batch", [(128, 1), (384, 3), (1152, 2), (2048, 1)])
+def test_potrf_trtri_against_lapack(engine, n, batch):
+    """jitchol / dtrtri stand-ins: L and L^-1 against NumPy's LAPACK on the same matrices."""
+    torch = _torch()
+    rng = np.random.default_rng(n)
+    G = rng.standard_normal((batch, n, n))
+    S = G @ G.transpose(0, 2, 1) / n + np.eye(n)
+    A = torch.from_numpy(S).cuda().contiguous()
+    Mi, Ui = torch.zeros_like(A), torch.zeros_like(A)
+    info = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    engine.potrf(A.data_ptr(), n, batch, Mi.data_ptr(), Ui.data_ptr(), info.data_ptr())
+    torch.cuda.synchronize()
+    assert info.cpu().tolist() == [0] * batch
+    for b in range(batch):
+        Lr = np.linalg.cholesky(S[b])
+        assert np.abs(np.tril(A[b].cpu().numpy()) - Lr).max() <= 1e-12
+        Wr = np.linalg.inv(Lr)
+        assert np.abs(np.tril(Mi[b].cpu().numpy()) - Wr).max() <= 1e-11
+        assert np.abs(np.triu(Ui[b].cpu().numpy()) - Wr.T).max() <= 1e-11
+
+
+def test_large_n_roundtrip_properties(engine):
+    """Size-independent properties at a size the oracle would take minutes for: L L^T = B, M L = I (n = 4096)."""
+    torch = _torch()
+    n = 4096
+    torch.manual_seed(0)
+    G = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    S = G @ G.T / n + torch.eye(n, dtype=torch.float64, device="cuda")
+    A = S.clone()
+    Mi, Ui = torch.zeros_like(A), torch.zeros_like(A)
+    engine.potrf(A.data_ptr(), n, 1, Mi.data_ptr(), Ui.data_ptr(), 0)
+    torch.cuda.synchronize()
+    L = torch.tril(A)
+    assert (L @ L.T - S).abs().max().item() <= 1e-12 * S.abs().max().item() * n ** 0.5
+    assert (torch.tril(Mi) @ L - torch.eye(n, dtype=torch.float64, device="cuda")).abs().max().item() <= 1e-11
+    assert torch.equal(torch.triu(Ui), torch.tril(Mi).T.contiguous())
+
+
+# ---- selection parity: the same search on the CUDA engine and on the oracle-backed engine -----------------------
+def test_search_selects_identical_structures_as_oracle(engine):
+    """north_star: identical selected kernel structure and ordering per search depth.  The host (grammar, restarts,
+    L-BFGS-B) is shared; only the scoring back end differs (CUDA engine vs tests/fake_engine.OracleEngine)."""
+    from autogpc_b200 import engine as eng_mod
+    from autogpc_b200 import gpckernel
+    from autogpc_b200.gpcdata import GPCData
+    from autogpc_b200.gpcsearch import GPCSearch
+    from tests.fake_engine import OracleEngine
+
+    def run(e, criterion):
+        eng_mod.set_default_engine(e)
+        gpckernel.set_rng(5)
+        X, y = synth(150, 3, 8)
+        d = GPCData(X, y.reshape(-1, 1), seed=1)
+        s = GPCSearch(d, base_kernels="SE,Lin,Per", max_depth=2, beam_width=1, criterion=criterion, n_folds=3, max_evals=30)
+        best, best1d = s.search()
+        return ([k.kernel.structure() for k in best], [[k.kernel.structure() for k in lvl] for lvl in s.history],
+                [[s.score(k) for k in lvl] for lvl in s.history])
+
+    try:
+        for criterion in ("bic", "error"):
+            bg, hg, sg = run(engine, criterion)
+            bo, ho, so = run(OracleEngine(), criterion)
+            assert bg == bo, (criterion, bg, bo)
+            assert hg == ho, (criterion, hg, ho)
+            for a, b in zip(sg, so):
+                assert np.allclose(a, b, rtol=1e-5, atol=1e-9)
+    finally:
+        eng_mod.set_default_engine(None)
