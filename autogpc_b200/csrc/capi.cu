@@ -212,6 +212,8 @@ int agpc_potrf(agpc_ctx* ctx, double* A, int32_t n, int32_t batch, double* Minv,
   ms.T = want_inv ? (double*)p : nullptr;
   if (make_tensor_map(&ms.mapA, ms.A, n, n, batch, n, ms.stride) || make_tensor_map(&ms.mapM, ms.M, n, n, batch, n, ms.stride) ||
       make_tensor_map(&ms.mapU, ms.U, n, n, batch, n, ms.stride) ||
+      make_tensor_map(&ms.mapA32, ms.A, n, n, batch, n, ms.stride, 32) ||
+      make_tensor_map(&ms.mapM32, ms.M, n, n, batch, n, ms.stride, 32) ||
       (want_inv && make_tensor_map(&ms.mapT, ms.T, n, n, batch, n, ms.stride)))
     return fail(ctx, AGPC_E_CUDA, "cuTensorMapEncodeTiled failed");
   Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches, &ctx->prof};

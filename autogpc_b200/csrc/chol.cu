@@ -13,13 +13,13 @@
 
 namespace agpc {
 
-constexpr int POTF2_THREADS = 512;
+constexpr int POTF2_THREADS = 256;
 constexpr int POTF2_LD = TILE + 1;
 constexpr int POTF2_SMEM = (TILE * POTF2_LD + 2 * TILE + TILE + 16) * 8;
 
 // One CTA per batch item factors the 128 x 128 diagonal block AND inverts its factor, entirely in registers.
 //
-// The square S (thread (ty, tx) of a 32 x 16 grid owns rows ty + 32a, columns tx + 16b: cyclic, so every thread
+// The square S (thread (ty, tx) of a 16 x 16 grid owns rows ty + 16a, columns tx + 16b, 8 x 8 each: cyclic, so every thread
 // stays busy as the active region shrinks) holds the lower triangle of A (-> L) and, transposed into its strict
 // upper triangle, the strict lower triangle of the running inverse W (W[i][c] at S[c][i]); diag(W) = 1 / diag(L) is
 // kept aside.  With that packing the right-looking Cholesky step and the forward-substitution step of W = L^-1 are
@@ -29,7 +29,131 @@ constexpr int POTF2_SMEM = (TILE * POTF2_LD + 2 * TILE + TILE + 16) * 8;
 //     S[:, j] *= 1 / sqrt(a_jj)     (final: columns <= j are never touched again)
 // Column j is broadcast through a double-buffered shared-memory vector, one __syncthreads per step; the owners of
 // column j + 1 update and publish it (and the pivot's reciprocal square root) before the bulk of step j, so the
-// sqrt / divide latency of the pivot sits off the critical path.
+// rsqrt latency of the pivot sits off the critical path.
+//
+// Masking is branch-free.  Element (r, q) is "lower" (part of A, live from the start) when r >= q and "upper"
+// (W[q][r], created at step r) otherwise; an upper element must not move before step r, which is arranged by
+// multiplying it with u_low (u with the rows r > j zeroed) instead of u.  Whether an element is lower is a
+// compile-time fact except on the 16 x 16 patches on the diagonal (a == b), where it is ty >= tx.
+struct Potf2Smem {
+  double* vbuf;   // [2][128] broadcast column
+  double* winv;   // [128]    1 / L_jj
+  double* ibuf;   // [2][4]   {1/a_jj, 1/sqrt(a_jj), sqrt(a_jj)}
+  int* badflag;
+};
+
+// publishes column jn, held in col[0..4) by the threads that own it, and its pivot terms
+__device__ __forceinline__ void potf2_publish(const Potf2Smem& sm, const double (&col)[8], int jn, int ty) {
+  double* vb = sm.vbuf + (jn & 1) * TILE;
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int r = ty + 16 * a;
+    vb[r] = col[a];
+    if (r == jn) {
+      double d = col[a];
+      if (!(d > 0.0) || !isfinite(d)) {
+        *sm.badflag = 1;
+        d = 1.0;
+      }
+      double rinv = rsqrt(d);  // MUFU.RSQ64H + Newton: short dependent chain
+      rinv = fma(fma(-d * rinv, rinv, 1.0), 0.5 * rinv, rinv);
+      double* ib = sm.ibuf + (jn & 1) * 4;
+      ib[0] = rinv * rinv;
+      ib[1] = rinv;
+      ib[2] = d * rinv;
+      sm.winv[jn] = rinv;
+    }
+  }
+}
+
+template <int A, int B>
+__device__ __forceinline__ void potf2_row_update(double (&s)[8][8], const double (&uf)[8], const double (&ul)[8],
+                                                 bool diag_lower, double t) {
+  // patch (A, B): rows 16A.., columns 16B..: below the diagonal for A > B, above it for A < B
+  const double um = (A > B) ? uf[A] : (A < B) ? ul[A] : (diag_lower ? uf[A] : ul[A]);
+  s[A][B] = fma(um, t, s[A][B]);
+}
+
+template <int B>
+__device__ __forceinline__ void potf2_col_update(double (&s)[8][8], const double (&uf)[8], const double (&ul)[8],
+                                                 bool diag_lower, double t) {
+  potf2_row_update<0, B>(s, uf, ul, diag_lower, t);
+  potf2_row_update<1, B>(s, uf, ul, diag_lower, t);
+  potf2_row_update<2, B>(s, uf, ul, diag_lower, t);
+  potf2_row_update<3, B>(s, uf, ul, diag_lower, t);
+  potf2_row_update<4, B>(s, uf, ul, diag_lower, t);
+  potf2_row_update<5, B>(s, uf, ul, diag_lower, t);
+  potf2_row_update<6, B>(s, uf, ul, diag_lower, t);
+  potf2_row_update<7, B>(s, uf, ul, diag_lower, t);
+}
+
+template <int BJ, int B>
+__device__ __forceinline__ void potf2_rest(double (&s)[8][8], const double (&uf)[8], const double (&ul)[8],
+                                           bool diag_lower, const double* v, double inv, int tx) {
+  if constexpr (B < 8) {
+    const double t = v[tx + 16 * B] * inv;
+    potf2_col_update<B>(s, uf, ul, diag_lower, t);
+    potf2_rest<BJ, B + 1>(s, uf, ul, diag_lower, v, inv, tx);
+  }
+}
+
+// the 16 columns j = 16 BJ .. 16 BJ + 15
+template <int BJ>
+__device__ __forceinline__ void potf2_group(double (&s)[8][8], const Potf2Smem& sm, bool diag_lower, int tx, int ty) {
+#pragma unroll 1
+  for (int jj = 0; jj < 16; ++jj) {
+    const int j = 16 * BJ + jj;
+    const double* v = sm.vbuf + (j & 1) * TILE;
+    const double* ib = sm.ibuf + (j & 1) * 4;
+    const double inv = ib[0];
+    double uf[8], ul[8];  // -u for lower elements, -u_low for upper elements
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      const double vr = v[ty + 16 * a];
+      // rows of 16-row groups a < BJ are all <= j, rows of groups a > BJ are all > j
+      if (a < BJ) {
+        uf[a] = -vr;
+        ul[a] = -vr;
+      } else if (a > BJ) {
+        uf[a] = -vr;
+        ul[a] = 0.0;
+      } else {
+        uf[a] = (ty == jj) ? -1.0 : -vr;
+        ul[a] = (ty <= jj) ? uf[a] : 0.0;
+      }
+    }
+    // column j is final
+    {
+      const double rinv = ib[1], piv = ib[2];
+      const bool own = tx == jj;
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        double fin = s[a][BJ] * rinv;
+        if (a == BJ) fin = (ty == jj) ? piv : fin;
+        s[a][BJ] = own ? fin : s[a][BJ];
+      }
+    }
+    // columns of this 16-group first (lanes tx > jj), so that column j + 1 can be published early
+    {
+      const double t = (tx > jj) ? v[tx + 16 * BJ] * inv : 0.0;
+      potf2_col_update<BJ>(s, uf, ul, diag_lower, t);
+    }
+    if (jj < 15 && tx == jj + 1) {
+      const double col[8] = {s[0][BJ], s[1][BJ], s[2][BJ], s[3][BJ], s[4][BJ], s[5][BJ], s[6][BJ], s[7][BJ]};
+      potf2_publish(sm, col, j + 1, ty);
+    }
+    potf2_rest<BJ, BJ + 1>(s, uf, ul, diag_lower, v, inv, tx);
+    if constexpr (BJ < 7) {
+      if (jj == 15 && tx == 0) {
+        const double col[8] = {s[0][BJ + 1], s[1][BJ + 1], s[2][BJ + 1], s[3][BJ + 1],
+                               s[4][BJ + 1], s[5][BJ + 1], s[6][BJ + 1], s[7][BJ + 1]};
+        potf2_publish(sm, col, j + 1, ty);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(POTF2_THREADS, 1)
 potf2_inv_kernel(double* __restrict__ A, double* __restrict__ M, double* __restrict__ U, long long ld,
                  long long batch_stride, int diag_block, const int* __restrict__ active, int* __restrict__ info) {
@@ -37,105 +161,46 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ M, double* __restr
   if (active != nullptr && active[bi] == 0) return;
   extern __shared__ double smem[];
   double* stage = smem;                      // [128][129] output transposition buffer
-  double* vbuf = smem + TILE * POTF2_LD;     // [2][128]   broadcast column
-  double* winv = vbuf + 2 * TILE;            // [128]      1 / L_jj
-  double* ibuf = winv + TILE;                // [2][4]     {1/a_jj, 1/sqrt(a_jj), sqrt(a_jj)}
-  int* badflag = reinterpret_cast<int*>(ibuf + 8);
+  Potf2Smem sm;
+  sm.vbuf = smem + TILE * POTF2_LD;
+  sm.winv = sm.vbuf + 2 * TILE;
+  sm.ibuf = sm.winv + TILE;
+  sm.badflag = reinterpret_cast<int*>(sm.ibuf + 8);
   const long long base = (long long)bi * batch_stride + (long long)diag_block * TILE * ld + (long long)diag_block * TILE;
   double* Ab = A + base;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  if (tid == 0) *badflag = 0;
+  if (tid == 0) *sm.badflag = 0;
 
-  double s[4][8];
+  double s[8][8];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < 8; ++a)
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
-      const int r = ty + 32 * a, q = tx + 16 * b;
+      const int r = ty + 16 * a, q = tx + 16 * b;
       s[a][b] = (q <= r) ? Ab[(long long)r * ld + q] : 0.0;
     }
-
-  // publishes column jn (held in s[.][B] by the threads with tx == jn % 16) and its pivot terms
-#define POTF2_PUBLISH(B, jn)                                            \
-  {                                                                     \
-    double* vb_ = vbuf + ((jn)&1) * TILE;                               \
-    _Pragma("unroll") for (int a = 0; a < 4; ++a) {                     \
-      const int r = ty + 32 * a;                                        \
-      vb_[r] = s[a][B];                                                 \
-      if (r == (jn)) {                                                  \
-        double d = s[a][B];                                             \
-        if (!(d > 0.0) || !isfinite(d)) {                               \
-          *badflag = 1;                                                 \
-          d = 1.0;                                                      \
-        }                                                               \
-        double rinv = rsqrt(d); /* MUFU.RSQ64H + Newton: short chain */ \
-        rinv = fma(fma(-d * rinv, rinv, 1.0), 0.5 * rinv, rinv);        \
-        const double piv = d * rinv;                                    \
-        double* ib_ = ibuf + ((jn)&1) * 4;                              \
-        ib_[0] = rinv * rinv;                                           \
-        ib_[1] = rinv;                                                  \
-        ib_[2] = piv;                                                   \
-        winv[(jn)] = rinv;                                              \
-      }                                                                 \
-    }                                                                   \
+  const bool diag_lower = ty >= tx;
+  __syncthreads();
+  if (tx == 0) {
+    const double col[8] = {s[0][0], s[1][0], s[2][0], s[3][0], s[4][0], s[5][0], s[6][0], s[7][0]};
+    potf2_publish(sm, col, 0, ty);
   }
-
-  if (tx == 0) POTF2_PUBLISH(0, 0)
   __syncthreads();
 
-#pragma unroll
-  for (int bj = 0; bj < 8; ++bj) {
-#pragma unroll 1
-    for (int jj = 0; jj < 16; ++jj) {
-      const int j = 16 * bj + jj;
-      const double* v = vbuf + (j & 1) * TILE;
-      const double* ib = ibuf + (j & 1) * 4;
-      const double inv = ib[0];
-      double u[4];
-      bool low[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int r = ty + 32 * a;
-        const double vr = v[r];
-        u[a] = (r == j) ? -1.0 : -vr;
-        low[a] = r <= j;
-      }
-      // column j is final
-      if (tx == jj) {
-        const double rinv = ib[1], piv = ib[2];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) s[a][bj] = (ty + 32 * a == j) ? piv : s[a][bj] * rinv;
-      }
-      // columns of this 16-group first, so that column j + 1 can be published early
-      {
-        const int q = tx + 16 * bj;
-        const double t = v[q] * inv;
-        if (tx > jj) {
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-            if (low[a] || ty + 32 * a >= q) s[a][bj] = fma(u[a], t, s[a][bj]);
-        }
-      }
-      if (jj < 15 && tx == jj + 1) POTF2_PUBLISH(bj, j + 1)
-#pragma unroll
-      for (int b = bj + 1; b < 8; ++b) {
-        const int q = tx + 16 * b;
-        const double t = v[q] * inv;
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-          if (low[a] || ty + 32 * a >= q) s[a][b] = fma(u[a], t, s[a][b]);
-      }
-      if (jj == 15 && bj < 7 && tx == 0) POTF2_PUBLISH((bj < 7 ? bj + 1 : 7), j + 1)
-      __syncthreads();
-    }
-  }
-#undef POTF2_PUBLISH
+  potf2_group<0>(s, sm, diag_lower, tx, ty);
+  potf2_group<1>(s, sm, diag_lower, tx, ty);
+  potf2_group<2>(s, sm, diag_lower, tx, ty);
+  potf2_group<3>(s, sm, diag_lower, tx, ty);
+  potf2_group<4>(s, sm, diag_lower, tx, ty);
+  potf2_group<5>(s, sm, diag_lower, tx, ty);
+  potf2_group<6>(s, sm, diag_lower, tx, ty);
+  potf2_group<7>(s, sm, diag_lower, tx, ty);
 
   // transpose through shared memory so that L, W and W^T all leave with coalesced row writes
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < 8; ++a)
 #pragma unroll
-    for (int b = 0; b < 8; ++b) stage[(ty + 32 * a) * POTF2_LD + tx + 16 * b] = s[a][b];
+    for (int b = 0; b < 8; ++b) stage[(ty + 16 * a) * POTF2_LD + tx + 16 * b] = s[a][b];
   __syncthreads();
   double* Mb = M + base;
   double* Ub = U + base;
@@ -143,11 +208,11 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ M, double* __restr
     const int i = idx / TILE, jx = idx % TILE;
     const double sij = stage[i * POTF2_LD + jx];
     if (jx <= i) Ab[(long long)i * ld + jx] = sij;
-    const double wd = winv[i];
+    const double wd = sm.winv[i];
     Mb[(long long)i * ld + jx] = (jx < i) ? stage[jx * POTF2_LD + i] : (jx == i ? wd : 0.0);  // W[i][jx]
     Ub[(long long)i * ld + jx] = (jx > i) ? sij : (jx == i ? wd : 0.0);                       // W[jx][i]
   }
-  if (tid == 0 && *badflag != 0 && info != nullptr) info[bi] = AGPC_ST_NOT_PD;
+  if (tid == 0 && *sm.badflag != 0 && info != nullptr) info[bi] = AGPC_ST_NOT_PD;
 }
 
 cudaError_t potf2_inv_launch(const Launch& L, double* A, double* M, double* U, long long ld, long long batch_stride,
@@ -164,30 +229,92 @@ cudaError_t potf2_inv_launch(const Launch& L, double* A, double* M, double* U, l
 }
 
 // ---- drivers -----------------------------------------------------------------------------------------------
+// dst[r][c0 .. c0 + 128) = src[r][c0 .. c0 + 128) for rows r0 .. r0 + rows (one 128-wide panel, per batch item)
+__global__ void copy_panel_kernel(const double* __restrict__ src, double* __restrict__ dst, long long ld,
+                                  long long batch_stride, int r0, int c0, int rows, const int* __restrict__ active) {
+  const int b = blockIdx.y;
+  if (active != nullptr && active[b] == 0) return;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one double2 each
+  const int r = (int)(idx / (TILE / 2)), c = (int)(idx % (TILE / 2)) * 2;
+  if (r >= rows) return;
+  const long long o = (long long)b * batch_stride + (long long)(r0 + r) * ld + c0 + c;
+  *reinterpret_cast<double2*>(dst + o) = *reinterpret_cast<const double2*>(src + o);
+}
+static cudaError_t copy_panel_launch(const Launch& L, const double* src, double* dst, long long ld, long long batch_stride,
+                                     int r0, int c0, int rows, int batch, const int* active) {
+  ProfScope prof_scope(L, CLS_MISC);
+  const long long n2 = (long long)rows * (TILE / 2);
+  dim3 grid((unsigned)((n2 + 255) / 256), batch);
+  copy_panel_kernel<<<grid, 256, 0, L.stream>>>(src, dst, ld, batch_stride, r0, c0, rows, active);
+  L.bump();
+  return cudaGetLastError();
+}
+
+// Two-level blocking: 128-wide panels (the potf2_inv / trsm grain) grouped into outer blocks of POTRF_OUTER panels.
+// Inside an outer block the algorithm is left-looking (panel k is updated by the block's earlier panels, K <= 384);
+// the trailing matrix is updated once per outer block with K = 512, where the tile GEMM runs close to its DGEMM rate
+// (a K = 128 rank update pays the TMA prologue and the C round trip once per 8 k-iterations: 24 vs 33+ TFLOP/s).
+constexpr int POTRF_OUTER = 4;
+// one-tile-wide launches with fewer CTAs than this run as 128 x 32 tiles (4x the CTAs, a quarter of the latency)
+constexpr int THIN_CTA_LIMIT = 160;
+
 cudaError_t potrf_blocked(const Launch& L, const MatSet& ms, const int* active, int* info) {
   const int nblk = ms.np / TILE;
   const double wn = L.work_n > 0.0 ? L.work_n : (double)ms.np;
   L.add_work(CLS_GEMM, (double)L.work_items * wn * wn * wn / 3.0);  // LAPACK dpotrf count
-  for (int k = 0; k < nblk; ++k) {
-    AGPC_CUDA_TRY(potf2_inv_launch(L, ms.A, ms.M, ms.U, ms.np, ms.stride, k, ms.batch, active, info));
-    const int below = nblk - k - 1;
-    if (below == 0) break;
-    GemmArgs t{};
-    t.C = ms.A; t.Ct = nullptr; t.ldc = ms.np; t.c_batch = ms.stride;
-    t.a_row0 = (k + 1) * TILE; t.a_col0 = k * TILE;      // P_old (in place)
-    t.b_row0 = k * TILE; t.b_col0 = k * TILE;            // W_k from M's diagonal block
-    t.c_row0 = (k + 1) * TILE; t.c_col0 = k * TILE;
-    t.m_tiles = below; t.n_tiles = 1; t.k_tiles = TILE / GEMM_BK;
-    t.k_rule = KRULE_FULL; t.lower_only = 0; t.alpha = 1.0; t.beta = 0.0; t.active = active;
-    AGPC_CUDA_TRY(gemm_nt_launch(L, ms.mapA, ms.mapM, t, below, 1, ms.batch));
+  for (int k0 = 0; k0 < nblk; k0 += POTRF_OUTER) {
+    const int kb = nblk - k0 < POTRF_OUTER ? nblk - k0 : POTRF_OUTER;
+    for (int t = 0; t < kb; ++t) {
+      const int k = k0 + t;
+      if (t > 0) {
+        // A[k:, k] -= A[k:, k0:k] A[k, k0:k]^T
+        GemmArgs u{};
+        u.C = ms.A; u.Ct = nullptr; u.ldc = ms.np; u.c_batch = ms.stride;
+        u.a_row0 = k * TILE; u.a_col0 = k0 * TILE;
+        u.b_row0 = k * TILE; u.b_col0 = k0 * TILE;
+        u.c_row0 = k * TILE; u.c_col0 = k * TILE;
+        u.m_tiles = nblk - k; u.n_tiles = 1; u.k_tiles = t * (TILE / GEMM_BK);
+        u.k_rule = KRULE_FULL; u.lower_only = 0; u.alpha = -1.0; u.beta = 1.0; u.active = active;
+        if ((nblk - k) * ms.batch <= THIN_CTA_LIMIT) {
+          u.n_tiles = TILE / 32;
+          AGPC_CUDA_TRY(gemm_nt_thin_launch(L, ms.mapA, ms.mapA32, u, (nblk - k) * u.n_tiles, 1, ms.batch));
+        } else {
+          AGPC_CUDA_TRY(gemm_nt_launch(L, ms.mapA, ms.mapA, u, nblk - k, 1, ms.batch));
+        }
+      }
+      AGPC_CUDA_TRY(potf2_inv_launch(L, ms.A, ms.M, ms.U, ms.np, ms.stride, k, ms.batch, active, info));
+      const int below = nblk - k - 1;
+      if (below == 0) break;
+      // panel solve through the inverse: A[k+1:, k] <- A[k+1:, k] W_k^T  (in place; W_k = L_kk^-1 is lower: K clipped)
+      GemmArgs p{};
+      p.C = ms.A; p.Ct = nullptr; p.ldc = ms.np; p.c_batch = ms.stride;
+      p.a_row0 = (k + 1) * TILE; p.a_col0 = k * TILE;
+      p.b_row0 = k * TILE; p.b_col0 = k * TILE;  // W_k from M's diagonal block
+      p.c_row0 = (k + 1) * TILE; p.c_col0 = k * TILE;
+      p.m_tiles = below; p.n_tiles = 1; p.k_tiles = TILE / GEMM_BK;
+      p.k_rule = KRULE_END_AT_COL; p.lower_only = 0; p.alpha = 1.0; p.beta = 0.0; p.active = active;
+      if (below * ms.batch <= THIN_CTA_LIMIT) {
+        // four CTAs share one 128-row operand tile here, so the solve cannot run in place: stage the panel in the
+        // (still unused) strictly-lower part of M and read it from there
+        AGPC_CUDA_TRY(copy_panel_launch(L, ms.A, ms.M, ms.np, ms.stride, (k + 1) * TILE, k * TILE, below * TILE,
+                                        ms.batch, active));
+        p.n_tiles = TILE / 32;
+        AGPC_CUDA_TRY(gemm_nt_thin_launch(L, ms.mapM, ms.mapM32, p, below * p.n_tiles, 1, ms.batch));
+      } else {
+        AGPC_CUDA_TRY(gemm_nt_launch(L, ms.mapA, ms.mapM, p, below, 1, ms.batch));
+      }
+    }
+    const int rest = nblk - k0 - kb;
+    if (rest <= 0) break;
+    // trailing update with the whole outer block: A[r:, r:] -= A[r:, k0:r] A[r:, k0:r]^T, lower tiles only
     GemmArgs s{};
     s.C = ms.A; s.Ct = nullptr; s.ldc = ms.np; s.c_batch = ms.stride;
-    s.a_row0 = (k + 1) * TILE; s.a_col0 = k * TILE;
-    s.b_row0 = (k + 1) * TILE; s.b_col0 = k * TILE;
-    s.c_row0 = (k + 1) * TILE; s.c_col0 = (k + 1) * TILE;
-    s.m_tiles = below; s.n_tiles = below; s.k_tiles = TILE / GEMM_BK;
+    s.a_row0 = (k0 + kb) * TILE; s.a_col0 = k0 * TILE;
+    s.b_row0 = (k0 + kb) * TILE; s.b_col0 = k0 * TILE;
+    s.c_row0 = (k0 + kb) * TILE; s.c_col0 = (k0 + kb) * TILE;
+    s.m_tiles = rest; s.n_tiles = rest; s.k_tiles = kb * (TILE / GEMM_BK);
     s.k_rule = KRULE_FULL; s.lower_only = 1; s.alpha = -1.0; s.beta = 1.0; s.active = active;
-    AGPC_CUDA_TRY(gemm_nt_launch(L, ms.mapA, ms.mapA, s, below * (below + 1) / 2, 1, ms.batch));
+    AGPC_CUDA_TRY(gemm_nt_launch(L, ms.mapA, ms.mapA, s, rest * (rest + 1) / 2, 1, ms.batch));
   }
   return cudaSuccess;
 }

@@ -96,7 +96,9 @@ cudaError_t gemm_nt_launch(const Launch& L, const CUtensorMap& mapA, const CUten
                            int tiles_x, int groups, int batch);
 // Encodes a 3-D FP64 tensor map {cols, rows, batch} with a {16, 128, 1} box and 128-byte swizzle.
 int make_tensor_map(CUtensorMap* out, const double* base, long long cols, long long rows, long long batch,
-                    long long ld, long long batch_stride);
+                    long long ld, long long batch_stride, int box_rows = TILE);
+cudaError_t gemm_nt_thin_launch(const Launch& L, const CUtensorMap& mapA, const CUtensorMap& mapB32,
+                                const GemmArgs& args, int tiles_x, int groups, int batch);
 
 // One lock-step batch of padded np x np matrices (np % 128 == 0, ld == np, matrix b at base + b*stride) and the
 // tensor maps the GEMM kernel reads them through.
@@ -107,6 +109,7 @@ struct MatSet {
   long long stride = 0;
   double *K = nullptr, *A = nullptr, *M = nullptr, *U = nullptr, *T = nullptr;
   CUtensorMap mapA, mapM, mapU, mapT;
+  CUtensorMap mapA32, mapM32;  // 32-row boxes: B operands of the thin GEMM variant
 };
 
 // chol.cu

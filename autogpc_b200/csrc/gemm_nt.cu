@@ -61,9 +61,14 @@ __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, doubl
                : "d"(a), "d"(b));
 }
 
+// NJ = 4: 128 x 128 C tile (the throughput shape).  NJ = 1: 128 x 32 C tile for the thin, latency-bound launches of
+// a single-matrix factorisation (panel solve, in-block panel update), which would otherwise leave most SMs idle;
+// the B operand then comes through a tensor map with a 32-row box.  n_tiles / tj count BN-wide column tiles.
+template <int NJ>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const GemmArgs args) {
+  constexpr int BN = 32 * NJ;
   const int b = blockIdx.z;
   if (args.active != nullptr && args.active[b] == 0) return;
   const int g = blockIdx.y;
@@ -95,12 +100,13 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   int k_begin = 0, k_end = kt;
   if (args.k_rule == KRULE_BEGIN_AT_ROW) k_begin = ti * (TILE / GEMM_BK);
   if (args.k_rule == KRULE_END_AT_ROW) k_end = min(kt, (ti + 1) * (TILE / GEMM_BK));
-  if (args.k_rule == KRULE_END_AT_COL) k_end = min(kt, (tj + 1) * (TILE / GEMM_BK));
+  if (args.k_rule == KRULE_END_AT_COL) k_end = min(kt, (tj + 1) * (BN / GEMM_BK));
   const int n_iter = k_end - k_begin;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  constexpr uint32_t STAGE_BYTES = TILE * GEMM_BK * 8;  // 16 KB per operand per stage
+  constexpr uint32_t STAGE_BYTES = TILE * GEMM_BK * 8;  // 16 KB per operand per stage (B uses BN / 128 of it)
+  constexpr uint32_t B_BYTES = BN * GEMM_BK * 8;
   const uint32_t sA = smem_base;
   const uint32_t sB = smem_base + GEMM_STAGES * STAGE_BYTES;
   const uint32_t bars = sB + GEMM_STAGES * STAGE_BYTES;  // full[0..S), empty[0..S): 8 bytes each
@@ -119,13 +125,13 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // ---------------- TMA producer ----------------
     if (lane == 0) {
       const int a_row = args.a_row0 + shift + ti * TILE, a_col = args.a_col0 + shift;
-      const int b_row = args.b_row0 + shift + tj * TILE, b_col = args.b_col0 + shift;
+      const int b_row = args.b_row0 + shift + tj * BN, b_col = args.b_col0 + shift;
       for (int it = 0; it < n_iter; ++it) {
         const int s = it % GEMM_STAGES;
         const uint32_t ph = (uint32_t)(it / GEMM_STAGES) & 1u;
         mbar_wait(bars + 8 * (GEMM_STAGES + s), ph ^ 1u);
         const uint32_t full = bars + 8 * s;
-        mbar_expect_tx(full, 2 * STAGE_BYTES);
+        mbar_expect_tx(full, STAGE_BYTES + B_BYTES);
         const int kc = (k_begin + it) * GEMM_BK;
         tma_load_3d(sA + s * STAGE_BYTES, &mapA, full, a_col + kc, a_row, b);
         tma_load_3d(sB + s * STAGE_BYTES, &mapB, full, b_col + kc, b_row, b);
@@ -141,21 +147,21 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const uint32_t lane_off = (uint32_t)gid * 128u + (uint32_t)(tig & 1) * 8u;
   const uint32_t chunk0 = ((uint32_t)((tig >> 1) << 2) ^ (uint32_t)gid) << 4;
   const uint32_t a_off = (uint32_t)(wm * 32) * 128u + lane_off;
-  const uint32_t b_off = (uint32_t)(wn * 32) * 128u + lane_off;
+  const uint32_t b_off = (uint32_t)(wn * 8 * NJ) * 128u + lane_off;
 
   // C is folded in up front (acc = (beta / alpha) C, result = alpha acc): its load latency then overlaps the TMA
   // prologue instead of sitting between the last DMMA and the store, which matters for the K = 128 rank updates.
   const long long row0 = (long long)args.c_row0 + shift + ti * TILE + wm * 32 + gid;
-  const long long col0 = (long long)args.c_col0 + shift + tj * TILE + wn * 32 + tig * 2;
+  const long long col0 = (long long)args.c_col0 + shift + tj * BN + wn * (8 * NJ) + tig * 2;
   double* Cb = args.C + (long long)b * args.c_batch;
   const double alpha = args.alpha;
-  double acc[4][4][2];
+  double acc[4][NJ][2];
   if (args.beta != 0.0) {
     const double pre = args.beta / alpha;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NJ; ++j) {
         const double2 old = *reinterpret_cast<const double2*>(Cb + (row0 + i * 8) * args.ldc + col0 + j * 8);
         acc[i][j][0] = pre * old.x;
         acc[i][j][1] = pre * old.y;
@@ -164,7 +170,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   }
 
   for (int it = 0; it < n_iter; ++it) {
@@ -176,15 +182,15 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
     for (int jp = 0; jp < 4; ++jp) {
       const uint32_t ck = chunk0 ^ (uint32_t)(jp << 4);
-      double af[4], bf[4];
+      double af[4], bf[NJ];
 #pragma unroll
       for (int i = 0; i < 4; ++i) af[i] = lds_f64(pa + i * 1024 + ck);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bf[j] = lds_f64(pb + j * 1024 + ck);
+      for (int j = 0; j < NJ; ++j) bf[j] = lds_f64(pb + j * 1024 + ck);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        for (int j = 0; j < NJ; ++j) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(bars + 8 * (GEMM_STAGES + s));
@@ -194,7 +200,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NJ; ++j) {
       double2 v;
       v.x = alpha * acc[i][j][0];
       v.y = alpha * acc[i][j][1];
@@ -204,13 +210,13 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   }
   if (args.Ct != nullptr) {
-    const long long trow0 = (long long)args.ct_row0 + shift + tj * TILE + wn * 32 + tig * 2;
+    const long long trow0 = (long long)args.ct_row0 + shift + tj * BN + wn * (8 * NJ) + tig * 2;
     const long long tcol0 = (long long)args.ct_col0 + shift + ti * TILE + wm * 32 + gid;
     double* Tb = args.Ct + (long long)b * args.c_batch;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NJ; ++j) {
         Tb[(trow0 + j * 8) * args.ldc + tcol0 + i * 8] = acc[i][j][0];
         Tb[(trow0 + j * 8 + 1) * args.ldc + tcol0 + i * 8] = acc[i][j][1];
       }
@@ -222,12 +228,29 @@ cudaError_t gemm_nt_launch(const Launch& L, const CUtensorMap& mapA, const CUten
   ProfScope prof_scope(L, CLS_GEMM);
   static bool configured = false;
   if (!configured) {
-    AGPC_CUDA_TRY(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    AGPC_CUDA_TRY(cudaFuncSetAttribute(gemm_nt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    AGPC_CUDA_TRY(cudaFuncSetAttribute(gemm_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     configured = true;
   }
   if (tiles_x <= 0 || groups <= 0 || batch <= 0) return cudaSuccess;
   dim3 grid(tiles_x, groups, batch);
-  gemm_nt_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, L.stream>>>(mapA, mapB, args);
+  gemm_nt_kernel<4><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, L.stream>>>(mapA, mapB, args);
+  L.bump();
+  return cudaGetLastError();
+}
+
+// thin variant: args.n_tiles counts 32-wide column tiles; mapB must have a 32-row box (make_tensor_map box_rows = 32)
+cudaError_t gemm_nt_thin_launch(const Launch& L, const CUtensorMap& mapA, const CUtensorMap& mapB32,
+                                const GemmArgs& args, int tiles_x, int groups, int batch) {
+  ProfScope prof_scope(L, CLS_GEMM);
+  static bool configured = false;
+  if (!configured) {
+    AGPC_CUDA_TRY(cudaFuncSetAttribute(gemm_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    configured = true;
+  }
+  if (tiles_x <= 0 || groups <= 0 || batch <= 0) return cudaSuccess;
+  dim3 grid(tiles_x, groups, batch);
+  gemm_nt_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, L.stream>>>(mapA, mapB32, args);
   L.bump();
   return cudaGetLastError();
 }
@@ -250,13 +273,13 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int make_tensor_map(CUtensorMap* out, const double* base, long long cols, long long rows, long long batch,
-                    long long ld, long long batch_stride) {
+                    long long ld, long long batch_stride, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return AGPC_E_CUDA;
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 8ull, (cuuint64_t)batch_stride * 8ull};
   if (batch == 1) strides[1] = (cuuint64_t)ld * 8ull * (cuuint64_t)rows;
-  cuuint32_t box[3] = {GEMM_BK, TILE, 1};
+  cuuint32_t box[3] = {GEMM_BK, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -210,16 +210,180 @@ build_K_kernel(const BuildArgs a) {
   }
 }
 
+// ---- K build, register micro-tiled and symmetric ------------------------------------------------------------------
+// One CTA = one 64 x 64 tile, 256 threads, 4 x 4 pairs per thread (rows ty + 16r, columns tx + 16c).  The kernel
+// program is walked ONCE per thread with the leaf constants in registers and applied to all 16 pairs, so the
+// interpreter cost (the issue-bound part of build_K_kernel: 89 % SM busy at 24 % of HBM, profiles/r01_summary.md) is
+// amortised 16x.  When Xa == Xb (training K) only the tiles on or below the diagonal are evaluated; each is also
+// written transposed through shared memory, which halves the exp / sincos work per stored element -- that, not
+// HBM, is what bounds this kernel for anything beyond a single SE term.
+constexpr int KT = 64, KT_THREADS = 256, KT_LD = KT + 1;
+
+__global__ void __launch_bounds__(KT_THREADS, 3)
+build_K_tiled_kernel(const BuildArgs a, const int symmetric, const int tiles_n) {
+  const int b = blockIdx.z;
+  if (a.active != nullptr && a.active[b] == 0) return;
+  extern __shared__ double smem[];
+  __shared__ ProgShared P;
+  const int D = a.D;
+  double* xr = smem;                // [D][KT]
+  double* xc = smem + D * KT;       // [D][KT]
+  double* st = xc + D * KT;         // [KT][KT_LD] transposition buffer (symmetric mode)
+  int ti, tj;
+  if (symmetric) {
+    const int t = blockIdx.x;
+    ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while (ti * (ti + 1) / 2 > t) --ti;
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    tj = t - ti * (ti + 1) / 2;
+  } else {
+    ti = blockIdx.x / tiles_n;
+    tj = blockIdx.x % tiles_n;
+  }
+  const int row0 = ti * KT, col0 = tj * KT;
+  const int na = a.na_of ? a.na_of[b] : a.na_fixed, nb = a.nb_of ? a.nb_of[b] : a.nb_fixed;
+  load_program(P, a.progs[b], a.theta + (long long)b * a.theta_stride);
+  const double* Xa = a.Xa + (long long)b * a.xa_batch;
+  const double* Xb = a.Xb + (long long)b * a.xb_batch;
+  for (int idx = threadIdx.x; idx < KT * D; idx += KT_THREADS) {
+    const int r = idx / D, d = idx % D;
+    xr[d * KT + r] = (row0 + r < a.na_pad) ? Xa[(long long)(row0 + r) * D + d] : 0.0;
+    xc[d * KT + r] = (col0 + r < a.nb_pad) ? Xb[(long long)(col0 + r) * D + d] : 0.0;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+
+  // two passes of 2 x 4 pairs (rows ty + 16r, r = 2h, 2h + 1): keeps the live set near 80 registers -> 3 CTAs per SM,
+  // which is what hides the load -> compute -> store latency chain of a tile (the kernel is latency-, not ALU-bound)
+  double* out = a.out + (long long)b * a.out_batch;
+  const bool mirror = symmetric && ti != tj;
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    double K[2][4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) K[r][c] = 0.0;
+    const int n_terms = P.n_terms;
+    for (int t = 0; t < n_terms; ++t) {
+      const int len = P.term_len[t];
+      double arg[2][4];
+      double mr[2] = {1.0, 1.0}, mc[4] = {1.0, 1.0, 1.0, 1.0};  // LIN factors are separable: rows x columns
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) arg[r][c] = 0.0;
+      double scale = 1.0;
+      bool has_exp = false, has_mult = false;
+      for (int p = 0; p < len; ++p) {
+        const LeafConst& lc = P.leaf[P.term_leaf[t][p]];
+        scale *= lc.var;
+        if (lc.type == AGPC_LEAF_CONST) continue;
+        double xi[2], xj[4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) xi[r] = xr[lc.dim * KT + ty + 16 * (2 * h + r)];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) xj[c] = xc[lc.dim * KT + tx + 16 * c];
+        if (lc.type == AGPC_LEAF_SE) {
+          has_exp = true;
+          const double ha = 0.5 * lc.a;
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const double d = xi[r] - xj[c];
+              arg[r][c] -= ha * d * d;
+            }
+        } else if (lc.type == AGPC_LEAF_PER) {
+          has_exp = true;
+          const double w = M_PI * lc.a, hb = 0.5 * lc.b;
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const double sn = sin(w * (xi[r] - xj[c]));  // GPy: np.sin(np.pi * r / T)
+              arg[r][c] -= hb * sn * sn;
+            }
+        } else {  // LIN
+          has_mult = true;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) mr[r] *= xi[r] - lc.a;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) mc[c] *= xj[c] - lc.a;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          double v = scale;
+          if (has_mult) v *= mr[r] * mc[c];
+          if (has_exp) v *= exp(arg[r][c]);
+          K[r][c] += v;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int lr = ty + 16 * (2 * h + r);
+      const int i = row0 + lr;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = col0 + tx + 16 * c;
+        if (!(i < na && j < nb)) K[r][c] = 0.0;
+        if (i < a.na_pad && j < a.ld) out[(long long)i * a.ld + j] = K[r][c];
+        if (a.kdiag != nullptr && i == j && i < a.na_pad && ti == tj) a.kdiag[(long long)b * a.na_pad + i] = K[r][c];
+        if (mirror) st[lr * KT_LD + tx + 16 * c] = K[r][c];
+      }
+    }
+  }
+  if (mirror) {
+    __syncthreads();
+    // mirror tile: rows col0.., columns row0..; element (jj, ii) = st[ii][jj]
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int jrow = col0 + ty + 16 * r;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int icol = row0 + tx + 16 * c;
+        if (jrow < a.na_pad && icol < a.ld) out[(long long)jrow * a.ld + icol] = st[(tx + 16 * c) * KT_LD + ty + 16 * r];
+      }
+    }
+  }
+}
+
 cudaError_t build_K_launch(const Launch& L, const BuildArgs& a, int batch, bool grad) {
   ProfScope prof_scope(L, CLS_KBUILD);
-  dim3 grid((unsigned)((a.ld + KB_COLS - 1) / KB_COLS), (unsigned)((a.na_pad + KB_ROWS - 1) / KB_ROWS), batch);
-  const size_t smem = sizeof(double) * a.D * (KB_ROWS + KB_COLS);
-  if (grad)
+  if (grad) {
+    dim3 grid((unsigned)((a.ld + KB_COLS - 1) / KB_COLS), (unsigned)((a.na_pad + KB_ROWS - 1) / KB_ROWS), batch);
+    const size_t smem = sizeof(double) * a.D * (KB_ROWS + KB_COLS);
     build_K_kernel<true><<<grid, KB_THREADS, smem, L.stream>>>(a);
-  else
-    build_K_kernel<false><<<grid, KB_THREADS, smem, L.stream>>>(a);
+    L.bump();
+    return cudaGetLastError();
+  }
+  static bool configured = false;
+  const size_t smem = sizeof(double) * (2 * (size_t)a.D * KT + KT * KT_LD);
+  if (!configured || smem > 48 * 1024) {
+    AGPC_CUDA_TRY(cudaFuncSetAttribute(build_K_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(smem > 100 * 1024 ? smem : 100 * 1024)));
+    configured = true;
+  }
+  // symmetric when both point sets are the same array and the output is square enough to hold the mirror tiles
+  const bool symmetric = a.Xa == a.Xb && a.xa_batch == a.xb_batch && a.na_of == a.nb_of && a.na_fixed == a.nb_fixed &&
+                         a.na_pad == a.nb_pad && a.ld >= a.na_pad;
+  const int tiles_m = (a.na_pad + KT - 1) / KT;
+  const int cols = symmetric ? a.na_pad : (int)a.ld;
+  const int tiles_n = (cols + KT - 1) / KT;
+  dim3 grid(symmetric ? (unsigned)(tiles_m * (tiles_m + 1) / 2) : (unsigned)(tiles_m * tiles_n), 1, batch);
+  build_K_tiled_kernel<<<grid, KT_THREADS, smem, L.stream>>>(a, symmetric ? 1 : 0, tiles_n);
   L.bump();
-  return cudaGetLastError();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (symmetric && a.ld > a.na_pad) {
+    // padding columns [na_pad, ld) are not covered by the triangular tile list: clear them
+    return cudaMemset2DAsync(a.out + a.na_pad, sizeof(double) * a.ld, 0, sizeof(double) * (a.ld - a.na_pad),
+                             (size_t)a.na_pad * batch, L.stream);
+  }
+  return cudaSuccess;
 }
 
 cudaError_t gather_rows_launch(const Launch& L, const double* X, const double* y, const int* rows,

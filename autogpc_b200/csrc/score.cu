@@ -81,7 +81,8 @@ struct Chunk {
   }
   int make_maps() {
     return make_tensor_map(&ms.mapA, ms.A, np, np, nb, np, ms.stride) | make_tensor_map(&ms.mapM, ms.M, np, np, nb, np, ms.stride) |
-           make_tensor_map(&ms.mapU, ms.U, np, np, nb, np, ms.stride) | make_tensor_map(&ms.mapT, ms.T, np, np, nb, np, ms.stride);
+           make_tensor_map(&ms.mapU, ms.U, np, np, nb, np, ms.stride) | make_tensor_map(&ms.mapT, ms.T, np, np, nb, np, ms.stride) |
+           make_tensor_map(&ms.mapA32, ms.A, np, np, nb, np, ms.stride, 32) | make_tensor_map(&ms.mapM32, ms.M, np, np, nb, np, ms.stride, 32);
   }
 };
 

@@ -276,7 +276,11 @@ def main():
     prog_arr = (Program * B)(*progs)
     opt = EPOptions(1e-6, 1.0, 100, 0)
     did = eng.dataset(data.X, data.Y)
-    stream = torch.cuda.current_stream().cuda_stream
+    # one explicit stream for torch, the timing events and the engine's launches (a NULL stream would make the engine use
+    # its own non-blocking stream, which torch.cuda.Event on the default stream does not see)
+    side = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(side)
+    stream = side.cuda_stream
 
     def exchange(nlml_np, bic_np, status_np):
         if world == 1:
@@ -333,11 +337,20 @@ def main():
     thetas_p = [pin(t) for t in thetas]
     rows_p = [pin(r.astype(np.int32)) for r in rows]
 
+    host_ms = {"dataset_upload": 0.0, "score_batch": 0.0, "dataset_free": 0.0, "exchange": 0.0}
+
     def step_host():
+        t0 = time.perf_counter()
         d = eng.dataset(Xp, yp)
+        t1 = time.perf_counter()
         r = eng.score_batch(d, progs, thetas_p, rows_p)
+        t2 = time.perf_counter()
         eng.dataset_free(d)
+        t3 = time.perf_counter()
         exchange(r["nlml"], r["bic"], r["status"])
+        t4 = time.perf_counter()
+        for k, v in zip(host_ms, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+            host_ms[k] += 1e3 * v
         return r
 
     h2d = Xp.nbytes + yp.nbytes + B * stride * 8 + rows_cat.nbytes + B * 8 + B * 784
@@ -345,11 +358,16 @@ def main():
     e2e_steps = max(1, min(args.steps, 3))
     r = step_host()  # warm-up of the host path (staging allocations)
     barrier()
+    for k in host_ms:
+        host_ms[k] = 0.0
+    eng.profile_enable(True)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         r = step_host()
     barrier()
     e2e_s = time.perf_counter() - t0
+    prof_e2e = eng.profile_read()
+    eng.profile_enable(False)
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -372,7 +390,9 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, world, len(items)),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "matches_device_path": same},
+                    "steps": e2e_steps, "matches_device_path": same,
+                    "host_ms_per_step": {k: v / e2e_steps for k, v in host_ms.items()},
+                    "kernel_ms_per_step": sum(v["ms"] for v in prof_e2e.values()) / e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_nt_kernel (TMA + FP64 DMMA; potrf trailing/panel updates, "
