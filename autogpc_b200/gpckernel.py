@@ -260,12 +260,27 @@ def train_kernels(kernels: List[GPCKernel], mode="auto", n_folds=5, max_evals=10
     if my_models:
         optim.optimize_models(my_models, max_evals=max_evals)
     errs = {}
+    ok = []
     for i in mine:
         m = items[i][2]
         if getattr(m, "optimization_error", None) is not None or not np.isfinite(m._nlml):
             errs[i] = float("nan")   # failed fold: skipped below, like the reference's bare except
-            continue
-        errs[i] = _error_on_rows(m, kernels[items[i][0]].data, m._test_rows)
+        else:
+            ok.append(i)
+    # held-out error of every surviving fold model (computeError, gpckernel.py:837-846): one predict_batch per dataset
+    by_ds = {}
+    for i in ok:
+        by_ds.setdefault((id(items[i][2].engine), items[i][2]._dataset), []).append(i)
+    for group in by_ds.values():
+        ms_ = [items[i][2] for i in group]
+        for m in ms_:
+            m._ensure_sites()
+        p, _ = ms_[0].engine.predict_batch(ms_[0]._dataset, [m._program for m in ms_], [m.kern.param_array for m in ms_],
+                                           [m._rows for m in ms_], [m._tau for m in ms_], [m._nu for m in ms_],
+                                           [np.asarray(m._test_rows, dtype=np.int32) for m in ms_])
+        for i, m, pi in zip(group, ms_, p):
+            yte = kernels[items[i][0]].data.Y[np.asarray(m._test_rows), 0]
+            errs[i] = float(np.mean((pi - 0.5) * (yte - 0.5) < 0))
     if shard is not None:
         from . import sharding
         sharding.exchange_models(items, mine, errs, shard)
