@@ -67,7 +67,12 @@ int agpc_create(int device, agpc_ctx** out) {
   if (!c) return AGPC_E_NOMEM;
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // the look-ahead (panel) stream outranks the bulk updates
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_panel, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_rest, cudaEventDisableTiming) != cudaSuccess) {
     delete c;
     return AGPC_E_CUDA;
   }
@@ -90,6 +95,10 @@ int agpc_destroy(agpc_ctx* ctx) {
     cudaEventDestroy(r.e0);
     cudaEventDestroy(r.e1);
   }
+  cudaStreamSynchronize(ctx->side);
+  cudaEventDestroy(ctx->ev_panel);
+  cudaEventDestroy(ctx->ev_rest);
+  cudaStreamDestroy(ctx->side);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return AGPC_OK;
@@ -186,7 +195,7 @@ int agpc_gemm_nt(agpc_ctx* ctx, const double* A, const double* B, double* C, int
   g.C = C; g.ldc = N; g.c_batch = (long long)M * N;
   g.m_tiles = M / TILE; g.n_tiles = N / TILE; g.k_tiles = K / GEMM_BK;
   g.alpha = alpha; g.beta = beta;
-  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches, &ctx->prof};
+  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches, &ctx->prof, ctx->side, ctx->ev_panel, ctx->ev_rest};
   CK(ctx, gemm_nt_launch(L, ma, mb, g, g.m_tiles * g.n_tiles, 1, batch));
   return AGPC_OK;
 }
@@ -216,7 +225,7 @@ int agpc_potrf(agpc_ctx* ctx, double* A, int32_t n, int32_t batch, double* Minv,
       make_tensor_map(&ms.mapM32, ms.M, n, n, batch, n, ms.stride, 32) ||
       (want_inv && make_tensor_map(&ms.mapT, ms.T, n, n, batch, n, ms.stride)))
     return fail(ctx, AGPC_E_CUDA, "cuTensorMapEncodeTiled failed");
-  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches, &ctx->prof};
+  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches, &ctx->prof, ctx->side, ctx->ev_panel, ctx->ev_rest};
   if (info) CK(ctx, cudaMemsetAsync(info, 0, sizeof(int32_t) * batch, L.stream));
   CK(ctx, potrf_blocked(L, ms, nullptr, info));
   if (want_inv) CK(ctx, trtri_blocked(L, ms, nullptr));
@@ -245,7 +254,7 @@ int agpc_build_K(agpc_ctx* ctx, const agpc_program* program, const double* theta
   if (!ctx || !program || !theta_host || !X_dev || !K_dev || n <= 0 || D <= 0 || ld < n || (ld & 1))
     return fail(ctx, AGPC_E_ARG, "build_K: bad argument (ld must be even and >= n)");
   CK(ctx, cudaSetDevice(ctx->device));
-  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches, &ctx->prof};
+  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches, &ctx->prof, ctx->side, ctx->ev_panel, ctx->ev_rest};
   agpc_program* d_prog;
   double* d_theta;
   int rc = param_scratch(ctx, program, theta_host, L.stream, &d_prog, &d_theta);
@@ -263,7 +272,7 @@ int agpc_kernel_grad(agpc_ctx* ctx, const agpc_program* program, const double* t
   if (!ctx || !program || !theta_host || !X_dev || !G_dev || !grad_host || n <= 0 || D <= 0 || ld < n)
     return fail(ctx, AGPC_E_ARG, "kernel_grad: bad argument");
   CK(ctx, cudaSetDevice(ctx->device));
-  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches, &ctx->prof};
+  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches, &ctx->prof, ctx->side, ctx->ev_panel, ctx->ev_rest};
   agpc_program* d_prog;
   double* d_theta;
   int rc = param_scratch(ctx, program, theta_host, L.stream, &d_prog, &d_theta);

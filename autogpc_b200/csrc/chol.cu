@@ -38,116 +38,108 @@ constexpr int POTF2_SMEM = (TILE * POTF2_LD + 2 * TILE + TILE + 16) * 8;
 struct Potf2Smem {
   double* vbuf;   // [2][128] broadcast column
   double* winv;   // [128]    1 / L_jj
-  double* ibuf;   // [2][4]   {1/a_jj, 1/sqrt(a_jj), sqrt(a_jj)}
+  double* ibuf;   // [2][4]   1/a_jj (slot 0)
   int* badflag;
 };
 
-// publishes column jn, held in col[0..4) by the threads that own it, and its pivot terms
+// publishes column jn (of 16-group BP), held in col[0..8) by the threads that own it, and its pivot terms; the pivot
+// a_jn,jn can only sit in row group BP, on the thread with ty == jn % 16
+template <int BP>
 __device__ __forceinline__ void potf2_publish(const Potf2Smem& sm, const double (&col)[8], int jn, int ty) {
   double* vb = sm.vbuf + (jn & 1) * TILE;
 #pragma unroll
-  for (int a = 0; a < 8; ++a) {
-    const int r = ty + 16 * a;
-    vb[r] = col[a];
-    if (r == jn) {
-      double d = col[a];
-      if (!(d > 0.0) || !isfinite(d)) {
-        *sm.badflag = 1;
-        d = 1.0;
-      }
-      double rinv = rsqrt(d);  // MUFU.RSQ64H + Newton: short dependent chain
-      rinv = fma(fma(-d * rinv, rinv, 1.0), 0.5 * rinv, rinv);
-      double* ib = sm.ibuf + (jn & 1) * 4;
-      ib[0] = rinv * rinv;
-      ib[1] = rinv;
-      ib[2] = d * rinv;
-      sm.winv[jn] = rinv;
+  for (int a = 0; a < 8; ++a) vb[ty + 16 * a] = col[a];
+  if (ty == (jn & 15)) {
+    double d = col[BP];
+    if (!(d > 0.0) || !isfinite(d)) {
+      *sm.badflag = 1;
+      d = 1.0;
     }
+    const double rinv = rsqrt(d);  // 1 ulp (MUFU.RSQ64H + Newton)
+    sm.ibuf[(jn & 1) * 4] = rinv * rinv;
+    sm.winv[jn] = rinv;
   }
 }
 
+// um = multiplier of row group A for the 16 x 16 patch (A, B): below the diagonal (A > B) the element is part of A
+// and always live; above it (A < B) it is W[q][r], live once step r has passed; on the diagonal patch it depends on
+// the thread (ty >= tx).
 template <int A, int B>
-__device__ __forceinline__ void potf2_row_update(double (&s)[8][8], const double (&uf)[8], const double (&ul)[8],
-                                                 bool diag_lower, double t) {
-  // patch (A, B): rows 16A.., columns 16B..: below the diagonal for A > B, above it for A < B
-  const double um = (A > B) ? uf[A] : (A < B) ? ul[A] : (diag_lower ? uf[A] : ul[A]);
-  s[A][B] = fma(um, t, s[A][B]);
+__device__ __forceinline__ double potf2_um(const double (&uf)[8], const double (&ul)[8], bool diag_lower) {
+  return (A > B) ? uf[A] : (A < B) ? ul[A] : (diag_lower ? uf[A] : ul[A]);
+}
+
+template <int BJ, int B>
+__device__ __forceinline__ void potf2_load_t(double (&t)[8], const double* v, double inv, int tx, int jj) {
+  if constexpr (B < 8) {
+    const double x = v[tx + 16 * B] * inv;
+    t[B] = (B == BJ) ? ((tx > jj) ? x : 0.0) : x;  // finished columns of the current 16-group get a zero update
+    potf2_load_t<BJ, B + 1>(t, v, inv, tx, jj);
+  }
 }
 
 template <int B>
 __device__ __forceinline__ void potf2_col_update(double (&s)[8][8], const double (&uf)[8], const double (&ul)[8],
                                                  bool diag_lower, double t) {
-  potf2_row_update<0, B>(s, uf, ul, diag_lower, t);
-  potf2_row_update<1, B>(s, uf, ul, diag_lower, t);
-  potf2_row_update<2, B>(s, uf, ul, diag_lower, t);
-  potf2_row_update<3, B>(s, uf, ul, diag_lower, t);
-  potf2_row_update<4, B>(s, uf, ul, diag_lower, t);
-  potf2_row_update<5, B>(s, uf, ul, diag_lower, t);
-  potf2_row_update<6, B>(s, uf, ul, diag_lower, t);
-  potf2_row_update<7, B>(s, uf, ul, diag_lower, t);
+  s[0][B] = fma(-potf2_um<0, B>(uf, ul, diag_lower), t, s[0][B]);
+  s[1][B] = fma(-potf2_um<1, B>(uf, ul, diag_lower), t, s[1][B]);
+  s[2][B] = fma(-potf2_um<2, B>(uf, ul, diag_lower), t, s[2][B]);
+  s[3][B] = fma(-potf2_um<3, B>(uf, ul, diag_lower), t, s[3][B]);
+  s[4][B] = fma(-potf2_um<4, B>(uf, ul, diag_lower), t, s[4][B]);
+  s[5][B] = fma(-potf2_um<5, B>(uf, ul, diag_lower), t, s[5][B]);
+  s[6][B] = fma(-potf2_um<6, B>(uf, ul, diag_lower), t, s[6][B]);
+  s[7][B] = fma(-potf2_um<7, B>(uf, ul, diag_lower), t, s[7][B]);
 }
 
 template <int BJ, int B>
 __device__ __forceinline__ void potf2_rest(double (&s)[8][8], const double (&uf)[8], const double (&ul)[8],
-                                           bool diag_lower, const double* v, double inv, int tx) {
+                                           bool diag_lower, const double (&t)[8]) {
   if constexpr (B < 8) {
-    const double t = v[tx + 16 * B] * inv;
-    potf2_col_update<B>(s, uf, ul, diag_lower, t);
-    potf2_rest<BJ, B + 1>(s, uf, ul, diag_lower, v, inv, tx);
+    potf2_col_update<B>(s, uf, ul, diag_lower, t[B]);
+    potf2_rest<BJ, B + 1>(s, uf, ul, diag_lower, t);
   }
 }
 
-// the 16 columns j = 16 BJ .. 16 BJ + 15
+// the 16 columns j = 16 BJ .. 16 BJ + 15.  Column j is NOT scaled here: columns <= j simply stop receiving updates
+// (their t is zero / they are skipped), and the 1 / sqrt(a_jj) scaling of every finished column -- diagonal included,
+// a_jj / sqrt(a_jj) = L_jj -- is applied once at write-out.
 template <int BJ>
 __device__ __forceinline__ void potf2_group(double (&s)[8][8], const Potf2Smem& sm, bool diag_lower, int tx, int ty) {
 #pragma unroll 1
   for (int jj = 0; jj < 16; ++jj) {
     const int j = 16 * BJ + jj;
     const double* v = sm.vbuf + (j & 1) * TILE;
-    const double* ib = sm.ibuf + (j & 1) * 4;
-    const double inv = ib[0];
-    double uf[8], ul[8];  // -u for lower elements, -u_low for upper elements
+    const double inv = sm.ibuf[(j & 1) * 4];
+    double t[8];
+    potf2_load_t<BJ, BJ>(t, v, inv, tx, jj);
+    double uf[8], ul[8];
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
       const double vr = v[ty + 16 * a];
       // rows of 16-row groups a < BJ are all <= j, rows of groups a > BJ are all > j
       if (a < BJ) {
-        uf[a] = -vr;
-        ul[a] = -vr;
+        uf[a] = vr;
+        ul[a] = vr;
       } else if (a > BJ) {
-        uf[a] = -vr;
+        uf[a] = vr;
         ul[a] = 0.0;
       } else {
-        uf[a] = (ty == jj) ? -1.0 : -vr;
+        uf[a] = (ty == jj) ? 1.0 : vr;
         ul[a] = (ty <= jj) ? uf[a] : 0.0;
       }
     }
-    // column j is final
-    {
-      const double rinv = ib[1], piv = ib[2];
-      const bool own = tx == jj;
-#pragma unroll
-      for (int a = 0; a < 8; ++a) {
-        double fin = s[a][BJ] * rinv;
-        if (a == BJ) fin = (ty == jj) ? piv : fin;
-        s[a][BJ] = own ? fin : s[a][BJ];
-      }
-    }
     // columns of this 16-group first (lanes tx > jj), so that column j + 1 can be published early
-    {
-      const double t = (tx > jj) ? v[tx + 16 * BJ] * inv : 0.0;
-      potf2_col_update<BJ>(s, uf, ul, diag_lower, t);
-    }
+    potf2_col_update<BJ>(s, uf, ul, diag_lower, t[BJ]);
     if (jj < 15 && tx == jj + 1) {
       const double col[8] = {s[0][BJ], s[1][BJ], s[2][BJ], s[3][BJ], s[4][BJ], s[5][BJ], s[6][BJ], s[7][BJ]};
-      potf2_publish(sm, col, j + 1, ty);
+      potf2_publish<BJ>(sm, col, j + 1, ty);
     }
-    potf2_rest<BJ, BJ + 1>(s, uf, ul, diag_lower, v, inv, tx);
+    potf2_rest<BJ, BJ + 1>(s, uf, ul, diag_lower, t);
     if constexpr (BJ < 7) {
       if (jj == 15 && tx == 0) {
         const double col[8] = {s[0][BJ + 1], s[1][BJ + 1], s[2][BJ + 1], s[3][BJ + 1],
                                s[4][BJ + 1], s[5][BJ + 1], s[6][BJ + 1], s[7][BJ + 1]};
-        potf2_publish(sm, col, j + 1, ty);
+        potf2_publish<BJ + 1>(sm, col, j + 1, ty);
       }
     }
     __syncthreads();
@@ -183,7 +175,7 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ M, double* __restr
   __syncthreads();
   if (tx == 0) {
     const double col[8] = {s[0][0], s[1][0], s[2][0], s[3][0], s[4][0], s[5][0], s[6][0], s[7][0]};
-    potf2_publish(sm, col, 0, ty);
+    potf2_publish<0>(sm, col, 0, ty);
   }
   __syncthreads();
 
@@ -198,9 +190,11 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ M, double* __restr
 
   // transpose through shared memory so that L, W and W^T all leave with coalesced row writes
 #pragma unroll
-  for (int a = 0; a < 8; ++a)
+  for (int b = 0; b < 8; ++b) {
+    const double wq = sm.winv[tx + 16 * b];  // deferred column scaling
 #pragma unroll
-    for (int b = 0; b < 8; ++b) stage[(ty + 16 * a) * POTF2_LD + tx + 16 * b] = s[a][b];
+    for (int a = 0; a < 8; ++a) stage[(ty + 16 * a) * POTF2_LD + tx + 16 * b] = s[a][b] * wq;
+  }
   __syncthreads();
   double* Mb = M + base;
   double* Ub = U + base;
@@ -258,64 +252,116 @@ constexpr int POTRF_OUTER = 4;
 // one-tile-wide launches with fewer CTAs than this run as 128 x 32 tiles (4x the CTAs, a quarter of the latency)
 constexpr int THIN_CTA_LIMIT = 160;
 
+// panels k0 .. k0 + kb of one outer block: in-block left-looking update, diagonal block, panel solve
+static cudaError_t potrf_panels(const Launch& L, const MatSet& ms, const int* active, int* info, int k0, int kb) {
+  const int nblk = ms.np / TILE;
+  for (int t = 0; t < kb; ++t) {
+    const int k = k0 + t;
+    if (t > 0) {
+      // A[k:, k] -= A[k:, k0:k] A[k, k0:k]^T
+      GemmArgs u{};
+      u.C = ms.A; u.Ct = nullptr; u.ldc = ms.np; u.c_batch = ms.stride;
+      u.a_row0 = k * TILE; u.a_col0 = k0 * TILE;
+      u.b_row0 = k * TILE; u.b_col0 = k0 * TILE;
+      u.c_row0 = k * TILE; u.c_col0 = k * TILE;
+      u.m_tiles = nblk - k; u.n_tiles = 1; u.k_tiles = t * (TILE / GEMM_BK);
+      u.k_rule = KRULE_FULL; u.lower_only = 0; u.alpha = -1.0; u.beta = 1.0; u.active = active;
+      if ((nblk - k) * ms.batch <= THIN_CTA_LIMIT) {
+        u.n_tiles = TILE / 32;
+        AGPC_CUDA_TRY(gemm_nt_thin_launch(L, ms.mapA, ms.mapA32, u, (nblk - k) * u.n_tiles, 1, ms.batch));
+      } else {
+        AGPC_CUDA_TRY(gemm_nt_launch(L, ms.mapA, ms.mapA, u, nblk - k, 1, ms.batch));
+      }
+    }
+    AGPC_CUDA_TRY(potf2_inv_launch(L, ms.A, ms.M, ms.U, ms.np, ms.stride, k, ms.batch, active, info));
+    const int below = nblk - k - 1;
+    if (below == 0) break;
+    // panel solve through the inverse: A[k+1:, k] <- A[k+1:, k] W_k^T  (W_k = L_kk^-1 is lower: K clipped)
+    GemmArgs p{};
+    p.C = ms.A; p.Ct = nullptr; p.ldc = ms.np; p.c_batch = ms.stride;
+    p.a_row0 = (k + 1) * TILE; p.a_col0 = k * TILE;
+    p.b_row0 = k * TILE; p.b_col0 = k * TILE;  // W_k from M's diagonal block
+    p.c_row0 = (k + 1) * TILE; p.c_col0 = k * TILE;
+    p.m_tiles = below; p.n_tiles = 1; p.k_tiles = TILE / GEMM_BK;
+    p.k_rule = KRULE_END_AT_COL; p.lower_only = 0; p.alpha = 1.0; p.beta = 0.0; p.active = active;
+    if (below * ms.batch <= THIN_CTA_LIMIT) {
+      // four CTAs share one 128-row operand tile here, so the solve cannot run in place: stage the panel in the
+      // (still unused) strictly-lower part of M and read it from there
+      AGPC_CUDA_TRY(copy_panel_launch(L, ms.A, ms.M, ms.np, ms.stride, (k + 1) * TILE, k * TILE, below * TILE,
+                                      ms.batch, active));
+      p.n_tiles = TILE / 32;
+      AGPC_CUDA_TRY(gemm_nt_thin_launch(L, ms.mapM, ms.mapM32, p, below * p.n_tiles, 1, ms.batch));
+    } else {
+      AGPC_CUDA_TRY(gemm_nt_launch(L, ms.mapA, ms.mapM, p, below, 1, ms.batch));
+    }
+  }
+  return cudaSuccess;
+}
+
+// trailing update with outer block [k0, k0 + kb): C[r0:, c0 : c0 + ncols] -= A[., k0:k0+kb] A[., k0:k0+kb]^T for the
+// tiles on or below the diagonal.  (r0 == c0; ncols < 0: everything to the right, as a lower-triangular tile list)
+static cudaError_t potrf_trailing(const Launch& L, const MatSet& ms, const int* active, int k0, int kb, int r0, int ncols) {
+  const int nblk = ms.np / TILE;
+  const int rows = nblk - r0;
+  if (rows <= 0 || ncols == 0) return cudaSuccess;
+  GemmArgs s{};
+  s.C = ms.A; s.Ct = nullptr; s.ldc = ms.np; s.c_batch = ms.stride;
+  s.a_row0 = r0 * TILE; s.a_col0 = k0 * TILE;
+  s.b_row0 = r0 * TILE; s.b_col0 = k0 * TILE;
+  s.c_row0 = r0 * TILE; s.c_col0 = r0 * TILE;
+  s.k_tiles = kb * (TILE / GEMM_BK);
+  s.k_rule = KRULE_FULL; s.alpha = -1.0; s.beta = 1.0; s.active = active;
+  if (ncols < 0) {
+    s.m_tiles = rows; s.n_tiles = rows; s.lower_only = 1;
+    return gemm_nt_launch(L, ms.mapA, ms.mapA, s, rows * (rows + 1) / 2, 1, ms.batch);
+  }
+  const int nc = ncols < rows ? ncols : rows;
+  s.m_tiles = rows; s.n_tiles = nc; s.lower_only = 0; s.skip_upper = 1;
+  return gemm_nt_launch(L, ms.mapA, ms.mapA, s, rows * nc, 1, ms.batch);
+}
+
+// Small batches run with look-ahead: the trailing update of outer block i is split into its first POTRF_OUTER block
+// columns (the "head": exactly the panels of outer block i + 1) and the rest.  The latency-bound chain panels -> head
+// -> panels ... runs on the context's HIGH-PRIORITY stream, so its few CTAs get the next SM that frees up, while the
+// bulk rest(i) keeps every other SM busy on the caller's stream:
+//   hi:  panels(i) | head(i) [after rest(i-1)] | panels(i+1) | head(i+1) [after rest(i)] | ...
+//   lo:            | rest(i) [after panels(i), rest(i-1)]    | rest(i+1) ...
 cudaError_t potrf_blocked(const Launch& L, const MatSet& ms, const int* active, int* info) {
   const int nblk = ms.np / TILE;
   const double wn = L.work_n > 0.0 ? L.work_n : (double)ms.np;
   L.add_work(CLS_GEMM, (double)L.work_items * wn * wn * wn / 3.0);  // LAPACK dpotrf count
+  const bool lookahead = L.side != nullptr && ms.batch <= 4 && nblk > 2 * POTRF_OUTER;
+  if (!lookahead) {
+    for (int k0 = 0; k0 < nblk; k0 += POTRF_OUTER) {
+      const int kb = nblk - k0 < POTRF_OUTER ? nblk - k0 : POTRF_OUTER;
+      AGPC_CUDA_TRY(potrf_panels(L, ms, active, info, k0, kb));
+      if (k0 + kb < nblk) AGPC_CUDA_TRY(potrf_trailing(L, ms, active, k0, kb, k0 + kb, -1));
+    }
+    return cudaSuccess;
+  }
+  Launch H = L;  // high-priority chain
+  H.stream = L.side;
+  AGPC_CUDA_TRY(cudaEventRecord(L.ev_rest, L.stream));  // everything queued so far (form_B ...) precedes the chain
+  AGPC_CUDA_TRY(cudaStreamWaitEvent(H.stream, L.ev_rest, 0));
+  bool rest_pending = false;
   for (int k0 = 0; k0 < nblk; k0 += POTRF_OUTER) {
     const int kb = nblk - k0 < POTRF_OUTER ? nblk - k0 : POTRF_OUTER;
-    for (int t = 0; t < kb; ++t) {
-      const int k = k0 + t;
-      if (t > 0) {
-        // A[k:, k] -= A[k:, k0:k] A[k, k0:k]^T
-        GemmArgs u{};
-        u.C = ms.A; u.Ct = nullptr; u.ldc = ms.np; u.c_batch = ms.stride;
-        u.a_row0 = k * TILE; u.a_col0 = k0 * TILE;
-        u.b_row0 = k * TILE; u.b_col0 = k0 * TILE;
-        u.c_row0 = k * TILE; u.c_col0 = k * TILE;
-        u.m_tiles = nblk - k; u.n_tiles = 1; u.k_tiles = t * (TILE / GEMM_BK);
-        u.k_rule = KRULE_FULL; u.lower_only = 0; u.alpha = -1.0; u.beta = 1.0; u.active = active;
-        if ((nblk - k) * ms.batch <= THIN_CTA_LIMIT) {
-          u.n_tiles = TILE / 32;
-          AGPC_CUDA_TRY(gemm_nt_thin_launch(L, ms.mapA, ms.mapA32, u, (nblk - k) * u.n_tiles, 1, ms.batch));
-        } else {
-          AGPC_CUDA_TRY(gemm_nt_launch(L, ms.mapA, ms.mapA, u, nblk - k, 1, ms.batch));
-        }
-      }
-      AGPC_CUDA_TRY(potf2_inv_launch(L, ms.A, ms.M, ms.U, ms.np, ms.stride, k, ms.batch, active, info));
-      const int below = nblk - k - 1;
-      if (below == 0) break;
-      // panel solve through the inverse: A[k+1:, k] <- A[k+1:, k] W_k^T  (in place; W_k = L_kk^-1 is lower: K clipped)
-      GemmArgs p{};
-      p.C = ms.A; p.Ct = nullptr; p.ldc = ms.np; p.c_batch = ms.stride;
-      p.a_row0 = (k + 1) * TILE; p.a_col0 = k * TILE;
-      p.b_row0 = k * TILE; p.b_col0 = k * TILE;  // W_k from M's diagonal block
-      p.c_row0 = (k + 1) * TILE; p.c_col0 = k * TILE;
-      p.m_tiles = below; p.n_tiles = 1; p.k_tiles = TILE / GEMM_BK;
-      p.k_rule = KRULE_END_AT_COL; p.lower_only = 0; p.alpha = 1.0; p.beta = 0.0; p.active = active;
-      if (below * ms.batch <= THIN_CTA_LIMIT) {
-        // four CTAs share one 128-row operand tile here, so the solve cannot run in place: stage the panel in the
-        // (still unused) strictly-lower part of M and read it from there
-        AGPC_CUDA_TRY(copy_panel_launch(L, ms.A, ms.M, ms.np, ms.stride, (k + 1) * TILE, k * TILE, below * TILE,
-                                        ms.batch, active));
-        p.n_tiles = TILE / 32;
-        AGPC_CUDA_TRY(gemm_nt_thin_launch(L, ms.mapM, ms.mapM32, p, below * p.n_tiles, 1, ms.batch));
-      } else {
-        AGPC_CUDA_TRY(gemm_nt_launch(L, ms.mapA, ms.mapM, p, below, 1, ms.batch));
-      }
+    AGPC_CUDA_TRY(potrf_panels(H, ms, active, info, k0, kb));
+    const int r0 = k0 + kb;
+    if (r0 >= nblk) break;
+    AGPC_CUDA_TRY(cudaEventRecord(L.ev_panel, H.stream));
+    if (rest_pending) AGPC_CUDA_TRY(cudaStreamWaitEvent(H.stream, L.ev_rest, 0));  // rest(i-1) wrote the head's columns
+    AGPC_CUDA_TRY(potrf_trailing(H, ms, active, k0, kb, r0, POTRF_OUTER));
+    rest_pending = false;
+    if (r0 + POTRF_OUTER < nblk) {
+      AGPC_CUDA_TRY(cudaStreamWaitEvent(L.stream, L.ev_panel, 0));
+      AGPC_CUDA_TRY(potrf_trailing(L, ms, active, k0, kb, r0 + POTRF_OUTER, -1));
+      AGPC_CUDA_TRY(cudaEventRecord(L.ev_rest, L.stream));
+      rest_pending = true;
     }
-    const int rest = nblk - k0 - kb;
-    if (rest <= 0) break;
-    // trailing update with the whole outer block: A[r:, r:] -= A[r:, k0:r] A[r:, k0:r]^T, lower tiles only
-    GemmArgs s{};
-    s.C = ms.A; s.Ct = nullptr; s.ldc = ms.np; s.c_batch = ms.stride;
-    s.a_row0 = (k0 + kb) * TILE; s.a_col0 = k0 * TILE;
-    s.b_row0 = (k0 + kb) * TILE; s.b_col0 = k0 * TILE;
-    s.c_row0 = (k0 + kb) * TILE; s.c_col0 = (k0 + kb) * TILE;
-    s.m_tiles = rest; s.n_tiles = rest; s.k_tiles = kb * (TILE / GEMM_BK);
-    s.k_rule = KRULE_FULL; s.lower_only = 1; s.alpha = -1.0; s.beta = 1.0; s.active = active;
-    AGPC_CUDA_TRY(gemm_nt_launch(L, ms.mapA, ms.mapA, s, rest * (rest + 1) / 2, 1, ms.batch));
   }
+  AGPC_CUDA_TRY(cudaEventRecord(L.ev_panel, H.stream));  // join: the caller's stream continues after the chain
+  AGPC_CUDA_TRY(cudaStreamWaitEvent(L.stream, L.ev_panel, 0));
   return cudaSuccess;
 }
 

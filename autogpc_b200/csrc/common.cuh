@@ -30,6 +30,7 @@ struct GemmArgs {
   int m_kind, n_kind, k_kind;     // EXT_FIXED or EXT_H2 (right-half size of trtri group g, may be partial)
   int grp_blocks, half_blocks, nblk;  // trtri grouping: group g covers blocks [g*grp_blocks, ...)
   int k_rule, lower_only;
+  int skip_upper;  // rectangular tile grid whose C origin lies on the diagonal: tiles with ti < tj are not computed
   double alpha, beta;
   const int* active;  // per-batch-item flag (nullptr = all active)
 };
@@ -68,6 +69,8 @@ struct Launch {
   cudaStream_t stream;
   long long* counter;
   Profiler* prof = nullptr;
+  cudaStream_t side = nullptr;        // second stream + two events for the look-ahead of single-matrix factorisations
+  cudaEvent_t ev_panel = nullptr, ev_rest = nullptr;
   int work_items = 1;     // items still active in the batch      } algorithmic work accounting only
   double work_n = 0.0;    // mean true n of the batch's items     }
   void bump(int n = 1) const {

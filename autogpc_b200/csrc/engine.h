@@ -15,6 +15,8 @@ struct agpc_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;  // look-ahead stream of potrf_blocked
+  cudaEvent_t ev_panel = nullptr, ev_rest = nullptr;
   std::string err;
   long long launches = 0;
   void* arena = nullptr;

@@ -96,6 +96,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     ti = blockIdx.x / nt;
     tj = blockIdx.x % nt;
     if (ti >= mt) return;
+    if (args.skip_upper && ti * TILE < tj * BN) return;
   }
   int k_begin = 0, k_end = kt;
   if (args.k_rule == KRULE_BEGIN_AT_ROW) k_begin = ti * (TILE / GEMM_BK);

@@ -204,7 +204,7 @@ int agpc_score_batch_dev(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, con
   if ((opt->warm_start || opt->max_sweeps == 0) && (!tau_dev || !nu_dev))
     return fail(ctx, AGPC_E_ARG, "score_batch: warm start / frozen sites need tau and nu");
   CK(cudaSetDevice(ctx->device));
-  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches, &ctx->prof};
+  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches, &ctx->prof, ctx->side, ctx->ev_panel, ctx->ev_rest};
 
   // chunking: consecutive items, as many as the arena budget allows at the padded size of the largest item
   const int np_all = (int)align_up((size_t)n_max, TILE);
@@ -411,7 +411,7 @@ static int predict_impl(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, cons
   if (Xstar_host && n_items != 1) return fail(ctx, AGPC_E_ARG, "predict_points: one item only");
   const Dataset& ds = ctx->datasets[dataset_id];
   CK(cudaSetDevice(ctx->device));
-  Launch L{ctx->stream, &ctx->launches, &ctx->prof};
+  Launch L{ctx->stream, &ctx->launches, &ctx->prof, ctx->side, ctx->ev_panel, ctx->ev_rest};
   int n_max = 0, m_max = 0;
   for (int b = 0; b < n_items; ++b) {
     n_max = std::max<int>(n_max, (int)(row_off[b + 1] - row_off[b]));
