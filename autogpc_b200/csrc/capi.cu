@@ -1,6 +1,8 @@
 // C ABI of the engine (include/autogpc_b200.h): context, workspace arena, datasets, building-block entry points.
 // The scoring pipeline itself is in score.cu.
+#include <algorithm>
 #include <cstdio>
+#include <utility>
 #include <cstring>
 #include <new>
 
@@ -91,6 +93,7 @@ int agpc_destroy(agpc_ctx* ctx) {
   if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->prof.base) cudaEventDestroy(ctx->prof.base);
   for (auto& r : ctx->prof.recs) {
     cudaEventDestroy(r.e0);
     cudaEventDestroy(r.e1);
@@ -121,6 +124,11 @@ int agpc_profile_enable(agpc_ctx* ctx, int32_t on) {
   Profiler& p = ctx->prof;
   p.enabled = on != 0;
   p.used = 0;
+  if (p.base == nullptr && cudaEventCreate(&p.base) != cudaSuccess) return fail(ctx, AGPC_E_CUDA, "profile: event create");
+  if (on) {
+    cudaEventRecord(p.base, ctx->stream);
+    cudaEventSynchronize(p.base);
+  }
   for (int c = 0; c < CLS_COUNT; ++c) {
     p.work[c] = 0.0;
     p.count[c] = 0;
@@ -138,10 +146,30 @@ int agpc_profile_read(agpc_ctx* ctx, double* ms, double* work, int64_t* launches
     work[c] = p.work[c];
     launches[c] = p.count[c];
   }
+  // per class: length of the UNION of its launch intervals (launches of one class may overlap when the look-ahead
+  // stream and the bulk stream run the same kernel concurrently; a plain sum would count that time twice)
+  std::vector<std::pair<float, float>> iv[CLS_COUNT];
   for (size_t i = 0; i < p.used; ++i) {
-    float t = 0.f;
-    CK(ctx, cudaEventElapsedTime(&t, p.recs[i].e0, p.recs[i].e1));
-    ms[p.recs[i].cls] += (double)t;
+    float t0 = 0.f, t1 = 0.f;
+    CK(ctx, cudaEventElapsedTime(&t0, p.base, p.recs[i].e0));
+    CK(ctx, cudaEventElapsedTime(&t1, p.base, p.recs[i].e1));
+    iv[p.recs[i].cls].push_back({t0, t1});
+  }
+  for (int c = 0; c < CLS_COUNT; ++c) {
+    std::sort(iv[c].begin(), iv[c].end());
+    double total = 0.0;
+    float cur0 = 0.f, cur1 = -1.f;
+    for (auto& x : iv[c]) {
+      if (cur1 < cur0 || x.first > cur1) {
+        if (cur1 >= cur0) total += cur1 - cur0;
+        cur0 = x.first;
+        cur1 = x.second;
+      } else if (x.second > cur1) {
+        cur1 = x.second;
+      }
+    }
+    if (cur1 >= cur0) total += cur1 - cur0;
+    ms[c] = total;
   }
   return AGPC_OK;
 }

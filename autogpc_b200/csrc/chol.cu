@@ -330,7 +330,7 @@ cudaError_t potrf_blocked(const Launch& L, const MatSet& ms, const int* active, 
   const int nblk = ms.np / TILE;
   const double wn = L.work_n > 0.0 ? L.work_n : (double)ms.np;
   L.add_work(CLS_GEMM, (double)L.work_items * wn * wn * wn / 3.0);  // LAPACK dpotrf count
-  const bool lookahead = L.side != nullptr && ms.batch <= 4 && nblk > 2 * POTRF_OUTER;
+  const bool lookahead = L.side != nullptr && nblk > 2 * POTRF_OUTER;
   if (!lookahead) {
     for (int k0 = 0; k0 < nblk; k0 += POTRF_OUTER) {
       const int kb = nblk - k0 < POTRF_OUTER ? nblk - k0 : POTRF_OUTER;

@@ -47,6 +47,7 @@ struct Profiler {
     int cls;
   };
   bool enabled = false;
+  cudaEvent_t base = nullptr;  // recorded at enable(): launch intervals are measured from it
   std::vector<Rec> recs;
   size_t used = 0;
   double work[CLS_COUNT] = {0};

@@ -257,6 +257,9 @@ build_K_tiled_kernel(const BuildArgs a, const int symmetric, const int tiles_n) 
   // which is what hides the load -> compute -> store latency chain of a tile (the kernel is latency-, not ALU-bound)
   double* out = a.out + (long long)b * a.out_batch;
   const bool mirror = symmetric && ti != tj;
+  // fast path: an off-diagonal tile (no kdiag) that lies completely inside the valid n x n region, mirror included
+  const bool interior = ti != tj && row0 + KT <= na && col0 + KT <= nb && row0 + KT <= a.na_pad && col0 + KT <= a.ld &&
+                        (!mirror || (col0 + KT <= a.na_pad && row0 + KT <= a.ld));
 #pragma unroll 1
   for (int h = 0; h < 2; ++h) {
     double K[2][4];
@@ -322,30 +325,55 @@ build_K_tiled_kernel(const BuildArgs a, const int symmetric, const int tiles_n) 
           K[r][c] += v;
         }
     }
+    if (interior) {
+      // off-diagonal tile fully inside the valid region: no masks, one row pointer + immediate column offsets
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int lr = ty + 16 * (2 * h + r);
-      const int i = row0 + lr;
+      for (int r = 0; r < 2; ++r) {
+        const int lr = ty + 16 * (2 * h + r);
+        double* o = out + (long long)(row0 + lr) * a.ld + col0 + tx;
+        double* sp = st + lr * KT_LD + tx;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int j = col0 + tx + 16 * c;
-        if (!(i < na && j < nb)) K[r][c] = 0.0;
-        if (i < a.na_pad && j < a.ld) out[(long long)i * a.ld + j] = K[r][c];
-        if (a.kdiag != nullptr && i == j && i < a.na_pad && ti == tj) a.kdiag[(long long)b * a.na_pad + i] = K[r][c];
-        if (mirror) st[lr * KT_LD + tx + 16 * c] = K[r][c];
+        for (int c = 0; c < 4; ++c) {
+          o[16 * c] = K[r][c];
+          if (mirror) sp[16 * c] = K[r][c];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int lr = ty + 16 * (2 * h + r);
+        const int i = row0 + lr;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int j = col0 + tx + 16 * c;
+          if (!(i < na && j < nb)) K[r][c] = 0.0;
+          if (i < a.na_pad && j < a.ld) out[(long long)i * a.ld + j] = K[r][c];
+          if (a.kdiag != nullptr && i == j && i < a.na_pad && ti == tj) a.kdiag[(long long)b * a.na_pad + i] = K[r][c];
+          if (mirror) st[lr * KT_LD + tx + 16 * c] = K[r][c];
+        }
       }
     }
   }
   if (mirror) {
     __syncthreads();
     // mirror tile: rows col0.., columns row0..; element (jj, ii) = st[ii][jj]
+    if (interior) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int jrow = col0 + ty + 16 * r;
+      for (int r = 0; r < 4; ++r) {
+        double* o = out + (long long)(col0 + ty + 16 * r) * a.ld + row0 + tx;
+        const double* sp = st + tx * KT_LD + ty + 16 * r;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int icol = row0 + tx + 16 * c;
-        if (jrow < a.na_pad && icol < a.ld) out[(long long)jrow * a.ld + icol] = st[(tx + 16 * c) * KT_LD + ty + 16 * r];
+        for (int c = 0; c < 4; ++c) o[16 * c] = sp[16 * c * KT_LD];
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int jrow = col0 + ty + 16 * r;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int icol = row0 + tx + 16 * c;
+          if (jrow < a.na_pad && icol < a.ld) out[(long long)jrow * a.ld + icol] = st[(tx + 16 * c) * KT_LD + ty + 16 * r];
+        }
       }
     }
   }

@@ -300,11 +300,17 @@ def test_search_selects_identical_structures_as_oracle(engine):
                 assert sorted(og[lvl]) == sorted(oo[lvl])               # same candidate set
                 assert og[lvl][0] == oo[lvl][0]                         # same winner
                 if criterion == "bic":
-                    tol = lambda v: 5e-3 * max(1.0, abs(v))
+                    # position-by-position over the informative head (candidates clearly better than the pack: the
+                    # rest sit on the flat "explains nothing" plateau, BIC equal to ~0.5 %, where L-BFGS-B stops at
+                    # chaotic points); every candidate's own score must still agree to 2 %
+                    vals = np.array([so[lvl][nm] for nm in oo[lvl]])
+                    cut = vals[0] + 0.5 * (np.median(vals) - vals[0])
                     for i, name in enumerate(og[lvl]):
                         ref_i = so[lvl][oo[lvl][i]]
-                        assert abs(so[lvl][name] - ref_i) <= tol(ref_i), (criterion, lvl, i, name, oo[lvl][i])
-                        assert abs(sg[lvl][name] - so[lvl][name]) <= 25 * tol(ref_i), (criterion, lvl, name)
+                        if ref_i <= cut:
+                            assert name == oo[lvl][i] or abs(so[lvl][name] - ref_i) <= 1e-3 * max(1.0, abs(ref_i)), \
+                                (criterion, lvl, i, name, oo[lvl][i])
+                        assert abs(sg[lvl][name] - so[lvl][name]) <= 2e-2 * max(1.0, abs(so[lvl][name])), (criterion, lvl, name)
                     w = og[lvl][0]
                     assert abs(sg[lvl][w] - so[lvl][w]) <= 1e-6 * max(1.0, abs(so[lvl][w]))
                 else:
