@@ -200,7 +200,10 @@ ep_update_kernel(double* __restrict__ tau, double* __restrict__ nu, const double
   }
   __shared__ double red[32 * 3];
   const int n = n_of[b];
-  double acc[3] = {0.0, 0.0, 0.0};  // sum d_tau^2, sum d_nu^2, non-finite count
+  // damping <= 0: automatic schedule, undamped for the first 3 sweeps and 0.8 afterwards (oracle.ep_damping): undamped
+  // parallel EP limit-cycles on strongly correlated priors where GPy's sequential EP converges
+  if (damping <= 0.0) damping = (sweeps[b] + 1 <= 3) ? 1.0 : 0.8;
+  double acc[3] = {0.0, 0.0, 0.0};  // sum r_tau^2, sum r_nu^2 (undamped residuals), non-finite count
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const long long o = (long long)b * np + i;
     const double sg = sig[o], m = mu[o], tt = tau[o], vt = nu[o], y = yf[o];
@@ -212,17 +215,19 @@ ep_update_kernel(double* __restrict__ tau, double* __restrict__ nu, const double
     const double N = pdf_over_cdf(z);
     const double mu_hat = v_cav / tau_cav + y * N / den;
     const double s2_hat = 1.0 / tau_cav - N * (z + N) / den2;
-    double d_tau = damping * (1.0 / s2_hat - 1.0 / sg);
-    const double d_v = damping * (mu_hat / s2_hat - m / sg);
-    double new_tau = tt + d_tau;
+    const double f_tau = 1.0 / s2_hat - 1.0 / sg;  // full step = fixed-point residual
+    const double f_v = mu_hat / s2_hat - m / sg;
     const double floor_tau = 1e-10 / kdiag[o];  // keeps (1 - Binv_ii)/tau well defined; see DESIGN.md
+    double new_tau = tt + damping * f_tau;
     if (!(new_tau >= floor_tau)) new_tau = isnan(new_tau) ? new_tau : floor_tau;
-    d_tau = new_tau - tt;
-    const double new_v = vt + d_v;
+    double full_tau = tt + f_tau;
+    if (!(full_tau >= floor_tau)) full_tau = isnan(full_tau) ? full_tau : floor_tau;
+    const double r_tau = full_tau - tt;  // convergence is judged on the undamped residual
+    const double new_v = vt + damping * f_v;
     tau[o] = new_tau;
     nu[o] = new_v;
-    acc[0] += d_tau * d_tau;
-    acc[1] += d_v * d_v;
+    acc[0] += r_tau * r_tau;
+    acc[1] += f_v * f_v;
     if (!isfinite(new_tau) || !isfinite(new_v)) acc[2] += 1.0;
   }
   block_reduce<3>(acc, red);

@@ -295,6 +295,7 @@ def train_kernels(kernels: List[GPCKernel], mode="auto", n_folds=5, max_evals=10
         gk.kernel = gpy2gpss(gk.model.kern)
         gk.errorRate = float(np.mean([r["error"] for r in results]))
         gk.foldErrors = [r["error"] for r in results]
+        gk.foldModels = [r["model"] for r in results]
 
 
 # ---- helper functions (same names as the reference's module-level helpers) ------------------------------------

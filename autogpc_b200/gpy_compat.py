@@ -262,7 +262,7 @@ class GPClassification:
 
     def __init__(self, X=None, Y=None, kernel: Optional[Kern] = None, engine: Optional[_eng.Engine] = None,
                  _dataset: Optional[int] = None, _rows: Optional[np.ndarray] = None, _infer: bool = True,
-                 ep_epsilon: float = 1e-6, ep_damping: float = 1.0, ep_max_sweeps: int = 100):
+                 ep_epsilon: float = 1e-6, ep_damping: float = 0.0, ep_max_sweeps: int = 100):
         self.engine = engine if engine is not None else _eng.default_engine()
         self.ep = dict(epsilon=ep_epsilon, damping=ep_damping, max_sweeps=ep_max_sweeps)
         self._owns_dataset = _dataset is None

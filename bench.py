@@ -162,7 +162,7 @@ def oracle_item_seconds(data, folds, item):
     tr = folds[f][0]
     y = data.Y.reshape(-1)
     t = time.perf_counter()
-    o = orc.score(prog, kern.param_array, data.X[tr], y[tr])
+    o = orc.score(prog, kern.param_array, data.X[tr], y[tr], damping=0.0)
     return time.perf_counter() - t, o
 
 
@@ -274,7 +274,7 @@ def main():
     sweeps_d = torch.zeros(B, dtype=torch.int32, device=dev)
     status_d = torch.zeros(B, dtype=torch.int32, device=dev)
     prog_arr = (Program * B)(*progs)
-    opt = EPOptions(1e-6, 1.0, 100, 0)
+    opt = EPOptions(1e-6, 0.0, 100, 0)   # damping 0 = the engine's automatic schedule (production default)
     did = eng.dataset(data.X, data.Y)
     # one explicit stream for torch, the timing events and the engine's launches (a NULL stream would make the engine use
     # its own non-blocking stream, which torch.cuda.Event on the default stream does not see)
@@ -343,7 +343,7 @@ def main():
         t0 = time.perf_counter()
         d = eng.dataset(Xp, yp)
         t1 = time.perf_counter()
-        r = eng.score_batch(d, progs, thetas_p, rows_p)
+        r = eng.score_batch(d, progs, thetas_p, rows_p, damping=0.0)
         t2 = time.perf_counter()
         eng.dataset_free(d)
         t3 = time.perf_counter()

@@ -67,7 +67,8 @@ typedef struct agpc_program {
 /* EP options: GPy EP(epsilon=1e-6, eta=1, delta=1) (expectation_propagation.py); damping = delta. */
 typedef struct agpc_ep_options {
   double epsilon;     /* stop when mean(d tau^2) <= eps and mean(d nu^2) <= eps (tested from sweep 2 on)          */
-  double damping;     /* site update step, 1.0 = GPy default                                                      */
+  double damping;     /* site update step: 1.0 = GPy's delta; <= 0 = automatic schedule (1.0 for 3 sweeps, then   */
+                      /* 0.8), which is what makes the parallel schedule converge wherever sequential EP does     */
   int32_t max_sweeps; /* 0 = keep the supplied sites frozen (2016-GPy optimisation semantics)                     */
   int32_t warm_start; /* 1 = start from tau/nu as supplied, 0 = cold start (tau = nu = 0)                         */
 } agpc_ep_options;

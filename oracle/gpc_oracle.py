@@ -327,22 +327,40 @@ def ep_parallel(K, y, eps=1e-6, max_sweeps=100, damping=1.0, tau0=None, v0=None)
     tau_t = np.zeros(n) if tau0 is None else np.array(tau0, float)
     v_t = np.zeros(n) if v0 is None else np.array(v0, float)
     it, converged, jit_used = 0, False, 0.0
+    floor = TAU_FLOOR_REL / np.diag(K)
     while it < max_sweeps:
         _, sig, mu, jit = posterior_from_sites(K, tau_t, v_t)
         jit_used = max(jit_used, jit)
         tau_cav = 1.0 / sig - tau_t
         v_cav = mu / sig - v_t
         _, mu_hat, s2_hat, _ = moments_match(ypm, tau_cav, v_cav)
-        d_tau = damping * (1.0 / s2_hat - 1.0 / sig)
-        d_v = damping * (mu_hat / s2_hat - mu / sig)
-        new_tau = np.maximum(tau_t + d_tau, TAU_FLOOR_REL / np.diag(K))
-        d_tau = new_tau - tau_t
-        tau_t, v_t = new_tau, v_t + d_v
+        f_tau = 1.0 / s2_hat - 1.0 / sig            # full (undamped) step = the fixed-point residual
+        f_v = mu_hat / s2_hat - mu / sig
+        d = ep_damping(damping, it + 1)
+        new_tau = np.maximum(tau_t + d * f_tau, floor)
+        r_tau = np.maximum(tau_t + f_tau, floor) - tau_t
+        tau_t, v_t = new_tau, v_t + d * f_v
         it += 1
-        if it > 1 and np.mean(d_tau * d_tau) <= eps and np.mean(d_v * d_v) <= eps:
+        # convergence is judged on the undamped residual, so damping never loosens the stopping rule
+        # (identical to GPy's test for damping = 1)
+        if it > 1 and np.mean(r_tau * r_tau) <= eps and np.mean(f_v * f_v) <= eps:
             converged = True
             break
     return EPResult(tau_t, v_t, it, converged, jit_used)
+
+
+EP_AUTO_FREE_SWEEPS, EP_AUTO_DAMPING = 3, 0.8
+
+
+def ep_damping(damping, sweep: int) -> float:
+    """Step size of sweep ``sweep`` (1-based).  ``damping > 0``: constant (1.0 = GPy's delta).  ``damping <= 0`` /
+    None: the engine's automatic schedule -- undamped for the first 3 sweeps, 0.8 afterwards.  Undamped *parallel* EP
+    falls into a limit cycle on strongly correlated priors (large variance x long lengthscale: ~2 % of the evaluations
+    of a search) where GPy's sequential EP converges; 0.8 restores convergence to the same fixed point at the cost of
+    at most one extra sweep on the easy cases."""
+    if damping is None or damping <= 0:
+        return 1.0 if sweep <= EP_AUTO_FREE_SWEEPS else EP_AUTO_DAMPING
+    return float(damping)
 
 
 # --------------------------------------------------------------------------------------------------------------

@@ -64,6 +64,36 @@ def test_score_vs_sequential_ep(engine):
     assert np.all(np.abs(gt["grad"][0, :prog.n_theta] - ot["grad"]) <= GRAD_RTOL * scale)
 
 
+def test_auto_damping_converges_where_undamped_parallel_ep_cycles(engine):
+    """Strongly correlated prior (large variance x long lengthscale): undamped parallel EP limit-cycles (status 3 after
+    max_sweeps), GPy's sequential EP converges; the automatic damping schedule must reach the sequential fixed point."""
+    from autogpc_b200.gpcdata import GPCData
+    X, y = synth(150, 3, 8)
+    tr = GPCData(X, y.reshape(-1, 1), seed=1).kFoldIndices(3)[0][0]   # the fold on which a search run hit the cycle
+    rows = [tr]
+    Xr, yr = X[tr], y[tr]
+    for tree, theta in ((("SE", 2), np.array([11.1748701, 1.25597298])),
+                        (("*", ("SE", 0), ("SE", 2)), np.array([26.69141447, 2.30175307, 11.5477121, 1.34074968])),
+                        (("*", ("PER", 0), ("SE", 2)), np.array([3.5139884, 0.71536986, 8.36953579, 3.38838001, 1.21044942]))):
+        prog = orc.KernelProgram.from_tree(tree)
+        ep = to_engine_program(prog)
+        did = engine.dataset(X, y)
+        und = engine.score_batch(did, [ep], [theta], rows, damping=1.0, max_sweeps=60)
+        auto = engine.score_batch(did, [ep], [theta], rows, damping=0.0)
+        tight = engine.score_batch(did, [ep], [theta], rows, damping=0.0, epsilon=1e-13, max_sweeps=400)
+        engine.dataset_free(did)
+        o_auto = orc.score(prog, theta, Xr, yr, damping=0.0)
+        o_seq = orc.score(prog, theta, Xr, yr, ep="sequential", eps=1e-13, max_sweeps=400, rng=np.random.default_rng(3))
+        assert und["status"][0] == 3                                   # the failure mode this schedule exists for
+        assert auto["status"][0] == 0 and auto["sweeps"][0] == o_auto["sweeps"] and auto["sweeps"][0] <= 25
+        assert abs(auto["nlml"][0] - o_auto["nlml"]) <= 1e-9 * abs(o_auto["nlml"])
+        scale = np.maximum(np.abs(o_auto["grad"]), 1e-3 * np.abs(o_auto["grad"]).max())
+        assert np.all(np.abs(auto["grad"][0, :prog.n_theta] - o_auto["grad"]) <= 1e-6 * scale)
+        assert tight["status"][0] == 0
+        assert abs(tight["nlml"][0] - o_seq["nlml"]) <= NLML_RTOL * abs(o_seq["nlml"])   # same fixed point as GPy's EP
+        assert abs(auto["nlml"][0] - o_seq["nlml"]) <= 2e-5 * abs(o_seq["nlml"])          # at GPy's own epsilon
+
+
 def test_batch_mixed_items_and_folds(engine):
     """Several candidates x folds in one lock-step batch, different n per item, different programs."""
     N, D = 700, 4
@@ -263,64 +293,69 @@ def test_large_n_roundtrip_properties(engine):
 
 # ---- selection parity: the same search on the CUDA engine and on the oracle-backed engine -----------------------
 def test_search_selects_identical_structures_as_oracle(engine):
-    """north_star: identical selected kernel structure and ordering per search depth.  The host (grammar, restarts,
-    L-BFGS-B) is shared; only the scoring back end differs (CUDA engine vs tests/fake_engine.OracleEngine).
+    """north_star: identical selected kernel structure and ordering per search depth.
 
-    The selected kernel of every depth must be identical.  The full ranking of a depth must be identical *modulo
-    near-ties*: L-BFGS-B amplifies last-digit differences of the objective (any BLAS change does the same to GPy), so
-    two weak candidates whose scores differ by less than the tolerance may swap -- the candidate at rank i on the GPU
-    must carry an oracle score within the tolerance of the oracle's rank-i score."""
+    Two parts.  (1) Twin search: the same GPCSearch driven by the CUDA engine and by the oracle-backed engine
+    (tests/fake_engine.OracleEngine; host, grammar, restarts and L-BFGS-B shared) must select the same kernel at every
+    depth.  (2) Replay: L-BFGS-B amplifies last-digit differences of the objective, so the *full* ranking is compared at
+    identical hyper-parameters -- every candidate the GPU search scored is re-scored by the oracle at the GPU's theta*
+    (BIC of the median fold model; CV error over all fold models) and the oracle's ranking of those scores must be the
+    GPU's ranking, position by position."""
     from autogpc_b200 import engine as eng_mod
     from autogpc_b200 import gpckernel
     from autogpc_b200.gpcdata import GPCData
     from autogpc_b200.gpcsearch import GPCSearch
-    from tests.fake_engine import OracleEngine
+    from tests.fake_engine import OracleEngine, _to_oracle
 
     n_points, folds = 150, 3
+    X, y = synth(n_points, 3, 8)
 
     def run(e, criterion):
         eng_mod.set_default_engine(e)
         gpckernel.set_rng(5)
-        X, y = synth(n_points, 3, 8)
         d = GPCData(X, y.reshape(-1, 1), seed=1)
         s = GPCSearch(d, base_kernels="SE,Lin,Per", max_depth=2, beam_width=1, criterion=criterion, n_folds=folds,
-                      max_evals=100)
-        best, best1d = s.search()
-        return ([k.kernel.structure() for k in best],
-                [{k.kernel.structure(): s.score(k) for k in lvl} for lvl in s.history],
-                [[k.kernel.structure() for k in lvl] for lvl in s.history])
+                      max_evals=60)
+        best, _ = s.search()
+        return s, [k.kernel.structure() for k in best]
+
+    def oracle_fold(m):
+        prog = _to_oracle(m._program)
+        th = m.kern.param_array
+        o = orc.score(prog, th, X[m._rows], y[m._rows], p_eff=m._program.p_eff)
+        p, _, _ = orc.predict(prog, th, X[m._rows], X[m._test_rows], o["tau"], o["v"])
+        margin = np.abs(p - 0.5)
+        err = float(np.mean((p - 0.5) * (y[m._test_rows] - 0.5) < 0))
+        return o, err, int(np.sum(margin < 1e-5))
 
     try:
         for criterion in ("bic", "error"):
-            bg, sg, og = run(engine, criterion)
-            bo, so, oo = run(OracleEngine(), criterion)
-            assert bg == bo, (criterion, bg, bo)                       # identical selection at every depth
-            assert len(og) == len(oo)
-            for lvl in range(len(og)):
-                assert sorted(og[lvl]) == sorted(oo[lvl])               # same candidate set
-                assert og[lvl][0] == oo[lvl][0]                         # same winner
-                if criterion == "bic":
-                    # position-by-position over the informative head (candidates clearly better than the pack: the
-                    # rest sit on the flat "explains nothing" plateau, BIC equal to ~0.5 %, where L-BFGS-B stops at
-                    # chaotic points); every candidate's own score must still agree to 2 %
-                    vals = np.array([so[lvl][nm] for nm in oo[lvl]])
-                    cut = vals[0] + 0.5 * (np.median(vals) - vals[0])
-                    for i, name in enumerate(og[lvl]):
-                        ref_i = so[lvl][oo[lvl][i]]
-                        if ref_i <= cut:
-                            assert name == oo[lvl][i] or abs(so[lvl][name] - ref_i) <= 1e-3 * max(1.0, abs(ref_i)), \
-                                (criterion, lvl, i, name, oo[lvl][i])
-                        assert abs(sg[lvl][name] - so[lvl][name]) <= 2e-2 * max(1.0, abs(so[lvl][name])), (criterion, lvl, name)
-                    w = og[lvl][0]
-                    assert abs(sg[lvl][w] - so[lvl][w]) <= 1e-6 * max(1.0, abs(so[lvl][w]))
-                else:
-                    # CV error is a count over held-out points; for uninformative candidates (error ~ 0.5, p* ~ 0.5
-                    # everywhere) a last-digit change of theta flips several points, so only the informative head of
-                    # the ranking is compared position by position
-                    for i, name in enumerate(og[lvl]):
-                        ref_i = so[lvl][oo[lvl][i]]
-                        if ref_i < 0.35:   # informative head: same ranking modulo ties of <= 2 held-out points
-                            assert abs(so[lvl][name] - ref_i) <= 2.5 / n_points, (criterion, lvl, i, name, oo[lvl][i])
-                        assert abs(sg[lvl][name] - so[lvl][name]) <= 0.05, (criterion, lvl, name)
+            sg, bg = run(engine, criterion)
+            so, bo = run(OracleEngine(), criterion)
+            assert bg == bo, (criterion, bg, bo)                                  # (1) identical selection per depth
+            for lvl in sg.history:                                                # (2) replay at the GPU's theta*
+                gpu_scores, orc_scores, names = [], [], []
+                for k in lvl:
+                    names.append(k.kernel.structure())
+                    gpu_scores.append(sg.score(k))
+                    if criterion == "bic":
+                        o, _, _ = oracle_fold(k.model)
+                        assert abs(o["bic"] - k.model.bic) <= 2e-6 * abs(o["bic"]), (names[-1], o["bic"], k.model.bic)
+                        orc_scores.append(o["bic"])
+                    else:
+                        errs, shaky = [], 0
+                        for m in k.foldModels:
+                            o, e, nshaky = oracle_fold(m)
+                            assert abs(o["nlml"] - m._nlml) <= 2e-6 * abs(o["nlml"])
+                            errs.append(e)
+                            shaky += nshaky
+                        orc_scores.append(float(np.mean(errs)))
+                        assert abs(orc_scores[-1] - k.errorRate) <= (shaky + 1e-9) / (len(errs) * 1.0 * n_points / folds) + 1e-12, names[-1]
+                order_g = sorted(range(len(names)), key=lambda i: (gpu_scores[i], names[i]))
+                order_o = sorted(range(len(names)), key=lambda i: (orc_scores[i], names[i]))
+                assert order_g == list(range(len(names)))                        # history is stored in ranked order
+                for a, b in zip(order_g, order_o):                                # same ranking, modulo exact-ish ties
+                    assert a == b or abs(orc_scores[a] - orc_scores[b]) <= 2e-6 * max(1.0, abs(orc_scores[a])), \
+                        (criterion, names[a], names[b], orc_scores[a], orc_scores[b])
     finally:
         eng_mod.set_default_engine(None)
