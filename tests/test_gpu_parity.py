@@ -322,7 +322,7 @@ def test_search_selects_identical_structures_as_oracle(engine):
     def oracle_fold(m):
         prog = _to_oracle(m._program)
         th = m.kern.param_array
-        o = orc.score(prog, th, X[m._rows], y[m._rows], p_eff=m._program.p_eff)
+        o = orc.score(prog, th, X[m._rows], y[m._rows], p_eff=m._program.p_eff, damping=0.0)   # cold EP at theta*
         p, _, _ = orc.predict(prog, th, X[m._rows], X[m._test_rows], o["tau"], o["v"])
         margin = np.abs(p - 0.5)
         err = float(np.mean((p - 0.5) * (y[m._test_rows] - 0.5) < 0))
@@ -340,13 +340,13 @@ def test_search_selects_identical_structures_as_oracle(engine):
                     gpu_scores.append(sg.score(k))
                     if criterion == "bic":
                         o, _, _ = oracle_fold(k.model)
-                        assert abs(o["bic"] - k.model.bic) <= 2e-6 * abs(o["bic"]), (names[-1], o["bic"], k.model.bic)
+                        assert abs(o["bic"] - k.model.bic) <= 1e-5 * abs(o["bic"]), (names[-1], o["bic"], k.model.bic)
                         orc_scores.append(o["bic"])
                     else:
                         errs, shaky = [], 0
                         for m in k.foldModels:
                             o, e, nshaky = oracle_fold(m)
-                            assert abs(o["nlml"] - m._nlml) <= 2e-6 * abs(o["nlml"])
+                            assert abs(o["nlml"] - m._nlml) <= 1e-5 * abs(o["nlml"])   # warm- vs cold-started EP, eps 1e-6
                             errs.append(e)
                             shaky += nshaky
                         orc_scores.append(float(np.mean(errs)))
@@ -355,7 +355,7 @@ def test_search_selects_identical_structures_as_oracle(engine):
                 order_o = sorted(range(len(names)), key=lambda i: (orc_scores[i], names[i]))
                 assert order_g == list(range(len(names)))                        # history is stored in ranked order
                 for a, b in zip(order_g, order_o):                                # same ranking, modulo exact-ish ties
-                    assert a == b or abs(orc_scores[a] - orc_scores[b]) <= 2e-6 * max(1.0, abs(orc_scores[a])), \
+                    assert a == b or abs(orc_scores[a] - orc_scores[b]) <= 1e-5 * max(1.0, abs(orc_scores[a])), \
                         (criterion, names[a], names[b], orc_scores[a], orc_scores[b])
     finally:
         eng_mod.set_default_engine(None)
