@@ -62,8 +62,8 @@ def test_gpclassification_shim_matches_oracle_optimize(fake):
     lo, hi = d.getLengthscaleBounds()
     tr = orc.Transforms(np.array([0, 1, 0, 1]), np.array([0, lo[0], 0, lo[1]]), np.array([0, hi[0], 0, hi[1]]))
     ref = orc.optimize(prog, th0, X, y, tr, damping=0.0)
-    assert -m.log_likelihood() == pytest.approx(ref["nlml"], rel=1e-8)
-    assert np.allclose(m.kern.param_array, ref["theta"], rtol=1e-6)
+    assert -m.log_likelihood() == pytest.approx(ref["nlml"], rel=1e-6)   # warm- vs cold-started final EP (eps 1e-6)
+    assert np.allclose(m.kern.param_array, ref["theta"], rtol=1e-5)
     Phi, _ = m.predict(X[:7])
     assert Phi.shape == (7, 1) and np.all((Phi > 0) & (Phi < 1))
     assert m.bic == pytest.approx(2 * -m.log_likelihood() + 3 * np.log(90))                      # p_eff = 3
