@@ -185,7 +185,8 @@ cudaError_t marginals_launch(const Launch& L, const double* tau, const double* d
                              const int* active);
 cudaError_t ep_update_launch(const Launch& L, double* tau, double* nu, const double* sig, const double* mu,
                              const double* yf, const double* kdiag, const int* n_of, int np, int batch, double eps,
-                             double damping, int* active, int* sweeps, int* status, int* converged, const int* info);
+                             double damping, int min_sweeps, int* active, int* sweeps, int* status, int* converged,
+                             const int* info);
 cudaError_t ep_final_launch(const Launch& L, const double* tau, const double* nu, const double* sig, const double* mu,
                             const double* yf, const double* s, const double* z, const double* Lmat, long long stride,
                             const int* n_of, int np, int batch, const agpc_program* progs, double* alpha, double* nlml,

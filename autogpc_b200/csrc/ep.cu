@@ -186,7 +186,7 @@ __device__ __forceinline__ void block_reduce(double (&v)[NV], double* red /* [32
 __global__ void __launch_bounds__(1024)
 ep_update_kernel(double* __restrict__ tau, double* __restrict__ nu, const double* __restrict__ sig,
                  const double* __restrict__ mu, const double* __restrict__ yf, const double* __restrict__ kdiag,
-                 const int* __restrict__ n_of, int np, double eps, double damping, int* __restrict__ active,
+                 const int* __restrict__ n_of, int np, double eps, double damping, int min_sweeps, int* __restrict__ active,
                  int* __restrict__ sweeps, int* __restrict__ status, int* __restrict__ converged,
                  const int* __restrict__ info) {
   const int b = blockIdx.x;
@@ -237,7 +237,7 @@ ep_update_kernel(double* __restrict__ tau, double* __restrict__ nu, const double
     if (acc[2] > 0.0) {
       status[b] = AGPC_ST_NONFINITE;
       active[b] = 0;
-    } else if (sw > 1 && acc[0] / n <= eps && acc[1] / n <= eps) {
+    } else if (sw >= min_sweeps && acc[0] / n <= eps && acc[1] / n <= eps) {
       converged[b] = 1;
       active[b] = 0;
     }
@@ -246,9 +246,10 @@ ep_update_kernel(double* __restrict__ tau, double* __restrict__ nu, const double
 
 cudaError_t ep_update_launch(const Launch& L, double* tau, double* nu, const double* sig, const double* mu,
                              const double* yf, const double* kdiag, const int* n_of, int np, int batch, double eps,
-                             double damping, int* active, int* sweeps, int* status, int* converged, const int* info) {
+                             double damping, int min_sweeps, int* active, int* sweeps, int* status, int* converged,
+                             const int* info) {
   ProfScope prof_scope(L, CLS_EP);
-  ep_update_kernel<<<batch, 1024, 0, L.stream>>>(tau, nu, sig, mu, yf, kdiag, n_of, np, eps, damping, active, sweeps,
+  ep_update_kernel<<<batch, 1024, 0, L.stream>>>(tau, nu, sig, mu, yf, kdiag, n_of, np, eps, damping, min_sweeps, active, sweeps,
                                                   status, converged, info);
   L.bump();
   return cudaGetLastError();

@@ -282,8 +282,10 @@ int agpc_score_batch_dev(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, con
       } else {
         CK(posterior(L, c, c.active));
       }
+      // GPy measures convergence as the change between two sweeps (hence >= 2 from a cold start); the residual used here
+      // is an absolute fixed-point error, so warm-started sites that are already converged may stop after one sweep
       CK(ep_update_launch(L, c.tau, c.nu, c.sig, c.mu, c.yf, c.kdiag, c.n_of, np, nb, opt->epsilon, opt->damping,
-                          c.active, c.sweeps, c.status, c.converged, c.info));
+                          warm ? 1 : 2, c.active, c.sweeps, c.status, c.converged, c.info));
       int n_active = 0;
       rc = poll_active(ctx, L, c.active, nb, &n_active);
       if (rc) return rc;

@@ -2,93 +2,135 @@
 
 GPy optimises one model at a time with SciPy's L-BFGS-B (paramz ``opt_lbfgsb``: m = 10, factr = 1e7, pgtol = 1e-5,
 <= 1000 evaluations; <= 10 linear-algebra failures tolerated).  To keep those semantics bit-for-bit while giving the
-GPU a batch, every model gets its own SciPy L-BFGS-B instance in a host thread; each objective request parks its
-thread, and a coordinator turns the set of parked requests into ONE ``score_batch`` call.  Threads only wait on the
-GPU, so the GIL is irrelevant.
+GPU a batch, every model owns the state of one SciPy L-BFGS-B instance and is advanced through SciPy's own
+reverse-communication kernel (``scipy.optimize._lbfgsb.setulb``, the routine ``fmin_l_bfgs_b`` loops over) until it
+asks for an objective value; all outstanding requests of a round then become ONE ``score_batch`` call.  No threads:
+the first version parked one ``fmin_l_bfgs_b`` per model on a condition variable and spent 55 ms per round for 90
+models in wake-up storms -- more than the GPU needed for the evaluations at n = 1600.
 """
 from __future__ import annotations
 
-import threading
 from typing import Callable, List, Sequence, Tuple
 
 import numpy as np
-from scipy.optimize import fmin_l_bfgs_b
+from scipy.optimize import _lbfgsb
 
 FAIL_VALUE = 1e300
 ALLOWED_FAILURES = 10
 
+# ``setulb`` task codes (scipy/optimize/_lbfgsb_py.py): 3 = evaluate f and g, 1 = new iteration, 4 = converged, 5 = stop
+_TASK_FG, _TASK_NEW_X, _TASK_CONVERGED, _TASK_STOP = 3, 1, 4, 5
+_INT = np.int64 if getattr(_lbfgsb, "HAS_ILP64", False) else np.int32
+try:  # newer SciPy exposes the flag next to the driver
+    from scipy.optimize._lbfgsb_py import HAS_ILP64 as _ILP64
+    _INT = np.int64 if _ILP64 else np.int32
+except Exception:  # pragma: no cover
+    pass
 
-class _Lockstep:
-    def __init__(self, n: int, eval_batch: Callable[[List[int], List[np.ndarray]], List[Tuple[float, np.ndarray]]]):
-        self.n = n
-        self.eval_batch = eval_batch
-        self.cv = threading.Condition()
-        self.pending = {}
-        self.results = {}
-        self.alive = n
+
+class _Instance:
+    """State of one ``_minimize_lbfgsb`` call (same arrays, same loop, see scipy/optimize/_lbfgsb_py.py)."""
+
+    def __init__(self, x0, m, factr, pgtol, maxfun, maxiter, maxls):
+        n = x0.shape[0]
+        self.m, self.factr, self.pgtol, self.maxfun, self.maxiter, self.maxls = m, factr, pgtol, maxfun, maxiter, maxls
+        self.x = np.array(x0, dtype=np.float64)
+        self.f = np.array(0.0, dtype=np.float64)
+        self.g = np.zeros(n, dtype=np.float64)
+        self.low = np.zeros(n)
+        self.up = np.zeros(n)
+        self.nbd = np.zeros(n, dtype=_INT)          # unbounded: the transforms live in the objective
+        self.wa = np.zeros(2 * m * n + 5 * n + 11 * m * m + 8 * m, np.float64)
+        self.iwa = np.zeros(3 * n, dtype=_INT)
+        self.task = np.zeros(2, dtype=_INT)
+        self.ln_task = np.zeros(2, dtype=_INT)
+        self.lsave = np.zeros(4, dtype=_INT)
+        self.isave = np.zeros(44, dtype=_INT)
+        self.dsave = np.zeros(29, dtype=np.float64)
+        self.nit = 0
+        self.nfev = 0
+        self.last_x = None          # ScalarFunction's cache: f, g are re-used when x has not moved
+        self.done = False
         self.error = None
 
-    def request(self, i: int, x: np.ndarray):
-        with self.cv:
-            self.pending[i] = np.array(x, dtype=float)
-            self.cv.notify_all()
-            while i not in self.results and self.error is None:
-                self.cv.wait()
-            if self.error is not None:
-                raise RuntimeError("batched evaluation failed") from self.error
-            return self.results.pop(i)
+    def set_value(self, x, f, g):
+        self.last_x = np.array(x, copy=True)
+        self.f = f
+        self.g = np.asarray(g, dtype=np.float64)
+        self.nfev += 1
 
-    def finish(self, i: int):
-        with self.cv:
-            self.alive -= 1
-            self.cv.notify_all()
-
-    def coordinate(self):
+    def advance(self):
+        """Runs the SciPy loop until a *new* objective value is needed (returns the point) or the run ends (None)."""
         while True:
-            with self.cv:
-                while self.alive > 0 and len(self.pending) < self.alive:
-                    self.cv.wait()
-                if self.alive == 0:
-                    return
-                idx = sorted(self.pending)
-                xs = [self.pending.pop(i) for i in idx]
-            try:
-                out = self.eval_batch(idx, xs)
-            except BaseException as e:  # propagate to every parked worker
-                with self.cv:
-                    self.error = e
-                    self.cv.notify_all()
-                raise
-            with self.cv:
-                for i, r in zip(idx, out):
-                    self.results[i] = r
-                self.cv.notify_all()
+            self.g = self.g.astype(np.float64)
+            _lbfgsb.setulb(self.m, self.x, self.low, self.up, self.nbd, self.f, self.g, self.factr, self.pgtol, self.wa,
+                           self.iwa, self.task, self.lsave, self.isave, self.dsave, self.maxls, self.ln_task)
+            t = self.task[0]
+            if t == _TASK_FG:
+                if self.last_x is not None and np.array_equal(self.x, self.last_x):
+                    continue                      # cached (the start point was evaluated before the first call)
+                return self.x
+            if t == _TASK_NEW_X:
+                self.nit += 1
+                if self.nit >= self.maxiter:
+                    self.task[0], self.task[1] = _TASK_STOP, 504
+                elif self.nfev > self.maxfun:
+                    self.task[0], self.task[1] = _TASK_STOP, 502
+                continue
+            self.done = True
+            return None
+
+    def result(self):
+        if self.task[0] == _TASK_CONVERGED:
+            warnflag = 0
+        elif self.nfev > self.maxfun or self.nit >= self.maxiter:
+            warnflag = 1
+        else:
+            warnflag = 2
+        info = {"grad": self.g, "funcalls": self.nfev, "nit": self.nit, "warnflag": warnflag,
+                "task": (int(self.task[0]), int(self.task[1]))}
+        return self.x, float(self.f), info
 
 
-def lbfgsb_lockstep(eval_batch, x0s: Sequence[np.ndarray], max_evals: int = 1000, m: int = 10, factr: float = 1e7,
-                    pgtol: float = 1e-5):
-    """Minimise len(x0s) independent objectives; ``eval_batch(indices, xs) -> [(f, g), ...]`` is called with every
-    currently outstanding request.  Returns [(x, f, info)] in input order."""
+def lbfgsb_lockstep(eval_batch: Callable[[List[int], List[np.ndarray]], List[Tuple[float, np.ndarray]]],
+                    x0s: Sequence[np.ndarray], max_evals: int = 1000, m: int = 10, factr: float = 1e7,
+                    pgtol: float = 1e-5, maxiter: int = 15000, maxls: int = 20):
+    """Minimise len(x0s) independent objectives; ``eval_batch(indices, xs) -> [(f, g) | Exception, ...]`` is called
+    with every currently outstanding request.  Returns [(x, f, info) | Exception] in input order -- the same
+    trajectories, values and ``funcalls`` as ``fmin_l_bfgs_b(..., maxfun=max_evals)`` run once per objective."""
     n = len(x0s)
-    ls = _Lockstep(n, eval_batch)
+    inst = [_Instance(np.asarray(x0, dtype=np.float64).ravel(), m, factr, pgtol, max_evals, maxiter, maxls) for x0 in x0s]
     out = [None] * n
-
-    def work(i):
-        try:
-            out[i] = fmin_l_bfgs_b(lambda x: ls.request(i, x), np.array(x0s[i], float), maxfun=max_evals, m=m,
-                                   factr=factr, pgtol=pgtol)
-        except BaseException as e:
-            out[i] = e
-        finally:
-            ls.finish(i)
-
-    threads = [threading.Thread(target=work, args=(i,), daemon=True) for i in range(n)]
-    for t in threads:
-        t.start()
-    ls.coordinate()
-    for t in threads:
-        t.join()
+    # ScalarFunction evaluates the start point at construction
+    pending = {i: inst[i].x for i in range(n)}
+    while pending:
+        idx = sorted(pending)
+        res = eval_batch(idx, [np.array(pending[i], copy=True) for i in idx])
+        nxt = {}
+        # setulb factorises (2m x 2m) matrices through LAPACK: a multi-threaded BLAS spends ~0.3 ms per call spinning
+        # its pool up for them (measured: 28 ms per round of 90 models), so the host BLAS is pinned to one thread here
+        with _single_threaded_blas():
+            for i, r in zip(idx, res):
+                if isinstance(r, BaseException):
+                    out[i] = r
+                    continue
+                inst[i].set_value(pending[i], r[0], r[1])
+                x = inst[i].advance()
+                if x is None:
+                    out[i] = inst[i].result()
+                else:
+                    nxt[i] = x
+        pending = nxt
     return out
+
+
+def _single_threaded_blas():
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=1, user_api="blas")
+    except Exception:  # pragma: no cover - threadpoolctl is optional
+        import contextlib
+        return contextlib.nullcontext()
 
 
 def optimize_models(models, max_evals: int = 1000, warm_start: bool = True):
@@ -128,8 +170,9 @@ def optimize_models(models, max_evals: int = 1000, warm_start: bool = True):
                 st = int(r["status"][b])
                 if st in (2, 4) or not np.isfinite(r["nlml"][b]):
                     fails[i] += 1
-                    if fails[i] > ALLOWED_FAILURES:
-                        raise np.linalg.LinAlgError("too many failed evaluations")
+                    if fails[i] > ALLOWED_FAILURES:   # paramz gives up on THIS model; the others carry on
+                        res[i] = np.linalg.LinAlgError("too many failed evaluations")
+                        continue
                     mdl.status = st
                     res[i] = (FAIL_VALUE, np.zeros_like(x))
                     continue

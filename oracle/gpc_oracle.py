@@ -327,6 +327,9 @@ def ep_parallel(K, y, eps=1e-6, max_sweeps=100, damping=1.0, tau0=None, v0=None)
     tau_t = np.zeros(n) if tau0 is None else np.array(tau0, float)
     v_t = np.zeros(n) if v0 is None else np.array(v0, float)
     it, converged, jit_used = 0, False, 0.0
+    # GPy measures the change between two sweeps (so >= 2 sweeps); the residual is an absolute fixed-point error, so
+    # warm-started sites that are already converged may stop after one sweep
+    min_sweeps = 2 if tau0 is None else 1
     floor = TAU_FLOOR_REL / np.diag(K)
     while it < max_sweeps:
         _, sig, mu, jit = posterior_from_sites(K, tau_t, v_t)
@@ -343,7 +346,7 @@ def ep_parallel(K, y, eps=1e-6, max_sweeps=100, damping=1.0, tau0=None, v0=None)
         it += 1
         # convergence is judged on the undamped residual, so damping never loosens the stopping rule
         # (identical to GPy's test for damping = 1)
-        if it > 1 and np.mean(r_tau * r_tau) <= eps and np.mean(f_v * f_v) <= eps:
+        if it >= min_sweeps and np.mean(r_tau * r_tau) <= eps and np.mean(f_v * f_v) <= eps:
             converged = True
             break
     return EPResult(tau_t, v_t, it, converged, jit_used)
