@@ -126,3 +126,14 @@ def test_add_and_tosummands_score_unoptimised_models(fake):
     one.train(mode="full", n_folds=2, max_evals=20)
     assert one.monotonicity() in (-1, 0, 1)
     assert bestKernels1D([a.add(b)][:0]) == []
+
+
+def test_experiment_shim_runs_search_and_baseline(fake):
+    """gpcexperiment.py:50-61 flow (data -> search -> baseline) on arrays instead of pods downloads."""
+    from autogpc_b200.gpcexperiment import GPCExperiment
+    gpckernel.set_rng(2)
+    X, y = synth(60, 8, 9)
+    out = GPCExperiment(base_kernels="SE", n_folds=2, max_evals=15, verbose=False).pima(X, y, depth=1, width=1)
+    assert out["data"].getDim() == 4 and out["data"].getNum() == 60        # dims=(1,5,6,7) as in the reference
+    assert len(out["best"]) == 2 and out["best"][1].kernel.structure().startswith("SE")
+    assert isinstance(out["baseline"].kernel, ff.ConstKernel) and out["seconds"] > 0
