@@ -152,6 +152,8 @@ struct GradArgs {
   long long ld, g_batch;
   const double* alpha; // [batch][np]   (mode 0)
   const double* s;     // [batch][np]   (mode 0)
+  const double* ru;    // optional (mode 0): extra symmetric rank-2 weight 1/2 (ru_i rv_k + ru_k rv_i)  -- the implicit
+  const double* rv;    //   term of the Laplace gradient ([R&W] 5.24)
   int mode;
   double* partial;     // [batch][tiles][AGPC_MAX_THETA]
   int tiles_per_item;
@@ -191,6 +193,16 @@ cudaError_t ep_final_launch(const Launch& L, const double* tau, const double* nu
                             const double* yf, const double* s, const double* z, const double* Lmat, long long stride,
                             const int* n_of, int np, int batch, const agpc_program* progs, double* alpha, double* nlml,
                             double* nlml_gauss, double* bic, int* status, const int* info);
+cudaError_t laplace_lik_launch(const Launch& L, const double* f, const double* yf, double* W, double* s, double* b,
+                               double* g1, double* d3, const int* n_of, int np, int batch, const int* active);
+cudaError_t laplace_step_launch(const Launch& L, double* f, double* a, const double* f_new, const double* a_new,
+                                const double* yf, double* psi, const int* n_of, int np, int batch, double tol,
+                                int* active, int* iters, int* status, const int* info);
+cudaError_t laplace_final_launch(const Launch& L, const double* f, const double* a, const double* W, const double* g1,
+                                 const double* d3, const double* dB, const double* yf, const double* Lmat,
+                                 long long stride, const int* n_of, int np, int batch, const agpc_program* progs,
+                                 double* s2, double* nlml, double* nlml_gauss, double* bic, int* status, const int* info);
+cudaError_t axpy_launch(const Launch& L, const double* x, const double* y, double alpha, double* out, int np, int batch);
 cudaError_t predict_prob_launch(const Launch& L, const double* mu_s, const double* kss, const double* vsq, double* p,
                                 double* var, long long total);
 

@@ -317,6 +317,176 @@ cudaError_t ep_final_launch(const Launch& L, const double* tau, const double* nu
   return cudaGetLastError();
 }
 
+// ---- Laplace approximation ([R&W] alg. 3.1 / 5.1; oracle.laplace_mode, score_laplace) ------------------------------
+// log p(y|f) = log Phi(y f):  g1 = y h,  W = h (z + h),  d3 = y h ((z + h)(z + 2h) - 1)  with z = y f, h = phi/Phi(z);
+// also s = sqrt(W) and b = W f + g1 (the Newton right-hand side; with tau = W, nu = b the EP posterior formulas give
+// the Laplace posterior, which is how predict_* and the outputs reuse the site form).
+__global__ void laplace_lik_kernel(const double* __restrict__ f, const double* __restrict__ yf, double* __restrict__ W,
+                                   double* __restrict__ s, double* __restrict__ bv, double* __restrict__ g1,
+                                   double* __restrict__ d3, const int* __restrict__ n_of, int np,
+                                   const int* __restrict__ active) {
+  const int b = blockIdx.y;
+  if (active != nullptr && active[b] == 0) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= np) return;
+  const long long o = (long long)b * np + i;
+  if (i >= n_of[b]) {
+    W[o] = s[o] = bv[o] = g1[o] = d3[o] = 0.0;
+    return;
+  }
+  const double y = yf[o], fi = f[o];
+  const double z = y * fi, h = pdf_over_cdf(z);
+  const double w = h * (z + h);
+  W[o] = w;
+  s[o] = sqrt(w);
+  g1[o] = y * h;
+  d3[o] = y * h * ((z + h) * (z + 2.0 * h) - 1.0);
+  bv[o] = w * fi + y * h;
+}
+cudaError_t laplace_lik_launch(const Launch& L, const double* f, const double* yf, double* W, double* s, double* b,
+                               double* g1, double* d3, const int* n_of, int np, int batch, const int* active) {
+  ProfScope prof_scope(L, CLS_EP);
+  dim3 grid((np + 255) / 256, batch);
+  laplace_lik_kernel<<<grid, 256, 0, L.stream>>>(f, yf, W, s, b, g1, d3, n_of, np, active);
+  L.bump();
+  return cudaGetLastError();
+}
+
+// Newton step with halving on psi(f) = -1/2 a^T f + sum log Phi(y f): one CTA per item.
+__global__ void __launch_bounds__(1024)
+laplace_step_kernel(double* __restrict__ f, double* __restrict__ a, const double* __restrict__ f_new,
+                    const double* __restrict__ a_new, const double* __restrict__ yf, double* __restrict__ psi,
+                    const int* __restrict__ n_of, int np, double tol, int* __restrict__ active,
+                    int* __restrict__ iters, int* __restrict__ status, const int* __restrict__ info) {
+  const int b = blockIdx.x;
+  if (active[b] == 0) return;
+  if (info[b] != 0) {
+    if (threadIdx.x == 0) {
+      status[b] = info[b];
+      active[b] = 0;
+    }
+    return;
+  }
+  __shared__ double red[32 * 2];
+  __shared__ double s_step;
+  __shared__ int s_ok;
+  const int n = n_of[b];
+  const long long o0 = (long long)b * np;
+  const double psi_old = (iters[b] == 0) ? n * -0.69314718055994530942 : psi[b];  // cold start: f = a = 0
+  double step = 1.0, psi_t = 0.0;
+  bool ok = false;
+  for (int trial = 0; trial <= 10; ++trial) {
+    double acc[2] = {0.0, 0.0};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const double at = a[o0 + i] + step * (a_new[o0 + i] - a[o0 + i]);
+      const double ft = f[o0 + i] + step * (f_new[o0 + i] - f[o0 + i]);
+      acc[0] += at * ft;
+      acc[1] += log_cdf(yf[o0 + i] * ft);
+    }
+    block_reduce<2>(acc, red);
+    if (threadIdx.x == 0) {
+      const double p = -0.5 * acc[0] + acc[1];
+      s_step = p;
+      s_ok = (p >= psi_old - 1e-12 * fabs(psi_old)) ? 1 : 0;
+    }
+    __syncthreads();
+    psi_t = s_step;
+    ok = s_ok != 0;
+    __syncthreads();
+    if (ok || trial == 10) break;
+    step *= 0.5;
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    a[o0 + i] += step * (a_new[o0 + i] - a[o0 + i]);
+    f[o0 + i] += step * (f_new[o0 + i] - f[o0 + i]);
+  }
+  if (threadIdx.x == 0) {
+    iters[b] += 1;
+    psi[b] = psi_t;
+    if (!isfinite(psi_t)) {
+      status[b] = AGPC_ST_NONFINITE;
+      active[b] = 0;
+    } else if (ok && fabs(psi_t - psi_old) <= tol * fmax(1.0, fabs(psi_t))) {
+      active[b] = 0;
+    }
+  }
+}
+cudaError_t laplace_step_launch(const Launch& L, double* f, double* a, const double* f_new, const double* a_new,
+                                const double* yf, double* psi, const int* n_of, int np, int batch, double tol,
+                                int* active, int* iters, int* status, const int* info) {
+  ProfScope prof_scope(L, CLS_EP);
+  laplace_step_kernel<<<batch, 1024, 0, L.stream>>>(f, a, f_new, a_new, yf, psi, n_of, np, tol, active, iters, status, info);
+  L.bump();
+  return cudaGetLastError();
+}
+
+// log q = -1/2 a^T f + sum log Phi(y f) - sum log L_ii;  s2_i = 1/2 Sigma_ii d3_i with Sigma_ii = (1 - B^-1_ii) / W_i
+__global__ void __launch_bounds__(1024)
+laplace_final_kernel(const double* __restrict__ f, const double* __restrict__ a, const double* __restrict__ W,
+                     const double* __restrict__ g1, const double* __restrict__ d3, const double* __restrict__ dB,
+                     const double* __restrict__ yf, const double* __restrict__ Lmat, long long stride,
+                     const int* __restrict__ n_of, int np, const agpc_program* __restrict__ progs,
+                     double* __restrict__ s2, double* __restrict__ nlml, double* __restrict__ nlml_gauss,
+                     double* __restrict__ bic, int* __restrict__ status, const int* __restrict__ info) {
+  const int b = blockIdx.x;
+  __shared__ double red[32 * 3];
+  const int n = n_of[b];
+  const long long o0 = (long long)b * np;
+  const double* Lb = Lmat + (long long)b * stride;
+  double acc[3] = {0.0, 0.0, 0.0};  // psi terms, sum log L_ii, non-finite count
+  for (int i = threadIdx.x; i < np; i += blockDim.x) {
+    if (i >= n) {
+      s2[o0 + i] = 0.0;
+      continue;
+    }
+    const double lii = Lb[(long long)i * np + i];
+    const double sig = (1.0 - dB[o0 + i]) / W[o0 + i];
+    const double v = 0.5 * sig * d3[o0 + i];
+    s2[o0 + i] = v;
+    acc[0] += -0.5 * a[o0 + i] * f[o0 + i] + log_cdf(yf[o0 + i] * f[o0 + i]);
+    acc[1] += log(lii);
+    if (!isfinite(v) || !(lii > 0.0)) acc[2] += 1.0;
+  }
+  block_reduce<3>(acc, red);
+  if (threadIdx.x == 0) {
+    const double v = -(acc[0] - acc[1]);
+    nlml[b] = v;
+    nlml_gauss[b] = v;
+    bic[b] = 2.0 * v + progs[b].p_eff * log((double)n);
+    if (info[b] != 0) status[b] = info[b];
+    else if ((acc[2] > 0.0 || !isfinite(v)) && status[b] != AGPC_ST_NOT_PD) status[b] = AGPC_ST_NONFINITE;
+    if (status[b] == AGPC_ST_NOT_PD || status[b] == AGPC_ST_NONFINITE) {
+      nlml[b] = CUDART_INF;
+      nlml_gauss[b] = CUDART_INF;
+      bic[b] = CUDART_INF;
+    }
+  }
+}
+cudaError_t laplace_final_launch(const Launch& L, const double* f, const double* a, const double* W, const double* g1,
+                                 const double* d3, const double* dB, const double* yf, const double* Lmat,
+                                 long long stride, const int* n_of, int np, int batch, const agpc_program* progs,
+                                 double* s2, double* nlml, double* nlml_gauss, double* bic, int* status, const int* info) {
+  ProfScope prof_scope(L, CLS_EP);
+  laplace_final_kernel<<<batch, 1024, 0, L.stream>>>(f, a, W, g1, d3, dB, yf, Lmat, stride, n_of, np, progs, s2, nlml,
+                                                      nlml_gauss, bic, status, info);
+  L.bump();
+  return cudaGetLastError();
+}
+
+// out = x + alpha * y
+__global__ void axpy_kernel(const double* __restrict__ x, const double* __restrict__ y, double alpha,
+                            double* __restrict__ out, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) out[i] = x[i] + alpha * y[i];
+}
+cudaError_t axpy_launch(const Launch& L, const double* x, const double* y, double alpha, double* out, int np, int batch) {
+  ProfScope prof_scope(L, CLS_EP);
+  const long long total = (long long)np * batch;
+  axpy_kernel<<<(unsigned)((total + 255) / 256), 256, 0, L.stream>>>(x, y, alpha, out, total);
+  L.bump();
+  return cudaGetLastError();
+}
+
 // ---- predictive probability p* = Phi(mu* / sqrt(1 + v*)) -------------------------------------------------------
 __global__ void predict_prob_kernel(const double* __restrict__ mu_s, const double* __restrict__ kss,
                                     const double* __restrict__ vsq, double* __restrict__ p, double* __restrict__ var,

@@ -513,6 +513,11 @@ grad_contract_kernel(const GradArgs a) {
       if (j > i) continue;
       const double g = Gb[(long long)i * a.ld + j];
       w = 0.5 * (al[i] * al[j] - sv[i] * g * sv[j]);
+      if (a.ru != nullptr) {
+        const double* ru = a.ru + (long long)b * a.np;
+        const double* rv = a.rv + (long long)b * a.np;
+        w += 0.5 * (ru[i] * rv[j] + ru[j] * rv[i]);
+      }
       if (j < i) w *= 2.0;
     } else {
       w = Gb[(long long)i * a.ld + j];

@@ -165,6 +165,75 @@ int poll_active(agpc_ctx* ctx, const Launch& L, const int* active_dev, int nb, i
   return AGPC_OK;
 }
 
+// Laplace approximation for one lock-step chunk ([R&W] alg. 3.1 with step halving, then alg. 5.1); K is already built.
+// Vector roles: mu = f, alpha = a = K^-1 f, tau = W, s = sqrt(W), nu = b = W f + grad, w = grad log p, sig = d3.
+int laplace_chunk(agpc_ctx* ctx, Launch& L, Chunk& c, const agpc_ep_options* opt, int theta_stride, bool want_grad, int D) {
+  const int np = c.np, nb = c.nb;
+  const long long st = c.ms.stride;
+  const size_t vec = sizeof(double) * (size_t)nb * np;
+  CK(cudaMemsetAsync(c.mu, 0, vec, L.stream));
+  CK(cudaMemsetAsync(c.alpha, 0, vec, L.stream));
+  CK(cudaMemsetAsync(c.nlml_gauss, 0, sizeof(double) * nb, L.stream));  // psi per item lives here during the iteration
+  const int max_iter = opt->max_sweeps > 0 ? opt->max_sweeps : 50;
+  const double tol = opt->epsilon > 0.0 ? opt->epsilon : 1e-10;
+  const double n2 = 8.0 * L.work_n * L.work_n;
+  for (int it = 1; it <= max_iter; ++it) {
+    L.add_work(CLS_FORMB, n2 * L.work_items);
+    L.add_work(CLS_MATVEC, 3.0 * n2 * L.work_items);
+    CK(laplace_lik_launch(L, c.mu, c.yf, c.tau, c.s, c.nu, c.w, c.sig, c.n_of, np, nb, c.active));
+    CK(form_B_launch(L, c.ms.K, c.s, c.ms.A, np, st, nb, c.active));
+    CK(potrf_blocked(L, c.ms, c.active, c.info));
+    CK(trtri_blocked(L, c.ms, c.active));
+    CK(rowdot_launch(L, 0, false, c.ms.K, c.nu, c.kv, nullptr, np, np, st, np, np, nb, c.active));   // K b
+    CK(mul_launch(L, c.s, c.kv, c.u, np, nb, c.active));
+    CK(rowdot_launch(L, 1, false, c.ms.M, c.u, c.t, nullptr, np, np, st, np, np, nb, c.active));
+    CK(rowdot_launch(L, 2, false, c.ms.U, c.t, c.z, nullptr, np, np, st, np, np, nb, c.active));     // B^-1 (s o K b)
+    CK(mul_launch(L, c.s, c.z, c.tmp, np, nb, c.active));
+    CK(axpy_launch(L, c.nu, c.tmp, -1.0, c.u, np, nb));                                              // a_new
+    CK(rowdot_launch(L, 0, false, c.ms.K, c.u, c.kv, nullptr, np, np, st, np, np, nb, c.active));    // f_new = K a_new
+    CK(laplace_step_launch(L, c.mu, c.alpha, c.kv, c.u, c.yf, c.nlml_gauss, c.n_of, np, nb, tol, c.active, c.sweeps,
+                           c.status, c.info));
+    int n_active = 0;
+    int rc = poll_active(ctx, L, c.active, nb, &n_active);
+    if (rc) return rc;
+    if (n_active == 0) break;
+    L.work_items = n_active;
+  }
+  L.work_items = nb;
+  mark_unconverged_kernel<<<(nb + 255) / 256, 256, 0, L.stream>>>(c.active, c.status, nb);
+  L.bump();
+  // quantities at the final mode
+  CK(cudaMemsetAsync(c.info, 0, sizeof(int) * nb, L.stream));
+  L.add_work(CLS_FORMB, n2 * nb);
+  L.add_work(CLS_MATVEC, 2.5 * n2 * nb);
+  CK(laplace_lik_launch(L, c.mu, c.yf, c.tau, c.s, c.nu, c.w, c.sig, c.n_of, np, nb, nullptr));
+  CK(form_B_launch(L, c.ms.K, c.s, c.ms.A, np, st, nb, nullptr));
+  CK(potrf_blocked(L, c.ms, nullptr, c.info));
+  CK(trtri_blocked(L, c.ms, nullptr));
+  CK(rowdot_launch(L, 2, true, c.ms.U, c.nu, c.tmp, c.dB, np, np, st, np, np, nb, nullptr));         // diag(B^-1)
+  CK(laplace_final_launch(L, c.mu, c.alpha, c.tau, c.w, c.sig, c.dB, c.yf, c.ms.A, st, c.n_of, np, nb, c.progs, c.z,
+                          c.nlml, c.nlml_gauss, c.bic, c.status, c.info));
+  if (want_grad) {
+    // u = s2 - R K s2,  R = S^1/2 B^-1 S^1/2
+    CK(rowdot_launch(L, 0, false, c.ms.K, c.z, c.kv, nullptr, np, np, st, np, np, nb, nullptr));
+    CK(mul_launch(L, c.s, c.kv, c.u, np, nb, nullptr));
+    CK(rowdot_launch(L, 1, false, c.ms.M, c.u, c.t, nullptr, np, np, st, np, np, nb, nullptr));
+    CK(rowdot_launch(L, 2, false, c.ms.U, c.t, c.tmp, nullptr, np, np, st, np, np, nb, nullptr));
+    CK(mul_launch(L, c.s, c.tmp, c.u, np, nb, nullptr));
+    CK(axpy_launch(L, c.z, c.u, -1.0, c.dB, np, nb));
+    CK(lauum_blocked(L, c.ms, c.ms.T, nullptr));
+    GradArgs ga{};
+    ga.progs = c.progs; ga.theta = c.theta; ga.theta_stride = theta_stride; ga.Xf = c.Xf; ga.n_of = c.n_of;
+    ga.np = np; ga.D = D; ga.G = c.ms.T; ga.ld = np; ga.g_batch = st; ga.alpha = c.alpha; ga.s = c.s;
+    ga.ru = c.dB; ga.rv = c.w;
+    ga.mode = 0; ga.partial = c.partial; ga.tiles_per_item = grad_tiles(np, 0); ga.active = nullptr;
+    L.add_work(CLS_GRAD, 4.0 * L.work_n * L.work_n * nb);
+    CK(cudaMemsetAsync(c.grad, 0, sizeof(double) * (size_t)nb * theta_stride, L.stream));
+    CK(grad_contract_launch(L, ga, nb, -1.0, c.grad, theta_stride));
+  }
+  return AGPC_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -263,8 +332,16 @@ int agpc_score_batch_dev(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, con
     L.add_work(CLS_KBUILD, 8.0 * L.work_n * L.work_n * nb);
     CK(build_K_launch(L, ba, nb, false));
 
-    const bool frozen = opt->max_sweeps <= 0;
-    const bool warm = frozen || opt->warm_start != 0;
+    const bool laplace = opt->inference == AGPC_INFER_LAPLACE;
+    const bool frozen = !laplace && opt->max_sweeps <= 0;
+    const bool warm = !laplace && (frozen || opt->warm_start != 0);
+    if (laplace) {
+      rc = laplace_chunk(ctx, L, c, opt, theta_stride, grad_dev != nullptr, ds.D);
+      if (rc) return rc;
+      if (grad_dev)
+        CK(cudaMemcpyAsync(grad_dev + (size_t)first * theta_stride, c.grad, sizeof(double) * (size_t)nb * theta_stride,
+                           cudaMemcpyDeviceToDevice, L.stream));
+    } else {
     if (warm) {
       copy_strided_kernel<<<gvec, tb, 0, L.stream>>>(c.tau, np, tau_dev + (size_t)first * site_stride, site_stride, c.n_of, np, 1);
       copy_strided_kernel<<<gvec, tb, 0, L.stream>>>(c.nu, np, nu_dev + (size_t)first * site_stride, site_stride, c.n_of, np, 1);
@@ -316,6 +393,7 @@ int agpc_score_batch_dev(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, con
       CK(cudaMemcpyAsync(grad_dev + (size_t)first * theta_stride, c.grad, sizeof(double) * (size_t)nb * theta_stride,
                          cudaMemcpyDeviceToDevice, L.stream));
     }
+    }  // EP
     // ---- outputs ----
     CK(cudaMemcpyAsync(nlml_dev + first, c.nlml, sizeof(double) * nb, cudaMemcpyDeviceToDevice, L.stream));
     if (bic_dev) CK(cudaMemcpyAsync(bic_dev + first, c.bic, sizeof(double) * nb, cudaMemcpyDeviceToDevice, L.stream));

@@ -15,6 +15,7 @@ MAX_LEAVES, MAX_TERMS, MAX_TERM_LEN, MAX_THETA = 16, 16, 8, 48
 LEAF_SE, LEAF_PER, LEAF_LIN, LEAF_CONST = 0, 1, 2, 3
 LEAF_NPARAM = {LEAF_SE: 2, LEAF_PER: 3, LEAF_LIN: 2, LEAF_CONST: 1}
 ST_OK, ST_JITTER, ST_NOT_PD, ST_EP_NOT_CONVERGED, ST_NONFINITE = 0, 1, 2, 3, 4
+INFER_EP, INFER_LAPLACE = 0, 1
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libautogpc_b200.so")
 
@@ -62,7 +63,8 @@ class Program(C.Structure):
 
 
 class EPOptions(C.Structure):
-    _fields_ = [("epsilon", C.c_double), ("damping", C.c_double), ("max_sweeps", C.c_int32), ("warm_start", C.c_int32)]
+    _fields_ = [("epsilon", C.c_double), ("damping", C.c_double), ("max_sweeps", C.c_int32), ("warm_start", C.c_int32),
+                ("inference", C.c_int32), ("reserved", C.c_int32)]
 
 
 _lib = None
@@ -147,7 +149,7 @@ class Engine:
     def score_batch(self, dataset: int, programs: Sequence[Program], thetas: Sequence[np.ndarray],
                     rows: Sequence[np.ndarray], epsilon: float = 1e-6, damping: float = 1.0, max_sweeps: int = 100,
                     tau: Optional[Sequence[np.ndarray]] = None, nu: Optional[Sequence[np.ndarray]] = None,
-                    want_grad: bool = True, frozen_sites: bool = False) -> dict:
+                    want_grad: bool = True, frozen_sites: bool = False, inference: str = "ep") -> dict:
         """Scores B items; item b = (programs[b], thetas[b], rows[b]).  Returns a dict of NumPy arrays
         (nlml, grad[B x P_max], bic, nlml_gauss, sweeps, status) and lists tau/nu of per-item site vectors."""
         B = len(programs)
@@ -173,7 +175,11 @@ class Engine:
             for b in range(B):
                 tau_a[b, :len(rows[b])] = tau[b]
                 nu_a[b, :len(rows[b])] = nu[b]
-        opt = EPOptions(float(epsilon), float(damping), 0 if frozen_sites else int(max_sweeps), 1 if warm else 0)
+        if inference not in ("ep", "laplace"):
+            raise EngineError("inference must be 'ep' or 'laplace'")
+        lap = inference == "laplace"
+        opt = EPOptions(float(epsilon), float(damping), 0 if frozen_sites else int(max_sweeps),
+                        1 if (warm and not lap) else 0, INFER_LAPLACE if lap else INFER_EP, 0)
         progs = (Program * B)(*programs)
         nlml = np.zeros(B)
         grad = np.zeros((B, stride))

@@ -262,9 +262,13 @@ class GPClassification:
 
     def __init__(self, X=None, Y=None, kernel: Optional[Kern] = None, engine: Optional[_eng.Engine] = None,
                  _dataset: Optional[int] = None, _rows: Optional[np.ndarray] = None, _infer: bool = True,
-                 ep_epsilon: float = 1e-6, ep_damping: float = 0.0, ep_max_sweeps: int = 100):
+                 ep_epsilon: float = 1e-6, ep_damping: float = 0.0, ep_max_sweeps: int = 100,
+                 inference_method=None):
         self.engine = engine if engine is not None else _eng.default_engine()
         self.ep = dict(epsilon=ep_epsilon, damping=ep_damping, max_sweeps=ep_max_sweeps)
+        # GPy: GPClassification(..., inference_method=GPy.inference.latent_function_inference.Laplace()); default EP
+        if inference_method is not None and getattr(inference_method, "name", str(inference_method)).lower() == "laplace":
+            self.ep = dict(epsilon=1e-10, damping=0.0, max_sweeps=50, inference="laplace")
         self._owns_dataset = _dataset is None
         if _dataset is None:
             X = np.asarray(X, float)
@@ -363,3 +367,14 @@ class GPClassification:
 
 
 models = SimpleNamespace(GPClassification=GPClassification)
+
+
+class _EP:
+    name = "ep"
+
+
+class _Laplace:
+    name = "laplace"
+
+
+inference = SimpleNamespace(latent_function_inference=SimpleNamespace(EP=_EP, Laplace=_Laplace))

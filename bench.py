@@ -274,7 +274,7 @@ def main():
     sweeps_d = torch.zeros(B, dtype=torch.int32, device=dev)
     status_d = torch.zeros(B, dtype=torch.int32, device=dev)
     prog_arr = (Program * B)(*progs)
-    opt = EPOptions(1e-6, 0.0, 100, 0)   # damping 0 = the engine's automatic schedule (production default)
+    opt = EPOptions(1e-6, 0.0, 100, 0, 0, 0)   # damping 0 = the engine's automatic schedule (production default)
     did = eng.dataset(data.X, data.Y)
     # one explicit stream for torch, the timing events and the engine's launches (a NULL stream would make the engine use
     # its own non-blocking stream, which torch.cuda.Event on the default stream does not see)

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define AGPC_VERSION 100
+#define AGPC_VERSION 101
 
 /* error codes */
 #define AGPC_OK 0
@@ -71,7 +71,14 @@ typedef struct agpc_ep_options {
                       /* 0.8), which is what makes the parallel schedule converge wherever sequential EP does     */
   int32_t max_sweeps; /* 0 = keep the supplied sites frozen (2016-GPy optimisation semantics)                     */
   int32_t warm_start; /* 1 = start from tau/nu as supplied, 0 = cold start (tau = nu = 0)                         */
+  int32_t inference;  /* AGPC_INFER_EP (GPy's default for GPClassification) or AGPC_INFER_LAPLACE (R&W alg. 3.1 + */
+                      /* 5.1; epsilon = relative tolerance on the Newton objective, max_sweeps = Newton iterations,*/
+                      /* always cold-started; tau / nu return W and W f + grad log p, the site form of the         */
+                      /* Laplace posterior, so agpc_predict_* work unchanged)                                       */
+  int32_t reserved;
 } agpc_ep_options;
+#define AGPC_INFER_EP 0
+#define AGPC_INFER_LAPLACE 1
 
 typedef struct agpc_ctx agpc_ctx;
 

@@ -485,6 +485,102 @@ def score(prog: KernelProgram, theta, X, y, eps=1e-6, max_sweeps=100, damping=1.
     return out
 
 
+# --------------------------------------------------------------------------------------------------------------
+# Laplace approximation ([R&W] Algorithms 3.1 and 5.1) -- north_star's "(or Laplace)".  No reference behaviour exists:
+# AutoGPC never selects it (GPClassification defaults to EP); flexible_function.py:2021-2028 only names it.
+# --------------------------------------------------------------------------------------------------------------
+LAPLACE_TOL, LAPLACE_MAX_ITER, LAPLACE_MAX_HALVINGS = 1e-10, 50, 10
+
+
+def probit_derivatives(ypm, f):
+    """log p(y|f) = log Phi(y f) and its first three derivatives in f.  With z = y f, h = phi(z)/Phi(z):
+    d1 = y h,  d2 = -h (z + h) = -W,  d3 = y h ((z + h)(z + 2h) - 1)."""
+    z = ypm * f
+    h = pdf_over_cdf(z)
+    return log_cdf(z), ypm * h, h * (z + h), ypm * h * ((z + h) * (z + 2.0 * h) - 1.0)
+
+
+def laplace_mode(K, y, tol=LAPLACE_TOL, max_iter=LAPLACE_MAX_ITER, f0=None, a0=None):
+    """Newton iteration of [R&W] Alg. 3.1 with step halving on psi(f) = -1/2 a^T f + sum log p(y|f), a = K^-1 f.
+    Returns dict(f, a, W, grad, d3, psi, L, iters, converged, jitter); L = chol(I + W^1/2 K W^1/2) at the final f."""
+    ypm = labels_pm1(y)
+    n = K.shape[0]
+    f = np.zeros(n) if f0 is None else np.array(f0, float)
+    a = np.zeros(n) if a0 is None else np.array(a0, float)
+    lp, d1, W, _ = probit_derivatives(ypm, f)
+    psi = -0.5 * float(a @ f) + float(np.sum(lp))
+    it, converged, jit_used = 0, False, 0.0
+    while it < max_iter:
+        sW = np.sqrt(W)
+        B = np.eye(n) + sW[:, None] * K * sW[None, :]
+        L, jit = jitchol(B)
+        jit_used = max(jit_used, jit)
+        b = W * f + d1
+        a_new = b - sW * sla.cho_solve((L, True), sW * (K @ b), check_finite=False)
+        f_new = K @ a_new
+        step, ok = 1.0, False
+        for _ in range(LAPLACE_MAX_HALVINGS + 1):
+            a_t = a + step * (a_new - a)
+            f_t = f + step * (f_new - f)
+            psi_t = -0.5 * float(a_t @ f_t) + float(np.sum(log_cdf(ypm * f_t)))
+            if psi_t >= psi - 1e-12 * abs(psi):
+                ok = True
+                break
+            step *= 0.5
+        it += 1
+        d_psi = psi_t - psi
+        a, f, psi = a_t, f_t, psi_t
+        lp, d1, W, _ = probit_derivatives(ypm, f)
+        if ok and abs(d_psi) <= tol * max(1.0, abs(psi)):
+            converged = True
+            break
+    lp, d1, W, d3 = probit_derivatives(ypm, f)
+    sW = np.sqrt(W)
+    L, jit = jitchol(np.eye(n) + sW[:, None] * K * sW[None, :])
+    return dict(f=f, a=a, W=W, grad=d1, d3=d3, psi=-0.5 * float(a @ f) + float(np.sum(lp)), L=L, iters=it,
+                converged=converged, jitter=max(jit_used, jit))
+
+
+def score_laplace(prog: KernelProgram, theta, X, y, p_eff: Optional[int] = None, tol=LAPLACE_TOL,
+                  max_iter=LAPLACE_MAX_ITER):
+    """NLML = -log q(y|X, theta) of the Laplace approximation, its gradient ([R&W] Alg. 5.1: explicit part + the
+    implicit part through the mode), BIC, and the posterior in the engine's site form: tau = W, v = W f + grad, for
+    which the EP posterior formulas (and ``predict``) return the Laplace posterior N(f, (K^-1 + W)^-1)."""
+    theta = np.asarray(theta, float)
+    X = np.asarray(X, float)
+    n = X.shape[0]
+    try:
+        K = kern_K(prog, theta, X)
+        m = laplace_mode(K, y, tol, max_iter)
+    except sla.LinAlgError:
+        P = prog.n_theta
+        return dict(status=ST_NOT_PD, sweeps=0, nlml=float("inf"), nlml_gauss=float("inf"), grad=np.zeros(P),
+                    bic=float("inf"), tau=None, v=None)
+    W, a, f, L = m["W"], m["a"], m["f"], m["L"]
+    sW = np.sqrt(W)
+    log_q = m["psi"] - float(np.sum(np.log(np.diag(L))))
+    Binv = sla.cho_solve((L, True), np.eye(n), check_finite=False)
+    R = sW[:, None] * Binv * sW[None, :]
+    sig_diag = (1.0 - np.diag(Binv)) / W                     # diag((K^-1 + W)^-1) = (1 - B^-1_ii) / W_i
+    # d log q / d theta_j = 1/2 a^T C a - 1/2 tr(R C) + s2^T (I - K R) C grad,   C = dK/dtheta_j          ([R&W] 5.22-5.24)
+    # with s2_i = 1/2 Sigma_ii d3_i (d3 = third derivative of log p); checked by finite differences in tests/test_oracle.py
+    s2 = 0.5 * sig_diag * m["d3"]
+    u = s2 - R @ (K @ s2)
+    G = 0.5 * (np.outer(a, a) - R) + 0.5 * (np.outer(u, m["grad"]) + np.outer(m["grad"], u))
+    g = kern_grad(prog, theta, X, G)                          # d log q / d theta
+    nlml = -log_q
+    p_eff = n_effective_params(prog) if p_eff is None else p_eff
+    st = ST_OK
+    if m["jitter"] > 0:
+        st = ST_JITTER
+    if not m["converged"]:
+        st = ST_EP_NOT_CONVERGED
+    if not (np.isfinite(nlml) and np.all(np.isfinite(g))):
+        st = ST_NONFINITE
+    return dict(status=st, sweeps=m["iters"], nlml=nlml, nlml_gauss=nlml, grad=-g, dlogz=g, bic=bic(nlml, p_eff, n),
+                tau=W, v=W * f + m["grad"], alpha=a, f=f, K=K, sig_diag=sig_diag, L=L)
+
+
 def predict(prog: KernelProgram, theta, X, Xstar, tau_t, v_t, K=None):
     """[GPy] GP.predict: mu* = K*^T alpha, v* = k** - diag(K*^T W^-1 K*), p* = Phi(mu*/sqrt(1+v*)).  gpckernel.py:832."""
     theta = np.asarray(theta, float)

@@ -30,7 +30,7 @@ class OracleEngine:
         self._ds.pop(did, None)
 
     def score_batch(self, dataset, programs, thetas, rows, epsilon=1e-6, damping=1.0, max_sweeps=100, tau=None, nu=None,
-                    want_grad=True, frozen_sites=False):
+                    want_grad=True, frozen_sites=False, inference="ep"):
         X, y = self._ds[dataset]
         B = len(programs)
         self.calls += 1
@@ -39,9 +39,14 @@ class OracleEngine:
         out = dict(nlml=np.zeros(B), grad=np.zeros((B, stride)), bic=np.zeros(B), nlml_gauss=np.zeros(B),
                    sweeps=np.zeros(B, dtype=np.int32), status=np.zeros(B, dtype=np.int32), tau=[], nu=[])
         for b in range(B):
-            r = orc.score(_to_oracle(programs[b]), thetas[b], X[rows[b]], y[rows[b]], eps=epsilon, max_sweeps=max_sweeps,
-                          damping=damping, p_eff=programs[b].p_eff, tau0=None if tau is None else tau[b],
-                          v0=None if nu is None else nu[b], frozen_sites=frozen_sites)
+            if inference == "laplace":
+                r = orc.score_laplace(_to_oracle(programs[b]), thetas[b], X[rows[b]], y[rows[b]], p_eff=programs[b].p_eff,
+                                      tol=epsilon, max_iter=max_sweeps)
+            else:
+                r = orc.score(_to_oracle(programs[b]), thetas[b], X[rows[b]], y[rows[b]], eps=epsilon,
+                              max_sweeps=max_sweeps, damping=damping, p_eff=programs[b].p_eff,
+                              tau0=None if tau is None else tau[b], v0=None if nu is None else nu[b],
+                              frozen_sites=frozen_sites)
             out["status"][b], out["sweeps"][b] = r["status"], r["sweeps"]
             out["nlml"][b], out["bic"][b], out["nlml_gauss"][b] = r["nlml"], r["bic"], r["nlml_gauss"]
             out["grad"][b, :programs[b].n_theta] = r["grad"]

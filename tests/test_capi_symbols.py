@@ -34,7 +34,7 @@ def test_header_symbols_are_exported():
 def test_library_loads_and_reports_version_without_gpu():
     _ensure_built()
     lib = ctypes.CDLL(LIB)
-    assert lib.agpc_version() == 100
+    assert lib.agpc_version() == 101
     ctx = ctypes.c_void_p()
     rc = lib.agpc_create(0, ctypes.byref(ctx))
     if rc == 0:            # a GPU is present (GPU box): clean up

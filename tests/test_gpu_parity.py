@@ -94,6 +94,34 @@ def test_auto_damping_converges_where_undamped_parallel_ep_cycles(engine):
         assert abs(auto["nlml"][0] - o_seq["nlml"]) <= 2e-5 * abs(o_seq["nlml"])          # at GPy's own epsilon
 
 
+@pytest.mark.parametrize("name", ["se0xse1", "se0xse1+per3+se2", "mix", "const"])
+def test_laplace_matches_oracle(engine, name):
+    """north_star's "(or Laplace)": Newton mode finding + R&W alg. 5.1 gradient on the same kernels (potrf / trtri / lauum,
+    fused contraction with the implicit rank-2 term) against oracle.score_laplace; predict through the site form."""
+    X, y = synth(330, 4, 12)
+    prog = orc.KernelProgram.from_tree(TREES[name])
+    th = random_theta(prog, np.random.default_rng(8))
+    tr, te = np.arange(0, 290, dtype=np.int32), np.arange(290, 330, dtype=np.int32)
+    ep = to_engine_program(prog)
+    did = engine.dataset(X, y)
+    g = engine.score_batch(did, [ep, ep], [th, th * 1.1], [tr, tr[:200]], inference="laplace", epsilon=1e-10, max_sweeps=50)
+    p, mu, var, _ = engine.predict_batch(did, [ep], [th], [tr], [g["tau"][0]], [g["nu"][0]], [te], want_latent=True)
+    engine.dataset_free(did)
+    for b, (theta, rows) in enumerate(((th, tr), (th * 1.1, tr[:200]))):
+        o = orc.score_laplace(prog, theta, X[rows], y[rows])
+        assert g["status"][b] == o["status"] == 0 and g["sweeps"][b] == o["sweeps"]
+        assert abs(g["nlml"][b] - o["nlml"]) <= 1e-9 * abs(o["nlml"])
+        assert abs(g["bic"][b] - o["bic"]) <= 1e-9 * abs(o["bic"])
+        scale = np.maximum(np.abs(o["grad"]), 1e-3 * np.abs(o["grad"]).max())
+        assert np.all(np.abs(g["grad"][b, :prog.n_theta] - o["grad"]) <= 1e-7 * scale)
+        assert np.allclose(g["tau"][b], o["tau"], rtol=1e-8, atol=1e-14)
+        assert np.allclose(g["nu"][b], o["v"], rtol=1e-8, atol=1e-10)
+    o = orc.score_laplace(prog, th, X[tr], y[tr])
+    po, muo, varo = orc.predict(prog, th, X[tr], X[te], o["tau"], o["v"])
+    assert np.allclose(mu[0], muo, rtol=1e-8, atol=1e-10) and np.allclose(var[0], varo, rtol=1e-7, atol=1e-10)
+    assert np.allclose(p[0], po, rtol=1e-8, atol=1e-12)
+
+
 def test_batch_mixed_items_and_folds(engine):
     """Several candidates x folds in one lock-step batch, different n per item, different programs."""
     N, D = 700, 4

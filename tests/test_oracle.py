@@ -144,3 +144,41 @@ def test_golden_fixtures(name):
     assert np.allclose(r["tau"], g["tau"], rtol=1e-8, atol=1e-12)
     p, _, _ = orc.predict(prog, g["theta"], g["X"], g["Xstar"], r["tau"], r["v"])
     assert np.allclose(p, g["pstar"], rtol=1e-9, atol=1e-12)
+
+
+# ---- Laplace approximation (R&W alg. 3.1 / 5.1) -------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["se0xse1", "se0xse1+per3+se2", "mix"])
+def test_laplace_gradient_fd_and_site_form(name):
+    from tests.util import TREES, random_theta, synth
+    X, y = synth(90, 4, 3)
+    prog = orc.KernelProgram.from_tree(TREES[name])
+    th = random_theta(prog, np.random.default_rng(2))
+    r = orc.score_laplace(prog, th, X, y)
+    assert r["status"] == 0 and r["sweeps"] <= 15
+    g = np.zeros_like(th)
+    for j in range(len(th)):
+        h = 1e-5 * max(1.0, abs(th[j]))
+        tp, tm = th.copy(), th.copy()
+        tp[j] += h
+        tm[j] -= h
+        g[j] = (orc.score_laplace(prog, tp, X, y)["nlml"] - orc.score_laplace(prog, tm, X, y)["nlml"]) / (2 * h)
+    assert np.all(np.abs(g - r["grad"]) <= 1e-6 * np.maximum(np.abs(g), 1e-3 * np.abs(g).max()))
+    # the mode is a fixed point of the Newton map, and the (tau = W, v = W f + grad) site form reproduces the posterior
+    e = orc.ep_log_marginal(r["K"], y, r["tau"], r["v"])
+    assert np.allclose(e["mu"], r["f"], atol=1e-9) and np.allclose(e["alpha"], r["alpha"], atol=1e-9)
+    assert np.allclose(e["sig_diag"], r["sig_diag"], rtol=1e-9)
+    # Laplace and EP approximate the same marginal likelihood: same ball park, Laplace (mode-based) is the larger NLML
+    ep = orc.score(prog, th, X, y, damping=0.0)
+    assert 0 < r["nlml"] - ep["nlml"] < 0.05 * ep["nlml"]
+
+
+def test_probit_derivatives_fd():
+    f = np.linspace(-4, 4, 41)
+    for ypm in (1.0, -1.0):
+        lp, d1, W, d3 = orc.probit_derivatives(ypm, f)
+        h = 1e-5
+        lpp, d1p, Wp, _ = orc.probit_derivatives(ypm, f + h)
+        lpm, d1m, Wm, _ = orc.probit_derivatives(ypm, f - h)
+        assert np.allclose((lpp - lpm) / (2 * h), d1, rtol=1e-7, atol=1e-9)
+        assert np.allclose((d1p - d1m) / (2 * h), -W, rtol=1e-7, atol=1e-9)
+        assert np.allclose(-(Wp - Wm) / (2 * h), d3, rtol=1e-6, atol=1e-8)
