@@ -291,6 +291,19 @@ int agpc_build_K(agpc_ctx* ctx, const agpc_program* program, const double* theta
   a.progs = d_prog; a.theta = d_theta; a.theta_stride = AGPC_MAX_THETA;
   a.Xa = X_dev; a.Xb = X_dev; a.na_fixed = n; a.nb_fixed = n; a.na_pad = n; a.nb_pad = n; a.D = D;
   a.out = K_dev; a.ld = ld; a.out_batch = (long long)n * ld; a.dK = dK_dev;
+  {  // the streaming dK kernel writes each parameter slab once: needs every leaf in exactly one term
+    int uses[AGPC_MAX_LEAVES] = {0};
+    bool unique = true;
+    for (int t = 0; t < program->n_terms && unique; ++t) {
+      if (program->term_len[t] <= 0 || program->term_len[t] > AGPC_MAX_TERM_LEN) return fail(ctx, AGPC_E_ARG, "build_K: bad term");
+      for (int q = 0; q < program->term_len[t]; ++q) {
+        const int l = program->term_leaf[t][q];
+        if (l < 0 || l >= program->n_leaves) return fail(ctx, AGPC_E_ARG, "build_K: bad term leaf");
+        if (++uses[l] > 1) unique = false;
+      }
+    }
+    a.dk_tiled = unique ? 1 : 0;
+  }
   CK(ctx, build_K_launch(L, a, 1, dK_dev != nullptr));
   return AGPC_OK;
 }

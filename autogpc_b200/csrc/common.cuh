@@ -140,6 +140,7 @@ struct BuildArgs {
   double* dK;                    // optional [batch][n_theta][na_pad][ld]
   double* kdiag;                 // optional [batch][na_pad] (only meaningful when Xa == Xb)
   const int* active;
+  int dk_tiled;                  // materialised dK: every leaf sits in exactly one term -> streaming tiled kernel
 };
 struct GradArgs {
   const agpc_program* progs;

@@ -379,8 +379,231 @@ build_K_tiled_kernel(const BuildArgs a, const int symmetric, const int tiles_n) 
   }
 }
 
+// ---- K AND materialised dK/dtheta, streaming ------------------------------------------------------------------------
+// Same 64 x 64 tiling and symmetry as build_K_tiled_kernel.  Each product term is evaluated once per pair (one exp);
+// the slabs of its leaves' parameters are that value times a cheap per-leaf factor and are written straight out --
+// possible because (checked on the host) every leaf belongs to exactly one term, so no slab is accumulated across
+// terms.  (1 + P) x 8 bytes per pair for one exp: this variant is HBM-write-bound.
+enum : int { SLAB_K = 0, SLAB_VAR, SLAB_SE_L, SLAB_PER_T, SLAB_PER_L, SLAB_LIN_C };
+
+struct SlabCtx {
+  const double (*ex)[4];   // exp part of the term, per pair
+  const double* mr;        // LIN factors of the term: rows / columns (for SLAB_LIN_C: without the leaf itself)
+  const double* mc;
+  const double* xi;        // coordinates of the leaf's dimension
+  const double* xj;
+  double s;                // scalar prefactor (product of variances as the slab needs it)
+  double p0, p1, p2;       // leaf constants
+};
+
+template <int KIND>
+__device__ __forceinline__ double slab_value(const SlabCtx& k, const double (&Kacc)[4][4], int r, int c) {
+  if (KIND == SLAB_K) return Kacc[r][c];
+  const double base = k.s * k.mr[r] * k.mc[c] * k.ex[r][c];
+  if (KIND == SLAB_VAR) return base;
+  const double d = k.xi[r] - k.xj[c];
+  if (KIND == SLAB_SE_L) return base * d * d * k.p0;                        // k r^2 / l^3
+  if (KIND == SLAB_LIN_C) return -base * (k.xi[r] + k.xj[c] - 2.0 * k.p0);  // -(rest) var (x + x' - 2c)
+  const double bb = M_PI * d * k.p0;                                        // PER: b = pi r / T
+  double sn, cs;
+  sincos(bb, &sn, &cs);
+  if (KIND == SLAB_PER_T) return base * sn * cs * (bb * k.p0) * k.p1;       // k sin b cos b (b / T) / l^2
+  return base * sn * sn * k.p2;                                             // k sin^2 b / l^3
+}
+
+// writes one 64 x 64 tile of one slab (and its mirror image through shared memory when the tile is off-diagonal)
+template <int KIND>
+__device__ __forceinline__ void emit_slab(const BuildArgs& a, double* __restrict__ dst, const SlabCtx& k,
+                                          const double (&Kacc)[4][4], double* st, int row0, int col0, int na, int nb,
+                                          int tx, int ty, bool mirror) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int lr = ty + 16 * r, i = row0 + lr;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int j = col0 + tx + 16 * c;
+      const double x = (i < na && j < nb) ? slab_value<KIND>(k, Kacc, r, c) : 0.0;
+      if (i < a.na_pad && j < a.ld) dst[(long long)i * a.ld + j] = x;
+      if (mirror) st[lr * KT_LD + tx + 16 * c] = x;
+    }
+  }
+  if (mirror) {
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int jrow = col0 + ty + 16 * r;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int icol = row0 + tx + 16 * c;
+        if (jrow < a.na_pad && icol < a.ld) dst[(long long)jrow * a.ld + icol] = st[(tx + 16 * c) * KT_LD + ty + 16 * r];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(KT_THREADS, 2)
+build_KdK_tiled_kernel(const BuildArgs a, const int symmetric, const int tiles_n) {
+  const int b = blockIdx.z;
+  if (a.active != nullptr && a.active[b] == 0) return;
+  extern __shared__ double smem[];
+  __shared__ ProgShared P;
+  const int D = a.D;
+  double* xr = smem;
+  double* xc = smem + D * KT;
+  double* st = xc + D * KT;
+  int ti, tj;
+  if (symmetric) {
+    const int t = blockIdx.x;
+    ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while (ti * (ti + 1) / 2 > t) --ti;
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    tj = t - ti * (ti + 1) / 2;
+  } else {
+    ti = blockIdx.x / tiles_n;
+    tj = blockIdx.x % tiles_n;
+  }
+  const int row0 = ti * KT, col0 = tj * KT;
+  const int na = a.na_of ? a.na_of[b] : a.na_fixed, nb = a.nb_of ? a.nb_of[b] : a.nb_fixed;
+  load_program(P, a.progs[b], a.theta + (long long)b * a.theta_stride);
+  const double* Xa = a.Xa + (long long)b * a.xa_batch;
+  const double* Xb = a.Xb + (long long)b * a.xb_batch;
+  for (int idx = threadIdx.x; idx < KT * D; idx += KT_THREADS) {
+    const int r = idx / D, d = idx % D;
+    xr[d * KT + r] = (row0 + r < a.na_pad) ? Xa[(long long)(row0 + r) * D + d] : 0.0;
+    xc[d * KT + r] = (col0 + r < a.nb_pad) ? Xb[(long long)(col0 + r) * D + d] : 0.0;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const bool mirror = symmetric && ti != tj;
+  double* outK = a.out + (long long)b * a.out_batch;
+  double* outdK = a.dK + (long long)b * P.n_theta * a.out_batch;
+
+  double K[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) K[r][c] = 0.0;
+
+  const int n_terms = P.n_terms;
+  for (int t = 0; t < n_terms; ++t) {
+    const int len = P.term_len[t];
+    // ---- term value, factored: scale (variances) * mr[r] mc[c] (LIN leaves) * ex[r][c] (exp of the summed exponents) ----
+    double ex[4][4], mr[4] = {1.0, 1.0, 1.0, 1.0}, mc[4] = {1.0, 1.0, 1.0, 1.0};
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) ex[r][c] = 0.0;
+    bool has_exp = false;
+    double scale = 1.0;
+    for (int p = 0; p < len; ++p) {
+      const LeafConst& lc = P.leaf[P.term_leaf[t][p]];
+      scale *= lc.var;
+      if (lc.type == AGPC_LEAF_CONST) continue;
+      double xi[4], xj[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) xi[r] = xr[lc.dim * KT + ty + 16 * r];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) xj[c] = xc[lc.dim * KT + tx + 16 * c];
+      if (lc.type == AGPC_LEAF_SE) {
+        has_exp = true;
+        const double ha = 0.5 * lc.a;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const double d = xi[r] - xj[c];
+            ex[r][c] -= ha * d * d;
+          }
+      } else if (lc.type == AGPC_LEAF_PER) {
+        has_exp = true;
+        const double w = M_PI * lc.a, hb = 0.5 * lc.b;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const double sn = sin(w * (xi[r] - xj[c]));
+            ex[r][c] -= hb * sn * sn;
+          }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) mr[r] *= xi[r] - lc.a;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mc[c] *= xj[c] - lc.a;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        ex[r][c] = has_exp ? exp(ex[r][c]) : 1.0;
+        K[r][c] += scale * mr[r] * mc[c] * ex[r][c];
+      }
+
+    // ---- the slabs of this term's leaves ----
+    for (int p = 0; p < len; ++p) {
+      const int l = P.term_leaf[t][p];
+      const LeafConst& lc = P.leaf[l];
+      double* slab = outdK + (long long)P.leaf_off[l] * a.out_batch;
+      double sx = 1.0;  // product of the OTHER leaves' variances: d/dvar without dividing by var
+      for (int q = 0; q < len; ++q)
+        if (q != p) sx *= P.leaf[P.term_leaf[t][q]].var;
+      double xi[4] = {0.0, 0.0, 0.0, 0.0}, xj[4] = {0.0, 0.0, 0.0, 0.0};
+      if (lc.type != AGPC_LEAF_CONST) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) xi[r] = xr[lc.dim * KT + ty + 16 * r];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) xj[c] = xc[lc.dim * KT + tx + 16 * c];
+      }
+      SlabCtx k{ex, mr, mc, xi, xj, sx, 0.0, 0.0, 0.0};
+      emit_slab<SLAB_VAR>(a, slab, k, K, st, row0, col0, na, nb, tx, ty, mirror);
+      k.s = scale;
+      if (lc.type == AGPC_LEAF_SE) {
+        k.p0 = lc.b;
+        emit_slab<SLAB_SE_L>(a, slab + a.out_batch, k, K, st, row0, col0, na, nb, tx, ty, mirror);
+      } else if (lc.type == AGPC_LEAF_PER) {
+        k.p0 = lc.a; k.p1 = lc.b; k.p2 = lc.d;
+        emit_slab<SLAB_PER_T>(a, slab + a.out_batch, k, K, st, row0, col0, na, nb, tx, ty, mirror);
+        emit_slab<SLAB_PER_L>(a, slab + 2 * a.out_batch, k, K, st, row0, col0, na, nb, tx, ty, mirror);
+      } else if (lc.type == AGPC_LEAF_LIN) {
+        // the term without this leaf's own factor (x - c)(x' - c): rebuild the LIN products from the other leaves
+        double mr2[4] = {1.0, 1.0, 1.0, 1.0}, mc2[4] = {1.0, 1.0, 1.0, 1.0};
+        for (int q = 0; q < len; ++q) {
+          const LeafConst& lq = P.leaf[P.term_leaf[t][q]];
+          if (q == p || lq.type != AGPC_LEAF_LIN) continue;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) mr2[r] *= xr[lq.dim * KT + ty + 16 * r] - lq.a;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) mc2[c] *= xc[lq.dim * KT + tx + 16 * c] - lq.a;
+        }
+        SlabCtx k2{ex, mr2, mc2, xi, xj, scale, lc.a, 0.0, 0.0};
+        emit_slab<SLAB_LIN_C>(a, slab + a.out_batch, k2, K, st, row0, col0, na, nb, tx, ty, mirror);
+      }
+    }
+  }
+  SlabCtx kk{nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, 0.0, 0.0, 0.0};
+  emit_slab<SLAB_K>(a, outK, kk, K, st, row0, col0, na, nb, tx, ty, mirror);
+}
+
 cudaError_t build_K_launch(const Launch& L, const BuildArgs& a, int batch, bool grad) {
   ProfScope prof_scope(L, CLS_KBUILD);
+  if (grad && a.dk_tiled) {
+    static bool configured = false;
+    const size_t smem = sizeof(double) * (2 * (size_t)a.D * KT + KT * KT_LD);
+    if (!configured || smem > 48 * 1024) {
+      AGPC_CUDA_TRY(cudaFuncSetAttribute(build_KdK_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(smem > 100 * 1024 ? smem : 100 * 1024)));
+      configured = true;
+    }
+    const bool symmetric = a.Xa == a.Xb && a.xa_batch == a.xb_batch && a.na_of == a.nb_of && a.na_fixed == a.nb_fixed &&
+                           a.na_pad == a.nb_pad && a.ld == a.na_pad;
+    const int tiles_m = (a.na_pad + KT - 1) / KT;
+    const int tiles_n = ((symmetric ? a.na_pad : (int)a.ld) + KT - 1) / KT;
+    dim3 grid(symmetric ? (unsigned)(tiles_m * (tiles_m + 1) / 2) : (unsigned)(tiles_m * tiles_n), 1, batch);
+    build_KdK_tiled_kernel<<<grid, KT_THREADS, smem, L.stream>>>(a, symmetric ? 1 : 0, tiles_n);
+    L.bump();
+    return cudaGetLastError();
+  }
   if (grad) {
     dim3 grid((unsigned)((a.ld + KB_COLS - 1) / KB_COLS), (unsigned)((a.na_pad + KB_ROWS - 1) / KB_ROWS), batch);
     const size_t smem = sizeof(double) * a.D * (KB_ROWS + KB_COLS);
