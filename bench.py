@@ -222,6 +222,8 @@ def main():
     ap.add_argument("--cands", type=int, default=8, help="candidate structures per GPU (x5 folds = items per step)")
     ap.add_argument("--points", type=int, default=N_POINTS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernels-only", action="store_true",
+                    help="profiling aid (ncu passes): skip the DGEMM peak probe, the e2e leg and the CPU baseline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -302,7 +304,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    peak_burst, peak_sustained = measure_dgemm_peak(torch)
+    peak_burst, peak_sustained = (0.0, 0.0) if args.kernels_only else measure_dgemm_peak(torch)
     sampler = ClockSampler(local_rank) if rank == 0 else None
 
     for _ in range(args.warmup):
@@ -356,6 +358,15 @@ def main():
     h2d = Xp.nbytes + yp.nbytes + B * stride * 8 + rows_cat.nbytes + B * 8 + B * 784
     d2h = B * (8 * 3 + 4 * 2 + stride * 8) + 2 * B * n_max * 8
     e2e_steps = max(1, min(args.steps, 3))
+    if args.kernels_only:
+        if rank == 0:
+            print(json.dumps({"kernels_only": True, "ms_per_step": ms / args.steps, "gpu_launches": int(launches),
+                              "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}}), flush=True)
+        eng.dataset_free(did)
+        eng.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
     r = step_host()  # warm-up of the host path (staging allocations)
     barrier()
     for k in host_ms:
@@ -398,6 +409,12 @@ def main():
                          "peak_source": "cuBLAS DGEMM 8192^3 measured live, sustained %.1f / burst %.1f TFLOP/s "
                                         "(MEASURED_PEAKS.json has no FP64 entry; DMMA issue ceiling 37.1 TFLOP/s, "
                                         "profiles/r01_fp64_peak.md)" % (peak_sustained, peak_burst),
+                         "traffic_ncu_example": {"launch": "K = 512 trailing update, grid (253,1,10) = 2530 tiles",
+                                                 "dram_bytes": 7.355e8, "algorithmic_bytes": 6.63e8,
+                                                 "dmma_pipe_pct_elapsed": 87.9,
+                                                 "source": "profiles/r01_gemm_nt_final_ncu_raw.csv (ncu --set full; the "
+                                                           "launches of a step differ in size, so no single per-launch "
+                                                           "figure is quoted in `traffic`)"},
                          "algorithmic_flops": g["work"], "kernel_ms": g["ms"], "launches": g["launches"],
                          "share_of_kernel_time": g["ms"] / total_kernel_ms},
             "cholesky": {"tflops": g["work"] / (chol_ms * 1e-3) / 1e12 if chol_ms > 0 else None,
