@@ -42,6 +42,26 @@ def test_score_matches_oracle(engine, name, N):
     assert np.allclose(g["nu"][0], o["v"], rtol=1e-7, atol=1e-10)
 
 
+def test_score_matches_oracle_beyond_the_lookahead_threshold(engine):
+    """n = 1500 / 1300 (12 and 11 panels): two-level blocking, the look-ahead streams and -- with two items -- the thin
+    128 x 32 GEMM tiles are all on the path; same bar as the small cases."""
+    N = 1500
+    X, y = synth(N, 4, 17)
+    prog = orc.KernelProgram.from_tree(TREES["se0xse1+per3+se2"])
+    th = random_theta(prog, np.random.default_rng(3))
+    rows = [np.arange(N, dtype=np.int32), np.arange(100, 1400, dtype=np.int32)]
+    did = engine.dataset(X, y)
+    g = engine.score_batch(did, [to_engine_program(prog)] * 2, [th, th * 0.9], rows, damping=0.0)
+    engine.dataset_free(did)
+    for b, (theta, r) in enumerate(((th, rows[0]), (th * 0.9, rows[1]))):
+        o = orc.score(prog, theta, X[r], y[r], damping=0.0)
+        assert g["status"][b] == o["status"] == 0 and g["sweeps"][b] == o["sweeps"]
+        assert abs(g["nlml"][b] - o["nlml"]) <= 1e-9 * abs(o["nlml"])
+        scale = np.maximum(np.abs(o["grad"]), 1e-3 * np.abs(o["grad"]).max())
+        assert np.all(np.abs(g["grad"][b, :prog.n_theta] - o["grad"]) <= 1e-7 * scale)
+        assert np.allclose(g["tau"][b], o["tau"], rtol=1e-7, atol=1e-12)
+
+
 def test_score_vs_sequential_ep(engine):
     """Against the GPy-literal sequential EP (random site order, rank-1 updates): the north_star tolerance.
 
