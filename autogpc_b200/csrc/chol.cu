@@ -3,9 +3,11 @@
 // Stands in for GPy util/linalg.py jitchol (dpotrf), dtrtrs / dtrtri and pdinv's dpotri + symmetrify, as reached
 // from EP.expectation_propagation and EP.inference for gpckernel.py:245-246.
 //
-//   potrf  : right-looking, 128-wide panels.  Per panel k: potf2_inv (one CTA per matrix) factors the diagonal
-//            block and inverts it; the panel solve P <- P W_k^T and the trailing update C -= P P^T both run on the
-//            TMA + DMMA tile kernel (gemm_nt.cu).  W_k = L_kk^-1 doubles as level 0 of trtri.
+//   potrf  : 128-wide panels in outer blocks of 4 (two-level blocking): inside a block left-looking (in-block update
+//            -> potf2_inv, one CTA per matrix, factors the diagonal block AND inverts it -> panel solve through the
+//            inverse, P <- P W_k^T), then one K = 512 trailing update per block; all products on the TMA + DMMA tile
+//            kernel (gemm_nt.cu).  Look-ahead: panels + the next block's columns on a high-priority stream, the rest
+//            of the trailing update on the caller's stream.  W_k = L_kk^-1 doubles as level 0 of trtri.
 //   trtri  : level-synchronous recursive doubling, M21 = -M22 L21 M11, two batched triangular-aware GEMMs per level;
 //            both M = L^-1 and U = M^T are kept so every product is in K-contiguous ("NT") form.
 //   lauum  : B^-1 = U U^T, lower tiles only, K range clipped at the tile row.

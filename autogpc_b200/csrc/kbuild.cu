@@ -9,9 +9,14 @@
 //   CONST k = v                                      dk/dv = 1
 // A product term is evaluated as (prod of scale factors) * exp(sum of exponents): one exp per term, not per leaf.
 //
-// Layout: one CTA = 32 rows x 128 columns; a warp writes 32 consecutive doubles (256 B) per store, the point
-// coordinates of the tile live in shared memory (dimension-major, so column reads are conflict-free and row reads
-// broadcast).  HBM-write-bound for light programs, FP64-ALU-bound once a term carries sin/cos.
+// Kernels here:
+//   build_K_tiled_kernel     K only (the scoring path): 64 x 64 tiles, 2 x 4 pairs per thread and pass, symmetric
+//                            (lower tiles + mirrored store through shared memory) when both point sets coincide
+//   build_KdK_tiled_kernel   K + materialised dK/dtheta, streaming: slabs written as each term is evaluated
+//   build_K_kernel<true>     general materialised dK (leaves shared between terms): 32 x 128 tiles, per-pair interpreter
+//   grad_contract_kernel     fused <W, dK/dtheta> contraction (never materialises dK): what score_batch uses
+// Point coordinates of a tile live in shared memory, dimension-major (column reads conflict-free, row reads broadcast).
+// HBM-write-bound for one-exp programs, FP64-ALU / issue-bound once a term carries sin/cos.
 #include "common.cuh"
 
 namespace agpc {

@@ -17,7 +17,8 @@ LEAF_NPARAM = {LEAF_SE: 2, LEAF_PER: 3, LEAF_LIN: 2, LEAF_CONST: 1}
 ST_OK, ST_JITTER, ST_NOT_PD, ST_EP_NOT_CONVERGED, ST_NONFINITE = 0, 1, 2, 3, 4
 INFER_EP, INFER_LAPLACE = 0, 1
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libautogpc_b200.so")
+# AGPC_LIB overrides the library path (used by tools/ to A/B kernel variants); the default is the in-tree build
+_LIB_PATH = os.environ.get("AGPC_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libautogpc_b200.so")
 
 
 class EngineError(RuntimeError):
