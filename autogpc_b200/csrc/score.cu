@@ -418,6 +418,16 @@ int agpc_score_batch(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, const a
   if (!ctx) return AGPC_E_ARG;
   if (n_items <= 0 || !theta || !rows || !row_off || !nlml || !status || theta_stride <= 0)
     return fail(ctx, AGPC_E_ARG, "score_batch: null argument");
+  if (dataset_id < 0 || dataset_id >= (int)ctx->datasets.size() || !ctx->datasets[dataset_id].X)
+    return fail(ctx, AGPC_E_ARG, "score_batch: bad dataset id");
+  {  // the row lists index the device-resident dataset: reject anything outside it before a kernel dereferences it
+    const int N = ctx->datasets[dataset_id].N;
+    if (row_off[0] != 0) return fail(ctx, AGPC_E_ARG, "score_batch: row_off[0] must be 0");
+    for (int b = 0; b < n_items; ++b)
+      if (row_off[b + 1] <= row_off[b]) return fail(ctx, AGPC_E_ARG, "score_batch: empty or unordered row list");
+    for (int64_t i = 0; i < row_off[n_items]; ++i)
+      if (rows[i] < 0 || rows[i] >= N) return fail(ctx, AGPC_E_ARG, "score_batch: row index outside the dataset");
+  }
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const size_t n_rows = (size_t)row_off[n_items];
@@ -490,6 +500,11 @@ static int predict_impl(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, cons
     return fail(ctx, AGPC_E_ARG, "predict: null argument");
   if (Xstar_host && n_items != 1) return fail(ctx, AGPC_E_ARG, "predict_points: one item only");
   const Dataset& ds = ctx->datasets[dataset_id];
+  for (int64_t i = 0; i < row_off[n_items]; ++i)
+    if (rows[i] < 0 || rows[i] >= ds.N) return fail(ctx, AGPC_E_ARG, "predict: training row index outside the dataset");
+  if (test_rows)
+    for (int64_t i = 0; i < test_off[n_items]; ++i)
+      if (test_rows[i] < 0 || test_rows[i] >= ds.N) return fail(ctx, AGPC_E_ARG, "predict: test row index outside the dataset");
   CK(cudaSetDevice(ctx->device));
   Launch L{ctx->stream, &ctx->launches, &ctx->prof, ctx->side, ctx->ev_panel, ctx->ev_rest};
   int n_max = 0, m_max = 0;

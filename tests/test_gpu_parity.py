@@ -407,3 +407,46 @@ def test_search_selects_identical_structures_as_oracle(engine):
                         (criterion, names[a], names[b], orc_scores[a], orc_scores[b])
     finally:
         eng_mod.set_default_engine(None)
+
+
+# ---- edge cases: tiny / degenerate inputs, limits, API misuse -------------------------------------------------------
+def test_edge_cases_tiny_n_single_dimension_and_one_class(engine):
+    """n = 3 (far below one 128-tile), D = 1, and a fold whose labels are all one class."""
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-2, 2, (40, 1))
+    y = (X[:, 0] > 0).astype(float)
+    prog = orc.KernelProgram.from_tree(("+", ("SE", 0), ("CONST",)))
+    ep = to_engine_program(prog)
+    th = np.array([1.2, 0.7, 0.5])
+    rows = [np.array([0, 1, 2], dtype=np.int32), np.arange(40, dtype=np.int32),
+            np.nonzero(y == 1)[0].astype(np.int32)]
+    did = engine.dataset(X, y)
+    g = engine.score_batch(did, [ep] * 3, [th] * 3, rows)
+    engine.dataset_free(did)
+    for b, r in enumerate(rows):
+        o = orc.score(prog, th, X[r], y[r])
+        assert g["status"][b] == o["status"] == 0 and g["sweeps"][b] == o["sweeps"]
+        assert abs(g["nlml"][b] - o["nlml"]) <= 1e-9 * max(1.0, abs(o["nlml"]))
+        assert np.allclose(g["grad"][b, :3], o["grad"], rtol=1e-6, atol=1e-9)
+
+
+def test_api_misuse_is_an_error_code_not_a_crash(engine):
+    from autogpc_b200.engine import EngineError, Program, LEAF_SE
+    X, y = synth(50, 2, 0)
+    prog = to_engine_program(orc.KernelProgram.from_tree(TREES["se0xse1"]))
+    th = np.ones(4)
+    did = engine.dataset(X, y)
+    with pytest.raises(EngineError):            # row index outside the dataset
+        engine.score_batch(did, [prog], [th], [np.array([0, 1, 50], dtype=np.int32)])
+    with pytest.raises(EngineError):            # unknown dataset
+        engine.score_batch(did + 1000, [prog], [th], [np.arange(10, dtype=np.int32)])
+    with pytest.raises(EngineError):            # theta of the wrong length
+        engine.score_batch(did, [prog], [np.ones(3)], [np.arange(10, dtype=np.int32)])
+    with pytest.raises(EngineError):            # leaf on a dimension the data does not have
+        bad = Program.build([LEAF_SE], [5], [0], [[0]], 2)
+        engine.score_batch(did, [bad], [np.ones(2)], [np.arange(10, dtype=np.int32)])
+    with pytest.raises(EngineError):            # more leaves than AGPC_MAX_LEAVES
+        Program.build([LEAF_SE] * 17, [0] * 17, list(range(0, 34, 2)), [[i] for i in range(16)], 34)
+    ok = engine.score_batch(did, [prog], [th], [np.arange(50, dtype=np.int32)])   # the context is still usable
+    engine.dataset_free(did)
+    assert ok["status"][0] == 0 and np.isfinite(ok["nlml"][0])
