@@ -255,10 +255,13 @@ constexpr int POTRF_OUTER = 4;
 constexpr int THIN_CTA_LIMIT = 160;
 
 // panels k0 .. k0 + kb of one outer block: in-block left-looking update, diagonal block, panel solve
-static cudaError_t potrf_panels(const Launch& L, const MatSet& ms, const int* active, int* info, int k0, int kb) {
+// first_staged: the head update of the previous outer block already duplicated panel k0 (rows > k0) into M
+static cudaError_t potrf_panels(const Launch& L, const MatSet& ms, const int* active, int* info, int k0, int kb,
+                                bool first_staged) {
   const int nblk = ms.np / TILE;
   for (int t = 0; t < kb; ++t) {
     const int k = k0 + t;
+    bool staged = (t == 0) && first_staged;  // is the panel below the diagonal block already duplicated in M?
     if (t > 0) {
       // A[k:, k] -= A[k:, k0:k] A[k, k0:k]^T
       GemmArgs u{};
@@ -270,6 +273,9 @@ static cudaError_t potrf_panels(const Launch& L, const MatSet& ms, const int* ac
       u.k_rule = KRULE_FULL; u.lower_only = 0; u.alpha = -1.0; u.beta = 1.0; u.active = active;
       if ((nblk - k) * ms.batch <= THIN_CTA_LIMIT) {
         u.n_tiles = TILE / 32;
+        // the thin solve below cannot run in place: this update stages its result (rows > k) in M as it goes
+        u.C2 = ms.M; u.c2_cols = u.n_tiles; u.c2_row_min = 1;
+        staged = true;
         AGPC_CUDA_TRY(gemm_nt_thin_launch(L, ms.mapA, ms.mapA32, u, (nblk - k) * u.n_tiles, 1, ms.batch));
       } else {
         AGPC_CUDA_TRY(gemm_nt_launch(L, ms.mapA, ms.mapA, u, nblk - k, 1, ms.batch));
@@ -289,8 +295,9 @@ static cudaError_t potrf_panels(const Launch& L, const MatSet& ms, const int* ac
     if (below * ms.batch <= THIN_CTA_LIMIT) {
       // four CTAs share one 128-row operand tile here, so the solve cannot run in place: stage the panel in the
       // (still unused) strictly-lower part of M and read it from there
-      AGPC_CUDA_TRY(copy_panel_launch(L, ms.A, ms.M, ms.np, ms.stride, (k + 1) * TILE, k * TILE, below * TILE,
-                                      ms.batch, active));
+      if (!staged)
+        AGPC_CUDA_TRY(copy_panel_launch(L, ms.A, ms.M, ms.np, ms.stride, (k + 1) * TILE, k * TILE, below * TILE,
+                                        ms.batch, active));
       p.n_tiles = TILE / 32;
       AGPC_CUDA_TRY(gemm_nt_thin_launch(L, ms.mapM, ms.mapM32, p, below * p.n_tiles, 1, ms.batch));
     } else {
@@ -302,7 +309,8 @@ static cudaError_t potrf_panels(const Launch& L, const MatSet& ms, const int* ac
 
 // trailing update with outer block [k0, k0 + kb): C[r0:, c0 : c0 + ncols] -= A[., k0:k0+kb] A[., k0:k0+kb]^T for the
 // tiles on or below the diagonal.  (r0 == c0; ncols < 0: everything to the right, as a lower-triangular tile list)
-static cudaError_t potrf_trailing(const Launch& L, const MatSet& ms, const int* active, int k0, int kb, int r0, int ncols) {
+static cudaError_t potrf_trailing(const Launch& L, const MatSet& ms, const int* active, int k0, int kb, int r0, int ncols,
+                                  bool stage_first_col = false) {
   const int nblk = ms.np / TILE;
   const int rows = nblk - r0;
   if (rows <= 0 || ncols == 0) return cudaSuccess;
@@ -319,6 +327,9 @@ static cudaError_t potrf_trailing(const Launch& L, const MatSet& ms, const int* 
   }
   const int nc = ncols < rows ? ncols : rows;
   s.m_tiles = rows; s.n_tiles = nc; s.lower_only = 0; s.skip_upper = 1;
+  if (stage_first_col) {  // next panel (first block column, rows below its diagonal block) also goes to the M scratch
+    s.C2 = ms.M; s.c2_cols = 1; s.c2_row_min = 1;
+  }
   return gemm_nt_launch(L, ms.mapA, ms.mapA, s, rows * nc, 1, ms.batch);
 }
 
@@ -336,7 +347,7 @@ cudaError_t potrf_blocked(const Launch& L, const MatSet& ms, const int* active, 
   if (!lookahead) {
     for (int k0 = 0; k0 < nblk; k0 += POTRF_OUTER) {
       const int kb = nblk - k0 < POTRF_OUTER ? nblk - k0 : POTRF_OUTER;
-      AGPC_CUDA_TRY(potrf_panels(L, ms, active, info, k0, kb));
+      AGPC_CUDA_TRY(potrf_panels(L, ms, active, info, k0, kb, false));
       if (k0 + kb < nblk) AGPC_CUDA_TRY(potrf_trailing(L, ms, active, k0, kb, k0 + kb, -1));
     }
     return cudaSuccess;
@@ -348,12 +359,14 @@ cudaError_t potrf_blocked(const Launch& L, const MatSet& ms, const int* active, 
   bool rest_pending = false;
   for (int k0 = 0; k0 < nblk; k0 += POTRF_OUTER) {
     const int kb = nblk - k0 < POTRF_OUTER ? nblk - k0 : POTRF_OUTER;
-    AGPC_CUDA_TRY(potrf_panels(H, ms, active, info, k0, kb));
+    // the head update of the previous block staged panel k0 when that panel will be solved with thin tiles
+    const bool first_staged = k0 > 0 && (nblk - k0 - 1) * ms.batch <= THIN_CTA_LIMIT;
+    AGPC_CUDA_TRY(potrf_panels(H, ms, active, info, k0, kb, first_staged));
     const int r0 = k0 + kb;
     if (r0 >= nblk) break;
     AGPC_CUDA_TRY(cudaEventRecord(L.ev_panel, H.stream));
     if (rest_pending) AGPC_CUDA_TRY(cudaStreamWaitEvent(H.stream, L.ev_rest, 0));  // rest(i-1) wrote the head's columns
-    AGPC_CUDA_TRY(potrf_trailing(H, ms, active, k0, kb, r0, POTRF_OUTER));
+    AGPC_CUDA_TRY(potrf_trailing(H, ms, active, k0, kb, r0, POTRF_OUTER, (nblk - r0 - 1) * ms.batch <= THIN_CTA_LIMIT));
     rest_pending = false;
     if (r0 + POTRF_OUTER < nblk) {
       AGPC_CUDA_TRY(cudaStreamWaitEvent(L.stream, L.ev_panel, 0));

@@ -24,6 +24,9 @@ enum : int { KRULE_FULL = 0, KRULE_BEGIN_AT_ROW = 1, KRULE_END_AT_ROW = 2, KRULE
 struct GemmArgs {
   double* C;                 // output (row-major), element (r, c) of batch b at C + b*c_batch + r*ldc + c
   double* Ct;                // optional second, transposed output: Ct + b*c_batch + c*ldc + r   (nullptr = none)
+  double* C2;                // optional duplicate of C (same layout and offsets) for the tiles with tj < c2_cols and
+  int c2_cols;               //   ti >= c2_row_min: stages the next panel for the thin solve without a copy kernel
+  int c2_row_min;
   long long ldc, c_batch;
   int a_row0, a_col0, b_row0, b_col0, c_row0, c_col0, ct_row0, ct_col0;  // element offsets (group-relative)
   int m_tiles, n_tiles, k_tiles;  // extents when EXT_FIXED: tiles of 128 x 128 x 16

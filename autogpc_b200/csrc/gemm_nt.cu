@@ -210,6 +210,14 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       acc[i][j][1] = v.y;
     }
   }
+  if (args.C2 != nullptr && tj < args.c2_cols && ti >= args.c2_row_min) {
+    double* C2b = args.C2 + (long long)b * args.c_batch;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+        *reinterpret_cast<double2*>(C2b + (row0 + i * 8) * args.ldc + col0 + j * 8) = make_double2(acc[i][j][0], acc[i][j][1]);
+  }
   if (args.Ct != nullptr) {
     const long long trow0 = (long long)args.ct_row0 + shift + tj * BN + wn * (8 * NJ) + tig * 2;
     const long long tcol0 = (long long)args.ct_col0 + shift + ti * TILE + wm * 32 + gid;
