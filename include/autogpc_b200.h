@@ -10,7 +10,9 @@
  * batch -- this is what lets GPCKernel.train's per-fold skip (gpckernel.py:196-199) and paramz's <=10 tolerated
  * linear-algebra failures be reproduced by the host.  One context per host thread; contexts are not shared.
  * All matrices are FP64 row-major.  "dev" pointers are CUDA device pointers on the context's device, "host"
- * pointers are ordinary host memory.  `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ * pointers are ordinary host memory.  `stream` is a cudaStream_t passed as void*; NULL means the CONTEXT'S OWN stream,
+ * which is non-blocking: it is not ordered with the legacy default stream, so a caller that prepared device buffers on
+ * another stream must either pass that stream or synchronise before the call (and after it, before reading results).
  */
 #ifndef AUTOGPC_B200_H
 #define AUTOGPC_B200_H

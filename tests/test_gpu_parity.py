@@ -282,6 +282,7 @@ def test_build_K_dK_and_fused_gradient(engine, name, n):
     ld = n + (n & 1)
     K = torch.zeros((n, ld), dtype=torch.float64, device="cuda")
     dK = torch.zeros((prog.n_theta, n, ld), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()   # the engine's stream is not ordered with torch's: buffers must be ready before the call
     engine.build_K(ep, th, Xd.data_ptr(), n, 4, K.data_ptr(), ld, dK.data_ptr())
     torch.cuda.synchronize()
     Ko = orc.kern_K(prog, th, X)
@@ -290,12 +291,14 @@ def test_build_K_dK_and_fused_gradient(engine, name, n):
     for q in range(prog.n_theta):
         assert np.abs(dK[q].cpu().numpy()[:, :n] - dKo[q]).max() <= 1e-12 * max(1.0, np.abs(dKo[q]).max())
     K2 = torch.zeros_like(K)
+    torch.cuda.synchronize()
     engine.build_K(ep, th, Xd.data_ptr(), n, 4, K2.data_ptr(), ld)      # K-only path (symmetric tiles)
     torch.cuda.synchronize()
     assert np.abs(K2.cpu().numpy()[:, :n] - Ko).max() <= 1e-13 * max(1.0, np.abs(Ko).max())
     assert torch.equal(K2[:, :n], K2[:, :n].T.contiguous())             # exactly symmetric
     G = np.random.default_rng(5).standard_normal((n, n))
     Gd = torch.from_numpy(G).cuda()
+    torch.cuda.synchronize()
     g = engine.kernel_grad(ep, th, Xd.data_ptr(), n, 4, Gd.data_ptr(), n)
     go = orc.kern_grad(prog, th, X, G)
     assert np.all(np.abs(g - go) <= 1e-10 * np.maximum(np.abs(go), 1e-3 * np.abs(go).max() + 1e-30))
@@ -311,6 +314,7 @@ def test_potrf_trtri_against_lapack(engine, n, batch):
     A = torch.from_numpy(S).cuda().contiguous()
     Mi, Ui = torch.zeros_like(A), torch.zeros_like(A)
     info = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()   # see test_build_K_dK_and_fused_gradient
     engine.potrf(A.data_ptr(), n, batch, Mi.data_ptr(), Ui.data_ptr(), info.data_ptr())
     torch.cuda.synchronize()
     assert info.cpu().tolist() == [0] * batch
@@ -322,6 +326,30 @@ def test_potrf_trtri_against_lapack(engine, n, batch):
         assert np.abs(np.triu(Ui[b].cpu().numpy()) - Wr.T).max() <= 1e-11
 
 
+@pytest.mark.parametrize("n,batch", [(1024, 1), (1152, 1), (1152, 5), (2304, 2), (2304, 9), (1280, 17)])
+def test_potrf_paths_around_the_scheduling_thresholds(engine, n, batch):
+    """8 vs 9 panels (look-ahead off / on), thin 128 x 32 tiles vs full tiles (CTA-count threshold), partial outer
+    blocks; every path must give the same factor.  Checked through L L^T = B and M L = I on random SPD matrices."""
+    torch = _torch()
+    torch.manual_seed(n + batch)
+    G = torch.randn(batch, n, n, dtype=torch.float64, device="cuda")
+    S = G @ G.transpose(1, 2) / n + torch.eye(n, dtype=torch.float64, device="cuda")
+    A = S.clone()
+    Mi, Ui = torch.zeros_like(A), torch.zeros_like(A)
+    info = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    for _ in range(2):                                   # twice: scratch regions and events are reused across calls
+        A.copy_(S)
+        torch.cuda.synchronize()
+        engine.potrf(A.data_ptr(), n, batch, Mi.data_ptr(), Ui.data_ptr(), info.data_ptr())
+        torch.cuda.synchronize()
+    assert info.cpu().tolist() == [0] * batch
+    L = torch.tril(A)
+    eye = torch.eye(n, dtype=torch.float64, device="cuda")
+    assert (L @ L.transpose(1, 2) - S).abs().max().item() <= 1e-12 * n ** 0.5 * S.abs().max().item()
+    assert (torch.tril(Mi) @ L - eye).abs().max().item() <= 1e-11
+    assert torch.equal(torch.triu(Ui), torch.tril(Mi).transpose(1, 2).contiguous())
+
+
 def test_large_n_roundtrip_properties(engine):
     """Size-independent properties at a size the oracle would take minutes for: L L^T = B, M L = I (n = 4096)."""
     torch = _torch()
@@ -331,6 +359,7 @@ def test_large_n_roundtrip_properties(engine):
     S = G @ G.T / n + torch.eye(n, dtype=torch.float64, device="cuda")
     A = S.clone()
     Mi, Ui = torch.zeros_like(A), torch.zeros_like(A)
+    torch.cuda.synchronize()
     engine.potrf(A.data_ptr(), n, 1, Mi.data_ptr(), Ui.data_ptr(), 0)
     torch.cuda.synchronize()
     L = torch.tril(A)
