@@ -11,6 +11,7 @@ Mi = torch.empty_like(S); Ui = torch.empty_like(S)
 P = lambda t: ctypes.c_void_p(t.data_ptr())
 for _ in range(2):
     A = S.clone()
+    torch.cuda.synchronize()   # the engine's stream is not ordered with torch's
     assert lib.agpc_potrf(ctx, P(A), n, batch, P(Mi), P(Ui), None, None) == 0
     torch.cuda.synchronize()
 print("ok")
