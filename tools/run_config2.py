@@ -23,8 +23,11 @@ depth1.sort(key=lambda k: (k.bic(), k.kernel.structure()))
 parent = depth1[0]
 children = [k for k in parent.expand(base_kernels="SE,Lin,Per") if len(k.getActiveDims()) > 1]
 t2 = time.time(); l1 = eng.launches
+eng.profile_enable(True)
 gk.train_kernels(children, mode="full", n_folds=5, max_evals=max_evals)
 t3 = time.time()
+prof = eng.profile_read()
+eng.profile_enable(False)
 children.sort(key=lambda k: (k.bic(), k.kernel.structure()))
 print(json.dumps({"config": "configs[1] greedy expansion D=4 n=%d" % N, "max_evals": max_evals,
                   "depth1": {"candidates": len(depth1), "seconds": t1 - t0, "launches": l1 - l0,
@@ -32,4 +35,7 @@ print(json.dumps({"config": "configs[1] greedy expansion D=4 n=%d" % N, "max_eva
                   "expansion": {"parent": parent.kernel.structure(), "candidates": len(children), "seconds": t3 - t2,
                                 "launches": eng.launches - l1,
                                 "candidates_per_s": len(children) / (t3 - t2),
+                                "kernel_ms": {k: round(v["ms"], 1) for k, v in prof.items()},
+                                "gpu_busy_fraction": sum(v["ms"] for v in prof.values()) / (1e3 * (t3 - t2)),
+                                "gemm_tflops": prof["gemm"]["work"] / (prof["gemm"]["ms"] * 1e-3) / 1e12,
                                 "ranking": [(k.kernel.structure(), round(k.bic(), 3), round(k.error(), 4)) for k in children]}}))
