@@ -234,6 +234,16 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # stdout must carry exactly ONE JSON line: native libraries (NCCL prints its version banner there) get stderr
+    # instead, and the line goes to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     import torch
     import torch.distributed as dist
     from autogpc_b200 import gpy_compat as GPy
@@ -245,7 +255,6 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
@@ -361,8 +370,8 @@ def main():
     e2e_steps = max(1, min(args.steps, 3))
     if args.kernels_only:
         if rank == 0:
-            print(json.dumps({"kernels_only": True, "ms_per_step": ms / args.steps, "gpu_launches": int(launches),
-                              "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}}), flush=True)
+            emit({"kernels_only": True, "ms_per_step": ms / args.steps, "gpu_launches": int(launches),
+                  "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}})
         eng.dataset_free(did)
         eng.close()
         if world > 1:
@@ -436,7 +445,7 @@ def main():
                                               % (B, len(rows[0]), o["sweeps"], cores, dt)}
             gn = float(nlml_d[0].item())
             line["cpu_baseline"]["nlml_rel_diff_vs_gpu"] = abs(gn - o["nlml"]) / abs(o["nlml"])
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.dataset_free(did)
     eng.close()
     if world > 1:
