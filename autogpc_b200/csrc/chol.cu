@@ -17,7 +17,7 @@ namespace agpc {
 
 constexpr int POTF2_THREADS = 256;
 constexpr int POTF2_LD = TILE + 1;
-constexpr int POTF2_SMEM = (TILE * POTF2_LD + 2 * TILE + TILE + 16) * 8;
+constexpr int POTF2_SMEM = (TILE * POTF2_LD + 4 * TILE + TILE + 16) * 8;
 
 // One CTA per batch item factors the 128 x 128 diagonal block AND inverts its factor, entirely in registers.
 //
@@ -29,37 +29,65 @@ constexpr int POTF2_SMEM = (TILE * POTF2_LD + 2 * TILE + TILE + 16) * 8;
 //     v = S[:, j]  (A[j:, j] below the diagonal, W'[j, :j] above it),  u = v with u_j = 1
 //     S[r][q] -= u_r v_q / a_jj     for q > j and (r <= j  or  r >= q)
 //     S[:, j] *= 1 / sqrt(a_jj)     (final: columns <= j are never touched again)
-// Column j is broadcast through a double-buffered shared-memory vector, one __syncthreads per step; the owners of
-// column j + 1 update and publish it (and the pivot's reciprocal square root) before the bulk of step j, so the
-// rsqrt latency of the pivot sits off the critical path.
+// Columns are taken two at a time (see potf2_publish_pair): the pair is broadcast through a double-buffered shared-
+// memory buffer, ONE __syncthreads per pair; the owners of the next pair update and publish it (and the pivot thread
+// the 2 x 2 pivot block's reciprocals) before the bulk of the current pair's update, so the pivot latency sits off
+// the critical path.  53.8 us per block (58 with one column per barrier, 405 for the first shared-memory version);
+// what remains is FP64 issue / dependency stalls of the update itself, not the barrier chain.
 //
 // Masking is branch-free.  Element (r, q) is "lower" (part of A, live from the start) when r >= q and "upper"
 // (W[q][r], created at step r) otherwise; an upper element must not move before step r, which is arranged by
 // multiplying it with u_low (u with the rows r > j zeroed) instead of u.  Whether an element is lower is a
 // compile-time fact except on the 16 x 16 patches on the diagonal (a == b), where it is ty >= tx.
 struct Potf2Smem {
-  double* vbuf;   // [2][128] broadcast column
+  double* vbuf;   // [2 buffers][2 columns][128] broadcast column pair
   double* winv;   // [128]    1 / L_jj
-  double* ibuf;   // [2][4]   1/a_jj (slot 0)
+  double* ibuf;   // [2][4]   {1/a1, c = S[j+1][j]/a1, 1/a2'}
   int* badflag;
 };
 
-// publishes column jn (of 16-group BP), held in col[0..8) by the threads that own it, and its pivot terms; the pivot
-// a_jn,jn can only sit in row group BP, on the thread with ty == jn % 16
+// Columns are eliminated in PAIRS (j even, j + 1): one barrier, one broadcast and one pivot chain per two columns.
+// With v1 = S[:, j], v2 = S[:, j+1] (both as they stand before the pair), a1 = v1[j], c = v1[j+1] / a1 and u1 = v1 with
+// u1[j] = 1, column j + 1 after step j is v2' = v2 - u1 c on EVERY row, its pivot a2' = v2'[j+1], and
+//     S[r][q] -= um1(r) v1[q] / a1 + um2(r) v2'[q] / a2'      (q > j + 1)
+// where um1 / um2 are u1 / u2' = v2' with u2'[j+1] = 1 under the liveness rule of their own column.
+//
+// Publishes the raw pair (jn, jn + 1) of 16-group BP.  The three pivot-block entries S[jn][jn], S[jn+1][jn],
+// S[jn+1][jn+1] all sit in s[BP][BP] of three lanes of ONE warp (ty = jn % 16 and ty + 1 share a warp), so the pivot
+// thread collects them with shuffles -- which every thread must therefore execute.
 template <int BP>
-__device__ __forceinline__ void potf2_publish(const Potf2Smem& sm, const double (&col)[8], int jn, int ty) {
-  double* vb = sm.vbuf + (jn & 1) * TILE;
+__device__ __forceinline__ void potf2_publish_pair(const Potf2Smem& sm, const double (&s)[8][8], int jn, int tx, int ty) {
+  const int jj = jn & 15;
+  const double d = s[BP][BP];
+  const double a11 = __shfl_sync(0xffffffffu, d, jj);
+  const double a21 = __shfl_sync(0xffffffffu, d, 16 + jj);
+  const double a22 = __shfl_sync(0xffffffffu, d, 16 + jj + 1);
+  if (tx == jj || tx == jj + 1) {
+    double* vb = sm.vbuf + ((jn >> 1) & 1) * (2 * TILE) + (tx - jj) * TILE;
 #pragma unroll
-  for (int a = 0; a < 8; ++a) vb[ty + 16 * a] = col[a];
-  if (ty == (jn & 15)) {
-    double d = col[BP];
-    if (!(d > 0.0) || !isfinite(d)) {
-      *sm.badflag = 1;
-      d = 1.0;
+    for (int a = 0; a < 8; ++a) vb[ty + 16 * a] = s[a][BP];
+    if (tx == jj && ty == jj) {  // pivot thread of the pair
+      double a1 = a11;
+      if (!(a1 > 0.0) || !isfinite(a1)) {
+        *sm.badflag = 1;
+        a1 = 1.0;
+      }
+      const double r1 = rsqrt(a1);
+      const double inv1 = r1 * r1;
+      const double c = a21 * inv1;
+      double a2 = fma(-a21, c, a22);
+      if (!(a2 > 0.0) || !isfinite(a2)) {
+        *sm.badflag = 1;
+        a2 = 1.0;
+      }
+      const double r2 = rsqrt(a2);
+      double* ib = sm.ibuf + ((jn >> 1) & 1) * 4;
+      ib[0] = inv1;
+      ib[1] = c;
+      ib[2] = r2 * r2;
+      sm.winv[jn] = r1;
+      sm.winv[jn + 1] = r2;
     }
-    const double rinv = rsqrt(d);  // 1 ulp (MUFU.RSQ64H + Newton)
-    sm.ibuf[(jn & 1) * 4] = rinv * rinv;
-    sm.winv[jn] = rinv;
   }
 }
 
@@ -71,78 +99,98 @@ __device__ __forceinline__ double potf2_um(const double (&uf)[8], const double (
   return (A > B) ? uf[A] : (A < B) ? ul[A] : (diag_lower ? uf[A] : ul[A]);
 }
 
-template <int BJ, int B>
-__device__ __forceinline__ void potf2_load_t(double (&t)[8], const double* v, double inv, int tx, int jj) {
-  if constexpr (B < 8) {
-    const double x = v[tx + 16 * B] * inv;
-    t[B] = (B == BJ) ? ((tx > jj) ? x : 0.0) : x;  // finished columns of the current 16-group get a zero update
-    potf2_load_t<BJ, B + 1>(t, v, inv, tx, jj);
-  }
+template <int A, int B>
+__device__ __forceinline__ void potf2_el_update(double (&s)[8][8], const double (&uf1)[8], const double (&ul1)[8],
+                                                const double (&uf2)[8], const double (&ul2)[8], bool diag_lower,
+                                                double t1, double t2) {
+  double x = fma(-potf2_um<A, B>(uf1, ul1, diag_lower), t1, s[A][B]);
+  s[A][B] = fma(-potf2_um<A, B>(uf2, ul2, diag_lower), t2, x);
 }
 
 template <int B>
-__device__ __forceinline__ void potf2_col_update(double (&s)[8][8], const double (&uf)[8], const double (&ul)[8],
-                                                 bool diag_lower, double t) {
-  s[0][B] = fma(-potf2_um<0, B>(uf, ul, diag_lower), t, s[0][B]);
-  s[1][B] = fma(-potf2_um<1, B>(uf, ul, diag_lower), t, s[1][B]);
-  s[2][B] = fma(-potf2_um<2, B>(uf, ul, diag_lower), t, s[2][B]);
-  s[3][B] = fma(-potf2_um<3, B>(uf, ul, diag_lower), t, s[3][B]);
-  s[4][B] = fma(-potf2_um<4, B>(uf, ul, diag_lower), t, s[4][B]);
-  s[5][B] = fma(-potf2_um<5, B>(uf, ul, diag_lower), t, s[5][B]);
-  s[6][B] = fma(-potf2_um<6, B>(uf, ul, diag_lower), t, s[6][B]);
-  s[7][B] = fma(-potf2_um<7, B>(uf, ul, diag_lower), t, s[7][B]);
+__device__ __forceinline__ void potf2_col_update(double (&s)[8][8], const double (&uf1)[8], const double (&ul1)[8],
+                                                 const double (&uf2)[8], const double (&ul2)[8], bool diag_lower,
+                                                 double t1, double t2) {
+  potf2_el_update<0, B>(s, uf1, ul1, uf2, ul2, diag_lower, t1, t2);
+  potf2_el_update<1, B>(s, uf1, ul1, uf2, ul2, diag_lower, t1, t2);
+  potf2_el_update<2, B>(s, uf1, ul1, uf2, ul2, diag_lower, t1, t2);
+  potf2_el_update<3, B>(s, uf1, ul1, uf2, ul2, diag_lower, t1, t2);
+  potf2_el_update<4, B>(s, uf1, ul1, uf2, ul2, diag_lower, t1, t2);
+  potf2_el_update<5, B>(s, uf1, ul1, uf2, ul2, diag_lower, t1, t2);
+  potf2_el_update<6, B>(s, uf1, ul1, uf2, ul2, diag_lower, t1, t2);
+  potf2_el_update<7, B>(s, uf1, ul1, uf2, ul2, diag_lower, t1, t2);
 }
 
 template <int BJ, int B>
-__device__ __forceinline__ void potf2_rest(double (&s)[8][8], const double (&uf)[8], const double (&ul)[8],
-                                           bool diag_lower, const double (&t)[8]) {
+__device__ __forceinline__ void potf2_load_t(double (&t1)[8], double (&t2)[8], const double* v1, const double* v2,
+                                             double inv1, double c, double inv2, int tx, int jj) {
   if constexpr (B < 8) {
-    potf2_col_update<B>(s, uf, ul, diag_lower, t[B]);
-    potf2_rest<BJ, B + 1>(s, uf, ul, diag_lower, t);
+    const double x1 = v1[tx + 16 * B];
+    const double x2 = fma(-x1, c, v2[tx + 16 * B]);  // column j + 1 after step j, at row q (q > j + 1: u1[q] = v1[q])
+    const bool on = (B != BJ) || (tx > jj + 1);      // finished / current columns of this 16-group get a zero update
+    t1[B] = on ? x1 * inv1 : 0.0;
+    t2[B] = on ? x2 * inv2 : 0.0;
+    potf2_load_t<BJ, B + 1>(t1, t2, v1, v2, inv1, c, inv2, tx, jj);
   }
 }
 
-// the 16 columns j = 16 BJ .. 16 BJ + 15.  Column j is NOT scaled here: columns <= j simply stop receiving updates
-// (their t is zero / they are skipped), and the 1 / sqrt(a_jj) scaling of every finished column -- diagonal included,
-// a_jj / sqrt(a_jj) = L_jj -- is applied once at write-out.
+template <int BJ, int B>
+__device__ __forceinline__ void potf2_rest(double (&s)[8][8], const double (&uf1)[8], const double (&ul1)[8],
+                                           const double (&uf2)[8], const double (&ul2)[8], bool diag_lower,
+                                           const double (&t1)[8], const double (&t2)[8]) {
+  if constexpr (B < 8) {
+    potf2_col_update<B>(s, uf1, ul1, uf2, ul2, diag_lower, t1[B], t2[B]);
+    potf2_rest<BJ, B + 1>(s, uf1, ul1, uf2, ul2, diag_lower, t1, t2);
+  }
+}
+
+// the 16 columns j = 16 BJ .. 16 BJ + 15, two at a time.  Finished columns are NOT scaled here: they simply stop
+// receiving updates, and the 1 / sqrt(pivot) scaling of every column -- diagonal included, a / sqrt(a) = L_jj -- is
+// applied once at write-out.
 template <int BJ>
 __device__ __forceinline__ void potf2_group(double (&s)[8][8], const Potf2Smem& sm, bool diag_lower, int tx, int ty) {
 #pragma unroll 1
-  for (int jj = 0; jj < 16; ++jj) {
+  for (int jj = 0; jj < 16; jj += 2) {
     const int j = 16 * BJ + jj;
-    const double* v = sm.vbuf + (j & 1) * TILE;
-    const double inv = sm.ibuf[(j & 1) * 4];
-    double t[8];
-    potf2_load_t<BJ, BJ>(t, v, inv, tx, jj);
-    double uf[8], ul[8];
+    const double* v1 = sm.vbuf + ((j >> 1) & 1) * (2 * TILE);
+    const double* v2 = v1 + TILE;
+    const double* ib = sm.ibuf + ((j >> 1) & 1) * 4;
+    const double inv1 = ib[0], c = ib[1], inv2 = ib[2];
+    double t1[8], t2[8];
+    potf2_load_t<BJ, BJ>(t1, t2, v1, v2, inv1, c, inv2, tx, jj);
+    double uf1[8], ul1[8], uf2[8], ul2[8], v2p[8];
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
-      const double vr = v[ty + 16 * a];
-      // rows of 16-row groups a < BJ are all <= j, rows of groups a > BJ are all > j
+      const double x1 = v1[ty + 16 * a];
+      // rows of 16-row groups a < BJ are all <= j, rows of groups a > BJ are all > j + 1
+      const double u1 = (a == BJ && ty == jj) ? 1.0 : x1;
+      const double x2 = fma(-u1, c, v2[ty + 16 * a]);  // column j + 1 after step j (every row is live for it)
+      const double u2 = (a == BJ && ty == jj + 1) ? 1.0 : x2;
+      v2p[a] = x2;
+      uf1[a] = u1;
+      uf2[a] = u2;
       if (a < BJ) {
-        uf[a] = vr;
-        ul[a] = vr;
+        ul1[a] = u1;
+        ul2[a] = u2;
       } else if (a > BJ) {
-        uf[a] = vr;
-        ul[a] = 0.0;
+        ul1[a] = 0.0;
+        ul2[a] = 0.0;
       } else {
-        uf[a] = (ty == jj) ? 1.0 : vr;
-        ul[a] = (ty <= jj) ? uf[a] : 0.0;
+        ul1[a] = (ty <= jj) ? u1 : 0.0;
+        ul2[a] = (ty <= jj + 1) ? u2 : 0.0;
       }
     }
-    // columns of this 16-group first (lanes tx > jj), so that column j + 1 can be published early
-    potf2_col_update<BJ>(s, uf, ul, diag_lower, t[BJ]);
-    if (jj < 15 && tx == jj + 1) {
-      const double col[8] = {s[0][BJ], s[1][BJ], s[2][BJ], s[3][BJ], s[4][BJ], s[5][BJ], s[6][BJ], s[7][BJ]};
-      potf2_publish<BJ>(sm, col, j + 1, ty);
+    // column j + 1 takes its post-step-j values (its owners published the raw ones)
+    if (tx == jj + 1) {
+#pragma unroll
+      for (int a = 0; a < 8; ++a) s[a][BJ] = v2p[a];
     }
-    potf2_rest<BJ, BJ + 1>(s, uf, ul, diag_lower, t);
+    // columns of this 16-group first (lanes tx > jj + 1), so that the next pair can be published early
+    potf2_col_update<BJ>(s, uf1, ul1, uf2, ul2, diag_lower, t1[BJ], t2[BJ]);
+    if (jj < 14) potf2_publish_pair<BJ>(sm, s, j + 2, tx, ty);
+    potf2_rest<BJ, BJ + 1>(s, uf1, ul1, uf2, ul2, diag_lower, t1, t2);
     if constexpr (BJ < 7) {
-      if (jj == 15 && tx == 0) {
-        const double col[8] = {s[0][BJ + 1], s[1][BJ + 1], s[2][BJ + 1], s[3][BJ + 1],
-                               s[4][BJ + 1], s[5][BJ + 1], s[6][BJ + 1], s[7][BJ + 1]};
-        potf2_publish<BJ + 1>(sm, col, j + 1, ty);
-      }
+      if (jj == 14) potf2_publish_pair<BJ + 1>(sm, s, j + 2, tx, ty);
     }
     __syncthreads();
   }
@@ -157,7 +205,7 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ M, double* __restr
   double* stage = smem;                      // [128][129] output transposition buffer
   Potf2Smem sm;
   sm.vbuf = smem + TILE * POTF2_LD;
-  sm.winv = sm.vbuf + 2 * TILE;
+  sm.winv = sm.vbuf + 4 * TILE;
   sm.ibuf = sm.winv + TILE;
   sm.badflag = reinterpret_cast<int*>(sm.ibuf + 8);
   const long long base = (long long)bi * batch_stride + (long long)diag_block * TILE * ld + (long long)diag_block * TILE;
@@ -175,10 +223,7 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ M, double* __restr
     }
   const bool diag_lower = ty >= tx;
   __syncthreads();
-  if (tx == 0) {
-    const double col[8] = {s[0][0], s[1][0], s[2][0], s[3][0], s[4][0], s[5][0], s[6][0], s[7][0]};
-    potf2_publish<0>(sm, col, 0, ty);
-  }
+  potf2_publish_pair<0>(sm, s, 0, tx, ty);
   __syncthreads();
 
   potf2_group<0>(s, sm, diag_lower, tx, ty);
