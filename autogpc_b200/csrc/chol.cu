@@ -429,7 +429,9 @@ cudaError_t potrf_blocked(const Launch& L, const MatSet& ms, const int* active, 
 cudaError_t trtri_blocked(const Launch& L, const MatSet& ms, const int* active) {
   const int nblk = ms.np / TILE;
   const double wn = L.work_n > 0.0 ? L.work_n : (double)ms.np;
-  L.add_work(CLS_GEMM, (double)L.work_items * wn * wn * wn / 3.0);  // dtrtri
+  L.add_work(CLS_GEMM_TRTRI, (double)L.work_items * wn * wn * wn / 3.0);  // dtrtri
+  Launch Lt = L;
+  Lt.gemm_cls = CLS_GEMM_TRTRI;
   for (int h = 1; h < nblk; h *= 2) {
     const int G = 2 * h;
     const int groups = (nblk + G - 1) / G;
@@ -443,7 +445,7 @@ cudaError_t trtri_blocked(const Launch& L, const MatSet& ms, const int* active) 
     a.m_kind = EXT_FIXED; a.n_kind = EXT_H2; a.k_kind = EXT_FIXED;
     a.grp_blocks = G; a.half_blocks = h; a.nblk = nblk;
     a.k_rule = KRULE_BEGIN_AT_ROW; a.lower_only = 0; a.alpha = 1.0; a.beta = 0.0; a.active = active;
-    AGPC_CUDA_TRY(gemm_nt_launch(L, ms.mapU, ms.mapA, a, h * h, groups, ms.batch));
+    AGPC_CUDA_TRY(gemm_nt_launch(Lt, ms.mapU, ms.mapA, a, h * h, groups, ms.batch));
     // step 2: M21 = -M22 * T^T ; U12 = M21^T
     GemmArgs c{};
     c.C = ms.M; c.Ct = ms.U; c.ldc = ms.np; c.c_batch = ms.stride;
@@ -455,7 +457,7 @@ cudaError_t trtri_blocked(const Launch& L, const MatSet& ms, const int* active) 
     c.m_kind = EXT_H2; c.n_kind = EXT_FIXED; c.k_kind = EXT_H2;
     c.grp_blocks = G; c.half_blocks = h; c.nblk = nblk;
     c.k_rule = KRULE_END_AT_ROW; c.lower_only = 0; c.alpha = -1.0; c.beta = 0.0; c.active = active;
-    AGPC_CUDA_TRY(gemm_nt_launch(L, ms.mapM, ms.mapT, c, h * h, groups, ms.batch));
+    AGPC_CUDA_TRY(gemm_nt_launch(Lt, ms.mapM, ms.mapT, c, h * h, groups, ms.batch));
   }
   return cudaSuccess;
 }
@@ -464,12 +466,14 @@ cudaError_t trtri_blocked(const Launch& L, const MatSet& ms, const int* active) 
 cudaError_t lauum_blocked(const Launch& L, const MatSet& ms, double* dst, const int* active) {
   const int nblk = ms.np / TILE;
   const double wn = L.work_n > 0.0 ? L.work_n : (double)ms.np;
-  L.add_work(CLS_GEMM, (double)L.work_items * wn * wn * wn / 3.0);  // dlauum
+  L.add_work(CLS_GEMM_LAUUM, (double)L.work_items * wn * wn * wn / 3.0);  // dlauum
+  Launch Ll = L;
+  Ll.gemm_cls = CLS_GEMM_LAUUM;
   GemmArgs a{};
   a.C = dst; a.Ct = nullptr; a.ldc = ms.np; a.c_batch = ms.stride;
   a.m_tiles = nblk; a.n_tiles = nblk; a.k_tiles = nblk * (TILE / GEMM_BK);
   a.k_rule = KRULE_BEGIN_AT_ROW; a.lower_only = 1; a.alpha = 1.0; a.beta = 0.0; a.active = active;
-  return gemm_nt_launch(L, ms.mapU, ms.mapU, a, nblk * (nblk + 1) / 2, 1, ms.batch);
+  return gemm_nt_launch(Ll, ms.mapU, ms.mapU, a, nblk * (nblk + 1) / 2, 1, ms.batch);
 }
 
 }  // namespace agpc

@@ -39,7 +39,8 @@ struct GemmArgs {
 };
 
 // Kernel classes of the optional per-launch event timing (agpc_profile_*): bench.py's roofline and the share table.
-enum : int { CLS_KBUILD = 0, CLS_GEMM, CLS_POTF2, CLS_MATVEC, CLS_EP, CLS_GRAD, CLS_FORMB, CLS_MISC, CLS_COUNT };
+enum : int { CLS_KBUILD = 0, CLS_GEMM, CLS_POTF2, CLS_MATVEC, CLS_EP, CLS_GRAD, CLS_FORMB, CLS_MISC, CLS_GEMM_TRTRI, CLS_GEMM_LAUUM,
+              CLS_COUNT };  // CLS_GEMM = the tile GEMM inside potrf (and predict); _TRTRI / _LAUUM = the same kernel in those phases
 
 // When enabled, every launcher brackets its kernel with a cudaEvent pair on the launching stream; the pairs are
 // summed per class by agpc_profile_read.  `work` is the ALGORITHMIC work the drivers attribute to a class
@@ -75,6 +76,7 @@ struct Launch {
   Profiler* prof = nullptr;
   cudaStream_t side = nullptr;        // second stream + two events for the look-ahead of single-matrix factorisations
   cudaEvent_t ev_panel = nullptr, ev_rest = nullptr;
+  int gemm_cls = CLS_GEMM;  // profiler class the tile GEMM is booked under (potrf / trtri / lauum phase)
   int work_items = 1;     // items still active in the batch      } algorithmic work accounting only
   double work_n = 0.0;    // mean true n of the batch's items     }
   void bump(int n = 1) const {

@@ -234,7 +234,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
 cudaError_t gemm_nt_launch(const Launch& L, const CUtensorMap& mapA, const CUtensorMap& mapB, const GemmArgs& args,
                            int tiles_x, int groups, int batch) {
-  ProfScope prof_scope(L, CLS_GEMM);
+  ProfScope prof_scope(L, L.gemm_cls);
   static bool configured = false;
   if (!configured) {
     AGPC_CUDA_TRY(cudaFuncSetAttribute(gemm_nt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -251,7 +251,7 @@ cudaError_t gemm_nt_launch(const Launch& L, const CUtensorMap& mapA, const CUten
 // thin variant: args.n_tiles counts 32-wide column tiles; mapB must have a 32-row box (make_tensor_map box_rows = 32)
 cudaError_t gemm_nt_thin_launch(const Launch& L, const CUtensorMap& mapA, const CUtensorMap& mapB32,
                                 const GemmArgs& args, int tiles_x, int groups, int batch) {
-  ProfScope prof_scope(L, CLS_GEMM);
+  ProfScope prof_scope(L, L.gemm_cls);
   static bool configured = false;
   if (!configured) {
     AGPC_CUDA_TRY(cudaFuncSetAttribute(gemm_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));

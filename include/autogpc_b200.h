@@ -107,7 +107,9 @@ int64_t agpc_launch_count(agpc_ctx* ctx);
 #define AGPC_CLS_GRAD 5
 #define AGPC_CLS_FORMB 6
 #define AGPC_CLS_MISC 7
-#define AGPC_CLS_COUNT 8
+#define AGPC_CLS_GEMM_TRTRI 8 /* the tile GEMM inside trtri (AGPC_CLS_GEMM: inside potrf / predict) */
+#define AGPC_CLS_GEMM_LAUUM 9 /* ... inside lauum */
+#define AGPC_CLS_COUNT 10
 int agpc_profile_enable(agpc_ctx* ctx, int32_t on);
 int agpc_profile_read(agpc_ctx* ctx, double* ms, double* work, int64_t* launches);
 

@@ -36,6 +36,6 @@ print(json.dumps({"config": "configs[1] greedy expansion D=4 n=%d" % N, "max_eva
                                 "launches": eng.launches - l1,
                                 "candidates_per_s": len(children) / (t3 - t2),
                                 "kernel_ms": {k: round(v["ms"], 1) for k, v in prof.items()},
-                                "gpu_busy_fraction": sum(v["ms"] for v in prof.values()) / (1e3 * (t3 - t2)),
+                                "gpu_busy_fraction": sum(v["ms"] for k, v in prof.items() if k != "gemm") / (1e3 * (t3 - t2)),
                                 "gemm_tflops": prof["gemm"]["work"] / (prof["gemm"]["ms"] * 1e-3) / 1e12,
                                 "ranking": [(k.kernel.structure(), round(k.bic(), 3), round(k.error(), 4)) for k in children]}}))
