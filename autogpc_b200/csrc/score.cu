@@ -165,6 +165,65 @@ int poll_active(agpc_ctx* ctx, const Launch& L, const int* active_dev, int nb, i
   return AGPC_OK;
 }
 
+// EP for one lock-step chunk (K is already built): parallel-schedule sweeps until every item has converged, then the
+// posterior at the final sites, log Z_EP, alpha and (optionally) the gradient.  tau_src / nu_src: warm-start sites.
+int ep_chunk(agpc_ctx* ctx, Launch& L, Chunk& c, const agpc_ep_options* opt, int theta_stride, bool want_grad, int D,
+             bool warm, bool frozen, const double* tau_src, const double* nu_src, int site_stride) {
+  const int np = c.np, nb = c.nb;
+  const int tb = 256;
+  dim3 gvec((np + tb - 1) / tb, nb);
+  if (warm) {
+    copy_strided_kernel<<<gvec, tb, 0, L.stream>>>(c.tau, np, tau_src, site_stride, c.n_of, np, 1);
+    copy_strided_kernel<<<gvec, tb, 0, L.stream>>>(c.nu, np, nu_src, site_stride, c.n_of, np, 1);
+    clamp_tau_kernel<<<gvec, tb, 0, L.stream>>>(c.tau, c.kdiag, c.n_of, np);
+    L.bump(3);
+  } else {
+    CK(cudaMemsetAsync(c.tau, 0, sizeof(double) * (size_t)nb * np, L.stream));
+    CK(cudaMemsetAsync(c.nu, 0, sizeof(double) * (size_t)nb * np, L.stream));
+  }
+
+  // ---- EP sweeps (parallel schedule) ----
+  for (int sweep = 1; sweep <= opt->max_sweeps; ++sweep) {
+    if (sweep == 1 && !warm) {
+      CK(marginals_launch(L, c.tau, c.dB, c.w, c.kv, c.kdiag, c.sig, c.mu, c.n_of, np, nb, 1, c.active));
+    } else {
+      CK(posterior(L, c, c.active));
+    }
+    // GPy measures convergence as the change between two sweeps (hence >= 2 from a cold start); the residual used here
+    // is an absolute fixed-point error, so warm-started sites that are already converged may stop after one sweep
+    CK(ep_update_launch(L, c.tau, c.nu, c.sig, c.mu, c.yf, c.kdiag, c.n_of, np, nb, opt->epsilon, opt->damping,
+                        warm ? 1 : 2, c.active, c.sweeps, c.status, c.converged, c.info));
+    int n_active = 0;
+    int rc = poll_active(ctx, L, c.active, nb, &n_active);
+    if (rc) return rc;
+    if (n_active == 0) break;
+    L.work_items = n_active;
+  }
+  L.work_items = nb;
+  if (!frozen) {
+    mark_unconverged_kernel<<<(nb + 255) / 256, 256, 0, L.stream>>>(c.active, c.status, nb);
+    L.bump();
+  }
+
+  // ---- final posterior at the final sites, log Z, gradient ----
+  CK(cudaMemsetAsync(c.info, 0, sizeof(int) * nb, L.stream));
+  CK(posterior(L, c, nullptr));
+  CK(ep_final_launch(L, c.tau, c.nu, c.sig, c.mu, c.yf, c.s, c.z, c.ms.A, c.ms.stride, c.n_of, np, nb, c.progs,
+                     c.alpha, c.nlml, c.nlml_gauss, c.bic, c.status, c.info));
+  if (want_grad) {
+    CK(lauum_blocked(L, c.ms, c.ms.T, nullptr));
+    GradArgs ga{};
+    ga.progs = c.progs; ga.theta = c.theta; ga.theta_stride = theta_stride; ga.Xf = c.Xf; ga.n_of = c.n_of;
+    ga.np = np; ga.D = D; ga.G = c.ms.T; ga.ld = np; ga.g_batch = c.ms.stride; ga.alpha = c.alpha; ga.s = c.s;
+    ga.mode = 0; ga.partial = c.partial; ga.tiles_per_item = grad_tiles(np, 0); ga.active = nullptr;
+    // d nlml / d theta = - sum dL_dK * dK/dtheta
+    L.add_work(CLS_GRAD, 4.0 * L.work_n * L.work_n * nb);  // lower triangle of B^-1 read once
+    CK(cudaMemsetAsync(c.grad, 0, sizeof(double) * (size_t)nb * theta_stride, L.stream));
+    CK(grad_contract_launch(L, ga, nb, -1.0, c.grad, theta_stride));
+  }
+  return AGPC_OK;
+}
+
 // Laplace approximation for one lock-step chunk ([R&W] alg. 3.1 with step halving, then alg. 5.1); K is already built.
 // Vector roles: mu = f, alpha = a = K^-1 f, tau = W, s = sqrt(W), nu = b = W f + grad, w = grad log p, sig = d3.
 int laplace_chunk(agpc_ctx* ctx, Launch& L, Chunk& c, const agpc_ep_options* opt, int theta_stride, bool want_grad, int D) {
@@ -335,65 +394,14 @@ int agpc_score_batch_dev(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, con
     const bool laplace = opt->inference == AGPC_INFER_LAPLACE;
     const bool frozen = !laplace && opt->max_sweeps <= 0;
     const bool warm = !laplace && (frozen || opt->warm_start != 0);
-    if (laplace) {
-      rc = laplace_chunk(ctx, L, c, opt, theta_stride, grad_dev != nullptr, ds.D);
-      if (rc) return rc;
-      if (grad_dev)
-        CK(cudaMemcpyAsync(grad_dev + (size_t)first * theta_stride, c.grad, sizeof(double) * (size_t)nb * theta_stride,
-                           cudaMemcpyDeviceToDevice, L.stream));
-    } else {
-    if (warm) {
-      copy_strided_kernel<<<gvec, tb, 0, L.stream>>>(c.tau, np, tau_dev + (size_t)first * site_stride, site_stride, c.n_of, np, 1);
-      copy_strided_kernel<<<gvec, tb, 0, L.stream>>>(c.nu, np, nu_dev + (size_t)first * site_stride, site_stride, c.n_of, np, 1);
-      clamp_tau_kernel<<<gvec, tb, 0, L.stream>>>(c.tau, c.kdiag, c.n_of, np);
-      L.bump(3);
-    } else {
-      CK(cudaMemsetAsync(c.tau, 0, sizeof(double) * (size_t)nb * np, L.stream));
-      CK(cudaMemsetAsync(c.nu, 0, sizeof(double) * (size_t)nb * np, L.stream));
-    }
-
-    // ---- EP sweeps (parallel schedule) ----
-    for (int sweep = 1; sweep <= opt->max_sweeps; ++sweep) {
-      if (sweep == 1 && !warm) {
-        CK(marginals_launch(L, c.tau, c.dB, c.w, c.kv, c.kdiag, c.sig, c.mu, c.n_of, np, nb, 1, c.active));
-      } else {
-        CK(posterior(L, c, c.active));
-      }
-      // GPy measures convergence as the change between two sweeps (hence >= 2 from a cold start); the residual used here
-      // is an absolute fixed-point error, so warm-started sites that are already converged may stop after one sweep
-      CK(ep_update_launch(L, c.tau, c.nu, c.sig, c.mu, c.yf, c.kdiag, c.n_of, np, nb, opt->epsilon, opt->damping,
-                          warm ? 1 : 2, c.active, c.sweeps, c.status, c.converged, c.info));
-      int n_active = 0;
-      rc = poll_active(ctx, L, c.active, nb, &n_active);
-      if (rc) return rc;
-      if (n_active == 0) break;
-      L.work_items = n_active;
-    }
-    L.work_items = nb;
-    if (!frozen) {
-      mark_unconverged_kernel<<<(nb + 255) / 256, 256, 0, L.stream>>>(c.active, c.status, nb);
-      L.bump();
-    }
-
-    // ---- final posterior at the final sites, log Z, gradient ----
-    CK(cudaMemsetAsync(c.info, 0, sizeof(int) * nb, L.stream));
-    CK(posterior(L, c, nullptr));
-    CK(ep_final_launch(L, c.tau, c.nu, c.sig, c.mu, c.yf, c.s, c.z, c.ms.A, c.ms.stride, c.n_of, np, nb, c.progs,
-                       c.alpha, c.nlml, c.nlml_gauss, c.bic, c.status, c.info));
-    if (grad_dev) {
-      CK(lauum_blocked(L, c.ms, c.ms.T, nullptr));
-      GradArgs ga{};
-      ga.progs = c.progs; ga.theta = c.theta; ga.theta_stride = theta_stride; ga.Xf = c.Xf; ga.n_of = c.n_of;
-      ga.np = np; ga.D = ds.D; ga.G = c.ms.T; ga.ld = np; ga.g_batch = c.ms.stride; ga.alpha = c.alpha; ga.s = c.s;
-      ga.mode = 0; ga.partial = c.partial; ga.tiles_per_item = grad_tiles(np, 0); ga.active = nullptr;
-      // d nlml / d theta = - sum dL_dK * dK/dtheta
-      L.add_work(CLS_GRAD, 4.0 * L.work_n * L.work_n * nb);  // lower triangle of B^-1 read once
-      CK(cudaMemsetAsync(c.grad, 0, sizeof(double) * (size_t)nb * theta_stride, L.stream));
-      CK(grad_contract_launch(L, ga, nb, -1.0, c.grad, theta_stride));
+    rc = laplace ? laplace_chunk(ctx, L, c, opt, theta_stride, grad_dev != nullptr, ds.D)
+                 : ep_chunk(ctx, L, c, opt, theta_stride, grad_dev != nullptr, ds.D, warm, frozen,
+                            warm ? tau_dev + (size_t)first * site_stride : nullptr,
+                            warm ? nu_dev + (size_t)first * site_stride : nullptr, site_stride);
+    if (rc) return rc;
+    if (grad_dev)
       CK(cudaMemcpyAsync(grad_dev + (size_t)first * theta_stride, c.grad, sizeof(double) * (size_t)nb * theta_stride,
                          cudaMemcpyDeviceToDevice, L.stream));
-    }
-    }  // EP
     // ---- outputs ----
     CK(cudaMemcpyAsync(nlml_dev + first, c.nlml, sizeof(double) * nb, cudaMemcpyDeviceToDevice, L.stream));
     if (bic_dev) CK(cudaMemcpyAsync(bic_dev + first, c.bic, sizeof(double) * nb, cudaMemcpyDeviceToDevice, L.stream));
