@@ -212,6 +212,61 @@ def test_predict_matches_oracle(engine):
     assert err_g == err_o
 
 
+@pytest.mark.parametrize("name", ["se0xse1+per3+se2", "mix"])
+def test_predict_points_and_mean_gradients(engine, name):
+    """m.predict(Xnew) / m._raw_predict / m.predictive_gradients (gpckernel.py:832, 431; gpcplot.py:110-114) at points that
+    are not dataset rows: p*, mu*, v* against the oracle, d mu*/d x* against central differences of the oracle's mean."""
+    X, y = synth(260, 4, 6)
+    prog = orc.KernelProgram.from_tree(TREES[name])
+    th = random_theta(prog, np.random.default_rng(12))
+    tr = np.arange(200, dtype=np.int32)
+    Xs = np.random.default_rng(1).uniform(-2.5, 2.5, (37, 4))
+    ep = to_engine_program(prog)
+    did = engine.dataset(X, y)
+    g = engine.score_batch(did, [ep], [th], [tr])
+    p, mu, var, dmu = engine.predict_points(did, ep, th, tr, g["tau"][0], g["nu"][0], Xs, want_gradients=True)
+    engine.dataset_free(did)
+    po, muo, varo = orc.predict(prog, th, X[tr], Xs, g["tau"][0], g["nu"][0])
+    assert np.allclose(mu, muo, rtol=1e-8, atol=1e-10) and np.allclose(var, varo, rtol=1e-7, atol=1e-10)
+    assert np.allclose(p, po, rtol=1e-8, atol=1e-12)
+    h = 1e-6
+    for d in range(4):
+        e = np.zeros(4)
+        e[d] = h
+        fd = (orc.predict(prog, th, X[tr], Xs + e, g["tau"][0], g["nu"][0])[1] -
+              orc.predict(prog, th, X[tr], Xs - e, g["tau"][0], g["nu"][0])[1]) / (2 * h)
+        assert np.allclose(dmu[:, d], fd, rtol=1e-5, atol=1e-7), d
+
+
+def test_gpy_shim_on_the_engine(engine):
+    """The GPy-shaped surface on the real engine: constructor = one inference, optimize() lowers the objective, predict /
+    _raw_predict / predictive_gradients shapes as AutoGPC consumes them."""
+    from autogpc_b200 import engine as eng_mod
+    from autogpc_b200 import gpy_compat as GPy
+    X, y = synth(180, 2, 5)
+    eng_mod.set_default_engine(engine)
+    try:
+        k = GPy.kern.RBF(1, variance=1.0, lengthscale=1.0, active_dims=np.array([0])) * \
+            GPy.kern.RBF(1, variance=1.0, lengthscale=1.0, active_dims=np.array([1]))
+        k.parts[0]["lengthscale"].constrain_bounded(0.05, 12.0, warning=False)
+        m = GPy.models.GPClassification(X, y.reshape(-1, 1), kernel=k)
+        prog = orc.KernelProgram.from_tree(("*", ("SE", 0), ("SE", 1)))
+        nl0 = -m.log_likelihood()
+        assert nl0 == pytest.approx(orc.score(prog, m.kern.param_array, X, y, damping=0.0)["nlml"], rel=1e-9)
+        m.optimize(max_iters=40)
+        assert -m.log_likelihood() < nl0
+        Phi, _ = m.predict(X[:9])
+        mu, var = m._raw_predict(X[:9])
+        dmu, _ = m.predictive_gradients(X[:9])
+        assert Phi.shape == (9, 1) and mu.shape == (9, 1) and var.shape == (9, 1) and dmu.shape == (9, 2, 1)
+        assert np.all((Phi > 0) & (Phi < 1)) and np.all(var > 0)
+        lap = GPy.models.GPClassification(X, y.reshape(-1, 1), kernel=m.kern.copy(),
+                                          inference_method=GPy.inference.latent_function_inference.Laplace())
+        assert -lap.log_likelihood() == pytest.approx(orc.score_laplace(prog, lap.kern.param_array, X, y)["nlml"], rel=1e-9)
+    finally:
+        eng_mod.set_default_engine(None)
+
+
 def test_not_pd_is_per_item_status(engine):
     """A hopeless item (negative variance) must not abort the batch (gpckernel.py:196-199 semantics)."""
     X, y = synth(200, 2, 1)
