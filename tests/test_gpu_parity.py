@@ -267,6 +267,35 @@ def test_gpy_shim_on_the_engine(engine):
         eng_mod.set_default_engine(None)
 
 
+def test_chunked_batches_equal_one_chunk(engine):
+    """A workspace limit that holds ~3 items forces a 10-item batch through several lock-step chunks (the path a
+    360-item search depth takes at n = 6400): results must be bit-identical to the single-chunk run."""
+    from autogpc_b200.engine import Engine
+    X, y = synth(400, 4, 14)
+    rng = np.random.default_rng(3)
+    progs, thetas, rows = [], [], []
+    for i, name in enumerate(["se0xse1", "per0", "mix", "se0+se1", "se0xse1+per3+se2"] * 2):
+        prog = orc.KernelProgram.from_tree(TREES[name])
+        progs.append(to_engine_program(prog))
+        thetas.append(random_theta(prog, rng))
+        rows.append(np.sort(rng.choice(400, size=300 + 7 * i, replace=False)).astype(np.int32))
+    did = engine.dataset(X, y)
+    one = engine.score_batch(did, progs, thetas, rows, damping=0.0)
+    engine.dataset_free(did)
+    per_item = 5 * 384 * 384 * 8 + 64 * 1024          # five padded n x n matrices + vectors
+    small = Engine(0, workspace_limit_bytes=int(3.5 * per_item))
+    try:
+        did2 = small.dataset(X, y)
+        many = small.score_batch(did2, progs, thetas, rows, damping=0.0)
+        small.dataset_free(did2)
+    finally:
+        small.close()
+    assert np.array_equal(one["status"], many["status"]) and np.array_equal(one["sweeps"], many["sweeps"])
+    assert np.array_equal(one["nlml"], many["nlml"]) and np.array_equal(one["grad"], many["grad"])
+    for a, b in zip(one["tau"], many["tau"]):
+        assert np.array_equal(a, b)
+
+
 def test_not_pd_is_per_item_status(engine):
     """A hopeless item (negative variance) must not abort the batch (gpckernel.py:196-199 semantics)."""
     X, y = synth(200, 2, 1)
