@@ -267,6 +267,61 @@ def test_gpy_shim_on_the_engine(engine):
         eng_mod.set_default_engine(None)
 
 
+def test_device_resident_entry_point_matches_host_entry_point(engine):
+    """agpc_score_batch_dev (theta / rows / sites / outputs in HBM, caller's stream) against agpc_score_batch."""
+    torch = _torch()
+    from autogpc_b200.engine import EPOptions, Program
+    X, y = synth(300, 4, 2)
+    names = ["se0xse1", "mix", "per0"]
+    oprogs = [orc.KernelProgram.from_tree(TREES[n]) for n in names]
+    progs = [to_engine_program(p) for p in oprogs]
+    thetas = [random_theta(p, np.random.default_rng(i)) for i, p in enumerate(oprogs)]
+    rows = [np.arange(0, 260, dtype=np.int32), np.arange(20, 300, dtype=np.int32), np.arange(0, 300, 2, dtype=np.int32)]
+    did = engine.dataset(X, y)
+    host = engine.score_batch(did, progs, thetas, rows, damping=0.0)
+    B, stride, n_max = 3, max(p.n_theta for p in progs), max(len(r) for r in rows)
+    th = np.zeros((B, stride))
+    for b, t in enumerate(thetas):
+        th[b, :len(t)] = t
+    off = np.zeros(B + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(r) for r in rows])
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        th_d = torch.from_numpy(th).cuda()
+        rows_d = torch.from_numpy(np.concatenate(rows)).cuda()
+        tau_d = torch.zeros((B, n_max), dtype=torch.float64, device="cuda")
+        nu_d = torch.zeros_like(tau_d)
+        nlml_d = torch.zeros(B, dtype=torch.float64, device="cuda")
+        grad_d = torch.zeros((B, stride), dtype=torch.float64, device="cuda")
+        bic_d, gauss_d = torch.zeros_like(nlml_d), torch.zeros_like(nlml_d)
+        sw_d = torch.zeros(B, dtype=torch.int32, device="cuda")
+        st_d = torch.zeros(B, dtype=torch.int32, device="cuda")
+        engine.score_batch_dev(did, (Program * B)(*progs), B, th_d.data_ptr(), stride, rows_d.data_ptr(), off,
+                               EPOptions(1e-6, 0.0, 100, 0, 0, 0), tau_d.data_ptr(), nu_d.data_ptr(), n_max,
+                               nlml_d.data_ptr(), grad_d.data_ptr(), bic_d.data_ptr(), gauss_d.data_ptr(), sw_d.data_ptr(),
+                               st_d.data_ptr(), st.cuda_stream)
+    st.synchronize()
+    engine.dataset_free(did)
+    assert np.array_equal(nlml_d.cpu().numpy(), host["nlml"]) and np.array_equal(grad_d.cpu().numpy(), host["grad"])
+    assert np.array_equal(sw_d.cpu().numpy(), host["sweeps"]) and np.array_equal(st_d.cpu().numpy(), host["status"])
+    for b in range(B):
+        assert np.array_equal(tau_d[b, :len(rows[b])].cpu().numpy(), host["tau"][b])
+
+
+def test_gemm_nt_building_block(engine):
+    torch = _torch()
+    torch.manual_seed(0)
+    for (M, N, K, batch, alpha, beta) in [(128, 128, 16, 1, 1.0, 0.0), (256, 384, 160, 2, -1.0, 1.0), (512, 256, 1024, 3, 0.5, 0.25)]:
+        A = torch.randn(batch, M, K, dtype=torch.float64, device="cuda")
+        Bm = torch.randn(batch, N, K, dtype=torch.float64, device="cuda")
+        C = torch.randn(batch, M, N, dtype=torch.float64, device="cuda")
+        ref = alpha * A @ Bm.transpose(1, 2) + beta * C
+        torch.cuda.synchronize()
+        engine.gemm_nt(A.data_ptr(), Bm.data_ptr(), C.data_ptr(), M, N, K, alpha, beta, batch)
+        torch.cuda.synchronize()
+        assert (C - ref).abs().max().item() <= 1e-13 * ref.abs().max().item() * K ** 0.5
+
+
 def test_chunked_batches_equal_one_chunk(engine):
     """A workspace limit that holds ~3 items forces a 10-item batch through several lock-step chunks (the path a
     360-item search depth takes at n = 6400): results must be bit-identical to the single-chunk run."""
