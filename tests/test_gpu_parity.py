@@ -322,6 +322,24 @@ def test_gemm_nt_building_block(engine):
         assert (C - ref).abs().max().item() <= 1e-13 * ref.abs().max().item() * K ** 0.5
 
 
+def test_profile_counters_book_the_launches(engine):
+    """agpc_profile_enable / agpc_profile_read: per-class event time, algorithmic work and launch counts."""
+    X, y = synth(300, 2, 1)
+    prog = to_engine_program(orc.KernelProgram.from_tree(TREES["se0xse1"]))
+    did = engine.dataset(X, y)
+    engine.profile_enable(True)
+    l0 = engine.launches
+    engine.score_batch(did, [prog], [np.ones(4)], [np.arange(300, dtype=np.int32)])
+    prof = engine.profile_read()
+    engine.profile_enable(False)
+    engine.dataset_free(did)
+    assert sum(v["launches"] for k, v in prof.items() if k != "gemm") <= engine.launches - l0
+    assert prof["kbuild"]["launches"] == 1 and prof["kbuild"]["work"] == pytest.approx(8.0 * 300 * 300)
+    assert prof["potf2"]["launches"] >= 3 and prof["gemm"]["launches"] > 0 and prof["gemm"]["ms"] > 0
+    assert prof["gemm"]["work"] == pytest.approx(prof["gemm_potrf"]["work"] + prof["gemm_trtri"]["work"] + prof["gemm_lauum"]["work"])
+    assert prof["gemm_lauum"]["work"] == pytest.approx(300.0 ** 3 / 3.0)
+
+
 def test_chunked_batches_equal_one_chunk(engine):
     """A workspace limit that holds ~3 items forces a 10-item batch through several lock-step chunks (the path a
     360-item search depth takes at n = 6400): results must be bit-identical to the single-chunk run."""
