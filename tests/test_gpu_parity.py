@@ -636,3 +636,85 @@ def test_api_misuse_is_an_error_code_not_a_crash(engine):
     ok = engine.score_batch(did, [prog], [th], [np.arange(50, dtype=np.int32)])   # the context is still usable
     engine.dataset_free(did)
     assert ok["status"][0] == 0 and np.isfinite(ok["nlml"][0])
+
+
+# ---- randomized sweep: random grammar-shaped programs, sizes and folds in one batch -----------------------------------
+def _random_tree(rng, D, depth):
+    if depth == 0 or rng.random() < 0.35:
+        kind = rng.choice(["SE", "PER", "LIN", "CONST"], p=[0.45, 0.25, 0.2, 0.1])
+        return ("CONST",) if kind == "CONST" else (str(kind), int(rng.integers(D)))
+    op = "+" if rng.random() < 0.5 else "*"
+    return (op,) + tuple(_random_tree(rng, D, depth - 1) for _ in range(int(rng.integers(2, 4))))
+
+
+def test_randomized_programs_batch(engine):
+    """24 random sum / product trees (up to 3 levels, shared leaves after distribution included), random theta, random
+    ragged row subsets, scored in ONE batch with the production EP schedule: NLML, gradient, BIC and sites against the oracle."""
+    rng = np.random.default_rng(2024)
+    D = 5
+    X, y = synth(420, D, 31)
+    progs, oprogs, thetas, rows = [], [], [], []
+    while len(progs) < 24:
+        prog = orc.KernelProgram.from_tree(_random_tree(rng, D, 3))
+        if len(prog.leaf_type) > 16 or len(prog.terms) > 16 or max(len(t) for t in prog.terms) > 8 or prog.n_theta > 48:
+            continue
+        if all(t == orc.LEAF_CONST for t in prog.leaf_type) and len(prog.leaf_type) > 1:
+            continue
+        oprogs.append(prog)
+        progs.append(to_engine_program(prog))
+        thetas.append(random_theta(prog, rng))
+        n = int(rng.integers(60, 400))
+        rows.append(np.sort(rng.choice(420, size=n, replace=False)).astype(np.int32))
+    did = engine.dataset(X, y)
+    g = engine.score_batch(did, progs, thetas, rows, damping=0.0)
+    engine.dataset_free(did)
+    for b, (prog, th, r) in enumerate(zip(oprogs, thetas, rows)):
+        o = orc.score(prog, th, X[r], y[r], damping=0.0)
+        assert g["status"][b] == o["status"], (b, g["status"][b], o["status"])
+        if o["status"] != 0:
+            continue
+        assert g["sweeps"][b] == o["sweeps"], b
+        assert abs(g["nlml"][b] - o["nlml"]) <= 1e-8 * abs(o["nlml"]), (b, g["nlml"][b], o["nlml"])
+        assert abs(g["bic"][b] - o["bic"]) <= 1e-8 * abs(o["bic"])
+        scale = np.maximum(np.abs(o["grad"]), 1e-3 * np.abs(o["grad"]).max() + 1e-12)
+        assert np.all(np.abs(g["grad"][b, :prog.n_theta] - o["grad"]) <= 1e-6 * scale), b
+        assert np.allclose(g["tau"][b], o["tau"], rtol=1e-6, atol=1e-12), b
+
+
+def test_baseline_config0_single_se_ard_n500(engine):
+    """BASELINE.json configs[0]: one SE-ARD (SE0 x SE1, gpckerneltest.py:53,80-81 spelling) GPClassification on synthetic
+    2-D data, n = 500, no folds, one full L-BFGS-B optimisation (gpckernel.py:245-246) -- through the GPy-shaped shim on
+    the engine against the oracle's restatement of the same optimisation: NLML and gradient at theta0 and at theta*."""
+    from autogpc_b200 import engine as eng_mod, flexible_function as ff, gpckernel
+    from autogpc_b200 import gpy_compat as GPy
+    from autogpc_b200.gpcdata import GPCData
+    X, y = synth(500, 2, 0)
+    d = GPCData(X, y.reshape(-1, 1))
+    prog = orc.KernelProgram.from_tree(("*", ("SE", 0), ("SE", 1)))
+    eprog = to_engine_program(prog)
+    eng_mod.set_default_engine(engine)
+    try:
+        k = ff.ProductKernel([ff.SqExpKernel(0, 1.0, 1.0), ff.SqExpKernel(1, 1.5, 0.8)])
+        m = GPy.models.GPClassification(X, y.reshape(-1, 1), kernel=gpckernel.gpss2gpy(k, data=d))
+        th0 = m.kern.param_array.copy()
+        m.optimize()
+        th1 = m.kern.param_array.copy()
+        nl1 = -m.log_likelihood()
+    finally:
+        eng_mod.set_default_engine(None)
+    lo, hi = d.getLengthscaleBounds()
+    tr = orc.Transforms(np.array([0, 1, 0, 1]), np.array([0, lo[0], 0, lo[1]]), np.array([0, hi[0], 0, hi[1]]))
+    rows = [np.arange(500, dtype=np.int32)]
+    did = engine.dataset(X, y)
+    for th in (th0, th1):                     # cold evaluations on both sides at theta0 and at the engine's theta*
+        g = engine.score_batch(did, [eprog], [th], rows, damping=0.0)     # the shim's (production) EP schedule
+        o = orc.score(prog, th, X, y, damping=0.0)
+        assert g["status"][0] == 0 and o["status"] == 0 and g["sweeps"][0] == o["sweeps"]
+        assert abs(g["nlml"][0] - o["nlml"]) <= 1e-9 * abs(o["nlml"])
+        # at theta* the gradient is the ~1e-4 remainder of O(|nlml|) terms that cancel: absolute floor from that scale
+        assert np.all(np.abs(g["grad"][0, :4] - o["grad"]) <= 1e-6 * np.abs(o["grad"]) + 1e-9 * abs(o["nlml"]))
+        assert abs(g["bic"][0] - (2 * o["nlml"] + 3 * np.log(500))) <= 1e-8 * abs(g["bic"][0])
+    engine.dataset_free(did)
+    ref = orc.optimize(prog, th0, X, y, tr, damping=0.0)
+    assert nl1 == pytest.approx(ref["nlml"], rel=1e-6)       # both optimisers stop at the same optimum
+    assert np.allclose(th1, ref["theta"], rtol=1e-4)
