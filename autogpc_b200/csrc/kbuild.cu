@@ -17,11 +17,87 @@
 //   grad_contract_kernel     fused <W, dK/dtheta> contraction (never materialises dK): what score_batch uses
 // Point coordinates of a tile live in shared memory, dimension-major (column reads conflict-free, row reads broadcast).
 // HBM-write-bound for one-exp programs, FP64-ALU / issue-bound once a term carries sin/cos.
+#include <math_constants.h>
+
 #include "common.cuh"
 
 namespace agpc {
 
 constexpr int KB_ROWS = 32, KB_COLS = 128, KB_THREADS = 256;
+
+// exp(x) for x <= 0 -- every exponent of a product term is -(sum of squares) / 2l^2.  libdevice's exp() spends more
+// issue slots on materialising its polynomial coefficients (two 32-bit moves per double under the 80-register cap of the
+// tiled kernels) and on its range / special-case tests than on arithmetic: 92 instructions per pair, ~25 of them FP64,
+// made build_K issue-bound at 54-61 % of HBM.  Here the coefficients are constant-bank operands of the DFMAs:
+// k = rint(x log2 e) via the 1.5 * 2^52 shifter, r = x - k ln2 (hi / lo split, exact product), Taylor polynomial on
+// the reduced argument, 2^k added into the exponent field.  Below -708 (result < 2.3e-308, subnormal) the
+// value is flushed to 0; NaN propagates; positive arguments are never produced by a valid program.
+__constant__ double EXP_C[14] = {
+    1.0, 1.0, 1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880, 1.0 / 3628800,
+    1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0};
+__constant__ double EXP_K[4] = {1.4426950408889634074, 6755399441055744.0, -6.93147180369123816490e-01,
+                                -1.90821492927058770002e-10};
+
+// select without a branch: ptxas otherwise turns the underflow test into a branch around the whole polynomial, which
+// serialises the independent exps of a register tile into one dependent DFMA chain each (ILP 1; "wait" stalls dominate)
+__device__ __forceinline__ double zero_if_below(double x, double lim, double v) {
+  double out;
+  asm("{ .reg .pred p; setp.lt.f64 p, %1, %2; selp.f64 %0, 0d0000000000000000, %3, p; }"
+      : "=d"(out) : "d"(x), "d"(lim), "d"(v));
+  return out;
+}
+
+// N independent exps in lock-step (every step is issued for all N values before the next one, so N dependent chains
+// are in flight), table-driven: k = rint(32 x log2 e), x = (k >> 5) ln2 + (k & 31) ln2/32 + r with |r| <= ln2/64, so a
+// degree-6 polynomial is exact to 4e-18 and exp(x) = 2^(k>>5) * T[k&31] * (1 + q(r)); 11 FP64 instructions per value
+// instead of 17 (the FP64 pipe issues one warp instruction every 2 cycles).  tab = EXP_T staged in shared memory.
+__constant__ double EXP_T[32] = {
+    0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, 0x1.11301d0125b51p+0,
+    0x1.172b83c7d517bp+0, 0x1.1d4873168b9aap+0, 0x1.2387a6e756238p+0, 0x1.29e9df51fdee1p+0,
+    0x1.306fe0a31b715p+0, 0x1.371a7373aa9cbp+0, 0x1.3dea64c123422p+0, 0x1.44e086061892dp+0,
+    0x1.4bfdad5362a27p+0, 0x1.5342b569d4f82p+0, 0x1.5ab07dd485429p+0, 0x1.6247eb03a5585p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.71f75e8ec5f74p+0, 0x1.7a11473eb0187p+0, 0x1.82589994cce13p+0,
+    0x1.8ace5422aa0dbp+0, 0x1.93737b0cdc5e5p+0, 0x1.9c49182a3f090p+0, 0x1.a5503b23e255dp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0,
+    0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0, 0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
+__constant__ double EXP_K32[4] = {0x1.71547652b82fep+5, 6755399441055744.0, -0x1.62e42fee00000p-6, -0x1.a39ef35793c76p-38};
+
+template <int N>
+__device__ __forceinline__ void exp_nonpos_n(double (&x)[N], const double* __restrict__ tab) {
+  double r[N], p[N], tj[N];
+  int e[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const double t = fma(x[j], EXP_K32[0], EXP_K32[1]);
+    const int ki = __double2loint(t);
+    const double kd = t - EXP_K32[1];
+    r[j] = fma(kd, EXP_K32[3], fma(kd, EXP_K32[2], x[j]));
+    tj[j] = tab[ki & 31];
+    e[j] = ki >> 5;
+    p[j] = EXP_C[6];
+  }
+#pragma unroll
+  for (int i = 5; i >= 1; --i)
+#pragma unroll
+    for (int j = 0; j < N; ++j) p[j] = fma(p[j], r[j], EXP_C[i]);
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const double v = fma(tj[j], p[j] * r[j], tj[j]);
+    x[j] = zero_if_below(x[j], -708.0, __hiloint2double(__double2hiint(v) + (e[j] << 20), __double2loint(v)));
+  }
+}
+
+// single value, table-free (generic kernels): Taylor degree 13 on |r| <= ln2 / 2
+__device__ __forceinline__ double exp_nonpos(double x) {
+  const double t = fma(x, EXP_K[0], EXP_K[1]);
+  const int k = __double2loint(t);
+  const double kd = t - EXP_K[1];
+  const double r = fma(kd, EXP_K[3], fma(kd, EXP_K[2], x));
+  double p = EXP_C[13];
+#pragma unroll
+  for (int i = 12; i >= 0; --i) p = fma(p, r, EXP_C[i]);
+  return zero_if_below(x, -708.0, __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p)));
+}
 
 struct LeafConst {
   int type, dim;
@@ -69,6 +145,80 @@ __device__ void load_program(ProgShared& P, const agpc_program& g, const double*
   }
 }
 
+// ---- prologue of the tiled kernels: everything a tile needs is requested in ONE round trip to memory --------------
+// The X panels go global -> shared with cp.async (no register staging, no wait before the next request), the program
+// words and the whole theta vector are loaded by other threads at the same time; the leaf constants (1/l^2, ...) are
+// then derived from shared memory.  (The first version chained program -> theta -> X loads: three dependent
+// round trips per 64 x 64 tile, ~30 % of the warp-time samples of build_K_tiled_kernel.)
+__device__ __forceinline__ void cp_async8(double* dst, const double* src, bool valid) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+  const int bytes = valid ? 8 : 0;   // 0 source bytes: the 8 destination bytes are zero-filled, src is not read
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(src), "r"(bytes) : "memory");
+}
+
+// xr[d][r] = Xa[row0 + r][d], xc[d][r] = Xb[col0 + r][d] for r < TILE_W; rows beyond *_pad read as 0.  256 threads.
+template <int TILE_W>
+__device__ __forceinline__ void load_x_tiles_async(double* xr, double* xc, const double* __restrict__ Xa,
+                                                   const double* __restrict__ Xb, int row0, int col0, int na_pad,
+                                                   int nb_pad, int D) {
+  static_assert(TILE_W == 64, "thread mapping assumes 64-wide tiles and 256 threads");
+  const int r = threadIdx.x & 63, which = threadIdx.x >> 7, d0 = (threadIdx.x >> 6) & 1;
+  const int g = (which ? col0 : row0) + r;
+  const bool ok = g < (which ? nb_pad : na_pad);
+  const double* src = (which ? Xb : Xa) + (ok ? (long long)g * D : 0);
+  double* dst = (which ? xc : xr) + r;
+  for (int d = d0; d < D; d += 2) cp_async8(dst + d * TILE_W, src + d, ok);
+}
+
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// phase A (any time before the first barrier): raw program words and theta -> shared
+__device__ __forceinline__ void load_program_raw(ProgShared& P, double* th_s, const agpc_program& g,
+                                                 const double* __restrict__ theta, int theta_stride) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    P.n_leaves = g.n_leaves;
+    P.n_terms = g.n_terms;
+    P.n_theta = g.n_theta;
+  }
+  if (tid < AGPC_MAX_TERMS) P.term_len[tid] = g.term_len[tid];
+  if (tid < AGPC_MAX_TERMS * AGPC_MAX_TERM_LEN) (&P.term_leaf[0][0])[tid] = (&g.term_leaf[0][0])[tid];
+  if (tid >= 128 && tid < 128 + AGPC_MAX_LEAVES) {
+    const int l = tid - 128;
+    P.leaf[l].type = g.leaf_type[l];
+    P.leaf[l].dim = g.leaf_dim[l];
+    P.leaf_off[l] = g.leaf_off[l];
+  }
+  if (tid >= 160 && tid < 160 + AGPC_MAX_THETA && tid - 160 < theta_stride) th_s[tid - 160] = theta[tid - 160];
+}
+
+// phase B (after the barrier that publishes phase A): leaf constants from shared memory; needs one more barrier
+__device__ __forceinline__ void derive_leaf_consts(ProgShared& P, const double* th_s) {
+  const int tid = threadIdx.x;
+  if (tid < P.n_leaves) {
+    LeafConst& lc = P.leaf[tid];
+    const int o = P.leaf_off[tid];
+    double a = 0.0, b = 0.0, d = 0.0;
+    if (lc.type == AGPC_LEAF_SE) {
+      const double l = th_s[o + 1];
+      a = 1.0 / (l * l);
+      b = 1.0 / (l * l * l);
+    } else if (lc.type == AGPC_LEAF_PER) {
+      const double T = th_s[o + 1], l = th_s[o + 2];
+      a = 1.0 / T;
+      b = 1.0 / (l * l);
+      d = 1.0 / (l * l * l);
+    } else if (lc.type == AGPC_LEAF_LIN) {
+      a = th_s[o + 1];
+    }
+    lc.var = th_s[o];
+    lc.a = a;
+    lc.b = b;
+    lc.c = 0.0;
+    lc.d = d;
+  }
+}
+
 // K(x, x') and (GRAD) its partials w.r.t. theta accumulated into dk[0..n_theta) with weight w.
 // xi(d) = xa[d * sa], xj(d) = xb[d * sb].
 template <bool GRAD>
@@ -104,7 +254,7 @@ __device__ __forceinline__ double eval_pair(const ProgShared& P, const double* x
       mult *= f;
       if (GRAD) fac[p] = f;
     }
-    const double e = has_exp ? exp(arg) : 1.0;
+    const double e = has_exp ? exp_nonpos(arg) : 1.0;
     const double v = mult * e;
     K += v;
     if (GRAD) {
@@ -230,6 +380,9 @@ build_K_tiled_kernel(const BuildArgs a, const int symmetric, const int tiles_n) 
   if (a.active != nullptr && a.active[b] == 0) return;
   extern __shared__ double smem[];
   __shared__ ProgShared P;
+  __shared__ double exp_tab[32];
+  __shared__ double th_s[AGPC_MAX_THETA];
+  if (threadIdx.x < 32) exp_tab[threadIdx.x] = EXP_T[threadIdx.x];
   const int D = a.D;
   double* xr = smem;                // [D][KT]
   double* xc = smem + D * KT;       // [D][KT]
@@ -237,7 +390,7 @@ build_K_tiled_kernel(const BuildArgs a, const int symmetric, const int tiles_n) 
   int ti, tj;
   if (symmetric) {
     const int t = blockIdx.x;
-    ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);  // estimate; the loops below make it exact
     while (ti * (ti + 1) / 2 > t) --ti;
     while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
     tj = t - ti * (ti + 1) / 2;
@@ -246,19 +399,17 @@ build_K_tiled_kernel(const BuildArgs a, const int symmetric, const int tiles_n) 
     tj = blockIdx.x % tiles_n;
   }
   const int row0 = ti * KT, col0 = tj * KT;
+  load_x_tiles_async<KT>(xr, xc, a.Xa + (long long)b * a.xa_batch, a.Xb + (long long)b * a.xb_batch, row0, col0,
+                         a.na_pad, a.nb_pad, D);
+  load_program_raw(P, th_s, a.progs[b], a.theta + (long long)b * a.theta_stride, a.theta_stride);
   const int na = a.na_of ? a.na_of[b] : a.na_fixed, nb = a.nb_of ? a.nb_of[b] : a.nb_fixed;
-  load_program(P, a.progs[b], a.theta + (long long)b * a.theta_stride);
-  const double* Xa = a.Xa + (long long)b * a.xa_batch;
-  const double* Xb = a.Xb + (long long)b * a.xb_batch;
-  for (int idx = threadIdx.x; idx < KT * D; idx += KT_THREADS) {
-    const int r = idx / D, d = idx % D;
-    xr[d * KT + r] = (row0 + r < a.na_pad) ? Xa[(long long)(row0 + r) * D + d] : 0.0;
-    xc[d * KT + r] = (col0 + r < a.nb_pad) ? Xb[(long long)(col0 + r) * D + d] : 0.0;
-  }
+  cp_async_wait_all();
+  __syncthreads();
+  derive_leaf_consts(P, th_s);
   __syncthreads();
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 
-  // two passes of 2 x 4 pairs (rows ty + 16r, r = 2h, 2h + 1): keeps the live set near 80 registers -> 3 CTAs per SM,
+  // two passes of 2 x 4 pairs (rows ty + 16r, r = 2h, 2h + 1): keeps the live set under 80 registers -> 3 CTAs per SM,
   // which is what hides the load -> compute -> store latency chain of a tile (the kernel is latency-, not ALU-bound)
   double* out = a.out + (long long)b * a.out_batch;
   const bool mirror = symmetric && ti != tj;
@@ -320,13 +471,14 @@ build_K_tiled_kernel(const BuildArgs a, const int symmetric, const int tiles_n) 
           for (int c = 0; c < 4; ++c) mc[c] *= xj[c] - lc.a;
         }
       }
+      if (has_exp) exp_nonpos_n<8>(reinterpret_cast<double(&)[8]>(arg), exp_tab);
 #pragma unroll
       for (int r = 0; r < 2; ++r)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           double v = scale;
           if (has_mult) v *= mr[r] * mc[c];
-          if (has_exp) v *= exp(arg[r][c]);
+          if (has_exp) v *= arg[r][c];
           K[r][c] += v;
         }
     }
@@ -360,6 +512,8 @@ build_K_tiled_kernel(const BuildArgs a, const int symmetric, const int tiles_n) 
     }
   }
   if (mirror) {
+    // (a direct store of the mirror image from registers -- 8 rows x 32 B per warp instruction -- was measured 20 %
+    // slower than this transposition through shared memory: 4x the L1 tag work per store instruction)
     __syncthreads();
     // mirror tile: rows col0.., columns row0..; element (jj, ii) = st[ii][jj]
     if (interior) {
@@ -453,6 +607,8 @@ build_KdK_tiled_kernel(const BuildArgs a, const int symmetric, const int tiles_n
   if (a.active != nullptr && a.active[b] == 0) return;
   extern __shared__ double smem[];
   __shared__ ProgShared P;
+  __shared__ double exp_tab[32];
+  if (threadIdx.x < 32) exp_tab[threadIdx.x] = EXP_T[threadIdx.x];
   const int D = a.D;
   double* xr = smem;
   double* xc = smem + D * KT;
@@ -460,7 +616,7 @@ build_KdK_tiled_kernel(const BuildArgs a, const int symmetric, const int tiles_n
   int ti, tj;
   if (symmetric) {
     const int t = blockIdx.x;
-    ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);  // estimate; the loops below make it exact
     while (ti * (ti + 1) / 2 > t) --ti;
     while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
     tj = t - ti * (ti + 1) / 2;
@@ -537,11 +693,12 @@ build_KdK_tiled_kernel(const BuildArgs a, const int symmetric, const int tiles_n
         for (int c = 0; c < 4; ++c) mc[c] *= xj[c] - lc.a;
       }
     }
+    if (has_exp) exp_nonpos_n<16>(reinterpret_cast<double(&)[16]>(ex), exp_tab);
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        ex[r][c] = has_exp ? exp(ex[r][c]) : 1.0;
+        if (!has_exp) ex[r][c] = 1.0;
         K[r][c] += scale * mr[r] * mc[c] * ex[r][c];
       }
 
@@ -707,7 +864,7 @@ grad_contract_kernel(const GradArgs a) {
   int ti, tj;
   if (a.mode == 0) {
     const int t = blockIdx.x;
-    ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);  // estimate; the loops below make it exact
     while (ti * (ti + 1) / 2 > t) --ti;
     while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
     tj = t - ti * (ti + 1) / 2;
