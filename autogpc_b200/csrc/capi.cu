@@ -90,9 +90,14 @@ int agpc_destroy(agpc_ctx* ctx) {
     if (d.X) cudaFree(d.X);
     if (d.y) cudaFree(d.y);
   }
+  for (auto& d : ctx->dataset_pool) {
+    cudaFree(d.X);
+    cudaFree(d.y);
+  }
   if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->stage) cudaFree(ctx->stage);
   if (ctx->prof.base) cudaEventDestroy(ctx->prof.base);
   for (auto& r : ctx->prof.recs) {
     cudaEventDestroy(r.e0);
@@ -181,8 +186,19 @@ int agpc_dataset_create(agpc_ctx* ctx, const double* X_host, const double* y_hos
   Dataset d;
   d.N = N;
   d.D = D;
-  CK(ctx, cudaMalloc(&d.X, sizeof(double) * (size_t)N * D));
-  CK(ctx, cudaMalloc(&d.y, sizeof(double) * (size_t)N));
+  for (size_t i = 0; i < ctx->dataset_pool.size(); ++i)
+    if (ctx->dataset_pool[i].N == N && ctx->dataset_pool[i].D == D) {
+      d = ctx->dataset_pool[i];
+      ctx->dataset_pool.erase(ctx->dataset_pool.begin() + i);
+      break;
+    }
+  if (!d.X) {
+    CK(ctx, cudaMalloc(&d.X, sizeof(double) * (size_t)N * D));
+    if (cudaMalloc(&d.y, sizeof(double) * (size_t)N) != cudaSuccess) {
+      cudaFree(d.X);
+      return fail(ctx, AGPC_E_NOMEM, "dataset_create cudaMalloc");
+    }
+  }
   CK(ctx, cudaMemcpyAsync(d.X, X_host, sizeof(double) * (size_t)N * D, cudaMemcpyHostToDevice, ctx->stream));
   // labels: 1 -> +1, everything else -> -1 (GPy bernoulli.py moments_match_ep)
   std::vector<double> ypm(N);
@@ -205,8 +221,12 @@ int agpc_dataset_destroy(agpc_ctx* ctx, int32_t id) {
   if (!ctx || id < 0 || id >= (int)ctx->datasets.size() || !ctx->datasets[id].X) return fail(ctx, AGPC_E_ARG, "bad dataset id");
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(ctx->datasets[id].X);
-  cudaFree(ctx->datasets[id].y);
+  if (ctx->dataset_pool.size() >= 4) {
+    cudaFree(ctx->dataset_pool.front().X);
+    cudaFree(ctx->dataset_pool.front().y);
+    ctx->dataset_pool.erase(ctx->dataset_pool.begin());
+  }
+  ctx->dataset_pool.push_back(ctx->datasets[id]);
   ctx->datasets[id] = Dataset();
   return AGPC_OK;
 }

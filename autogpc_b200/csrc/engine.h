@@ -25,7 +25,11 @@ struct agpc_ctx {
   void* pinned = nullptr;  // small pinned staging buffer for per-sweep flags
   size_t pinned_bytes = 0;
   void* scratch = nullptr;  // 64 KB device scratch: program + theta of the building-block entry points
+  void* stage = nullptr;    // grow-only device staging of the host-buffer entry point (cudaMalloc / cudaFree per
+  size_t stage_bytes = 0;   // call cost 0.5-350 ms on a box with > 100 GB allocated: profiles/r01_summary.md)
   std::vector<Dataset> datasets;
+  std::vector<Dataset> dataset_pool;  // buffers of destroyed datasets kept for re-use (at most 4): no cudaMalloc /
+                                      // cudaFree when a caller re-uploads a same-shaped dataset per step
   agpc::Profiler prof;
 
   int ensure_arena(size_t bytes);

@@ -7,6 +7,9 @@
 #include <cmath>
 #include <cstring>
 
+#include <chrono>
+#include <cstdlib>
+
 #include "engine.h"
 
 using namespace agpc;
@@ -116,6 +119,12 @@ __global__ void mark_unconverged_kernel(const int* __restrict__ active, int* __r
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < nb && active[b] != 0 && status[b] == AGPC_ST_OK) status[b] = AGPC_ST_EP_NOT_CONVERGED;
 }
+// need[b] = 1 unless the EP update left the item's sites untouched (converged[b] == 2, ep.cu): then the
+// factorisation, inverse and marginals in its buffers already belong to the final sites
+__global__ void need_final_kernel(const int* __restrict__ converged, int* __restrict__ need, int nb) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < nb) need[b] = converged[b] == 2 ? 0 : 1;
+}
 
 // posterior at the current sites for the items flagged in `active` (nullptr = all):
 // s, A = chol(B), M, U, w = K nu, z = B^-1 (s o w), dB = diag(B^-1), kv = K (s o z), then sig / mu.
@@ -205,9 +214,21 @@ int ep_chunk(agpc_ctx* ctx, Launch& L, Chunk& c, const agpc_ep_options* opt, int
     L.bump();
   }
 
-  // ---- final posterior at the final sites, log Z, gradient ----
+  // ---- final posterior at the final sites (only for the items whose sites moved after their last factorisation:
+  //      frozen or unconverged items and those that converged with a residual above the reuse threshold), log Z, gradient
   CK(cudaMemsetAsync(c.info, 0, sizeof(int) * nb, L.stream));
-  CK(posterior(L, c, nullptr));
+  need_final_kernel<<<(nb + 255) / 256, 256, 0, L.stream>>>(c.converged, c.active, nb);
+  L.bump();
+  int n_need = 0;
+  {
+    int rc = poll_active(ctx, L, c.active, nb, &n_need);
+    if (rc) return rc;
+  }
+  if (n_need > 0) {
+    L.work_items = n_need;
+    CK(posterior(L, c, c.active));
+    L.work_items = nb;
+  }
   CK(ep_final_launch(L, c.tau, c.nu, c.sig, c.mu, c.yf, c.s, c.z, c.ms.A, c.ms.stride, c.n_of, np, nb, c.progs,
                      c.alpha, c.nlml, c.nlml_gauss, c.bic, c.status, c.info));
   if (want_grad) {
@@ -442,7 +463,7 @@ int agpc_score_batch(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, const a
   const size_t nth = (size_t)n_items * theta_stride;
   const bool sites = tau && nu;
   const size_t nsite = sites ? (size_t)n_items * site_stride : 0;
-  // device staging (separate from the arena, which score_batch_dev may re-allocate)
+  // device staging (separate from the arena, which score_batch_dev may re-allocate); persistent in the context
   double *d_theta, *d_tau, *d_nu, *d_nlml, *d_grad, *d_bic, *d_gauss;
   int *d_rows, *d_sweeps, *d_status;
   auto carve = [&](char* base) {
@@ -461,8 +482,24 @@ int agpc_score_batch(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, const a
   };
   const size_t total = carve(nullptr);
   char* stage = nullptr;
-  CK(cudaMalloc(&stage, total));
+  static const bool trace = getenv("AGPC_TIMING") != nullptr;   // host-phase wall times of this call on stderr
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count();
+  };
+  const auto t0 = now();
+  if (ctx->stage_bytes < total) {   // grow-only: no cudaMalloc / cudaFree on the steady-state path
+    if (ctx->stage) cudaFree(ctx->stage);
+    ctx->stage = nullptr;
+    ctx->stage_bytes = 0;
+    const size_t want = total + total / 4;
+    if (cudaMalloc(&ctx->stage, want) != cudaSuccess) return fail(ctx, AGPC_E_NOMEM, "score_batch staging cudaMalloc");
+    ctx->stage_bytes = want;
+  }
+  stage = static_cast<char*>(ctx->stage);
   carve(stage);
+  const auto t1 = now();
+  auto t2 = t1, t3 = t1;
   int rc = AGPC_OK;
   cudaError_t e = cudaSuccess;
   do {
@@ -472,9 +509,11 @@ int agpc_score_batch(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, const a
       if ((e = cudaMemcpyAsync(d_tau, tau, sizeof(double) * nsite, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
       if ((e = cudaMemcpyAsync(d_nu, nu, sizeof(double) * nsite, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
     }
+    t2 = now();
     rc = agpc_score_batch_dev(ctx, dataset_id, n_items, programs, d_theta, theta_stride, d_rows, row_off, opt,
                               sites ? d_tau : nullptr, sites ? d_nu : nullptr, site_stride, d_nlml, grad ? d_grad : nullptr,
                               d_bic, d_gauss, d_sweeps, d_status, st);
+    t3 = now();
     if (rc) break;
     if ((e = cudaMemcpyAsync(nlml, d_nlml, sizeof(double) * n_items, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
     if (grad && (e = cudaMemcpyAsync(grad, d_grad, sizeof(double) * nth, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
@@ -489,7 +528,10 @@ int agpc_score_batch(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, const a
     e = cudaStreamSynchronize(st);
   } while (0);
   cudaStreamSynchronize(st);
-  cudaFree(stage);
+  const auto t4 = now();
+  if (trace)
+    fprintf(stderr, "[agpc] score_batch host phases (ms): staging %.3f  h2d %.3f  device %.3f  d2h+sync %.3f\n",
+            ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4));
   if (rc) return rc;
   if (e != cudaSuccess) return fail(ctx, AGPC_E_CUDA, "score_batch host copies", e);
   return AGPC_OK;

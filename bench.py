@@ -330,6 +330,10 @@ def main():
     e1.record()
     barrier()
     t_wall1 = time.time()
+    clocks = None
+    if sampler is not None:   # the samples of the timed region are in; stop nvidia-smi before the host-path leg
+        clocks = sampler.window(t_wall0, t_wall1)
+        sampler.stop()
     ms = e0.elapsed_time(e1)
     launches = eng.launches - launches0
     prof = eng.profile_read()
@@ -396,10 +400,6 @@ def main():
     e2e_value = n_cands_total * e2e_steps / e2e_s
     same = bool(np.allclose(r["nlml"], nlml_d.cpu().numpy(), rtol=1e-9, atol=0, equal_nan=True))
 
-    clocks = None
-    if sampler is not None:
-        clocks = sampler.window(t_wall0, t_wall1)
-        sampler.stop()
 
     if rank == 0:
         g = prof["gemm"]

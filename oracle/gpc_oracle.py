@@ -266,6 +266,7 @@ class EPResult:
     sweeps: int
     converged: bool
     jitter: float = 0.0
+    kept: bool = False      # parallel EP only: converged without a final update (posterior reuse)
 
 
 def ep_sequential(K, y, eps=1e-6, max_sweeps=100, rng: Optional[np.random.Generator] = None, eta=1.0, delta=1.0):
@@ -320,13 +321,14 @@ def ep_parallel(K, y, eps=1e-6, max_sweeps=100, damping=1.0, tau0=None, v0=None)
     Every sweep: (1) posterior marginals diag(Sigma), mu from the *current* sites (no factorisation needed while
     all tau~ are 0: Sigma = K, mu = 0); (2) all n cavity / moment-match / site updates from those marginals,
     new = old + damping * delta.  Convergence as in GPy: mean(d tau^2) <= eps and mean(d v^2) <= eps, tested from
-    the second sweep on.  Returns the sites *after* the last update (the caller recomputes the posterior).
+    the second sweep on.  Returns the sites *after* the last update (the caller recomputes the posterior), or -- when
+    the residual at the current sites is already ``EP_REUSE_FACTOR`` below the tolerance -- the current sites untouched.
     """
     ypm = labels_pm1(y)
     n = K.shape[0]
     tau_t = np.zeros(n) if tau0 is None else np.array(tau0, float)
     v_t = np.zeros(n) if v0 is None else np.array(v0, float)
-    it, converged, jit_used = 0, False, 0.0
+    it, converged, jit_used, kept = 0, False, 0.0, False
     # GPy measures the change between two sweeps (so >= 2 sweeps); the residual is an absolute fixed-point error, so
     # warm-started sites that are already converged may stop after one sweep
     min_sweeps = 2 if tau0 is None else 1
@@ -342,17 +344,26 @@ def ep_parallel(K, y, eps=1e-6, max_sweeps=100, damping=1.0, tau0=None, v0=None)
         d = ep_damping(damping, it + 1)
         new_tau = np.maximum(tau_t + d * f_tau, floor)
         r_tau = np.maximum(tau_t + f_tau, floor) - tau_t
-        tau_t, v_t = new_tau, v_t + d * f_v
         it += 1
         # convergence is judged on the undamped residual, so damping never loosens the stopping rule
         # (identical to GPy's test for damping = 1)
-        if it >= min_sweeps and np.mean(r_tau * r_tau) <= eps and np.mean(f_v * f_v) <= eps:
+        res_tau, res_v = np.mean(r_tau * r_tau), np.mean(f_v * f_v)
+        if it >= min_sweeps and res_tau <= eps and res_v <= eps:
             converged = True
+            # posterior reuse (engine: ep.cu EP_REUSE_FACTOR): the residual belongs to the CURRENT sites; when it is
+            # already 10x below the tolerance they are kept as the final sites, so the factorisation just computed is
+            # the final one.  Otherwise the update is applied as in GPy and the caller re-factorises.
+            if res_tau <= EP_REUSE_FACTOR * eps and res_v <= EP_REUSE_FACTOR * eps:
+                kept = True
+                break
+            tau_t, v_t = new_tau, v_t + d * f_v
             break
-    return EPResult(tau_t, v_t, it, converged, jit_used)
+        tau_t, v_t = new_tau, v_t + d * f_v
+    return EPResult(tau_t, v_t, it, converged, jit_used, kept)
 
 
 EP_AUTO_FREE_SWEEPS, EP_AUTO_DAMPING = 3, 0.8
+EP_REUSE_FACTOR = 0.1
 
 
 def ep_damping(damping, sweep: int) -> float:

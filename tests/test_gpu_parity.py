@@ -718,3 +718,61 @@ def test_baseline_config0_single_se_ard_n500(engine):
     ref = orc.optimize(prog, th0, X, y, tr, damping=0.0)
     assert nl1 == pytest.approx(ref["nlml"], rel=1e-6)       # both optimisers stop at the same optimum
     assert np.allclose(th1, ref["theta"], rtol=1e-4)
+
+
+def test_wide_inputs_odd_dimension_count(engine):
+    """D = 33 input columns (odd, wider than a warp; the X panels of a tile are staged per dimension): kernels on the
+    first, a middle and the last column, with and without materialised dK."""
+    rng = np.random.default_rng(77)
+    N, D = 333, 33
+    X = rng.uniform(-3, 3, (N, D))
+    y = (np.sin(X[:, 0]) + 0.5 * X[:, 16] * X[:, 32] + 0.3 * rng.standard_normal(N) > 0).astype(float)
+    prog = orc.KernelProgram.from_tree(("+", ("*", ("SE", 0), ("PER", 16)), ("LIN", 32), ("SE", 32)))
+    th = random_theta(prog, rng)
+    did = engine.dataset(X, y)
+    rows = [np.arange(N, dtype=np.int32), np.arange(5, 300, dtype=np.int32)]
+    g = engine.score_batch(did, [to_engine_program(prog)] * 2, [th, th * 1.1], rows, damping=0.0)
+    engine.dataset_free(did)
+    for b, t in enumerate((th, th * 1.1)):
+        o = orc.score(prog, t, X[rows[b]], y[rows[b]], damping=0.0)
+        assert g["status"][b] == o["status"] == 0 and g["sweeps"][b] == o["sweeps"]
+        assert abs(g["nlml"][b] - o["nlml"]) <= 1e-9 * abs(o["nlml"])
+        scale = np.maximum(np.abs(o["grad"]), 1e-3 * np.abs(o["grad"]).max())
+        assert np.all(np.abs(g["grad"][b, :prog.n_theta] - o["grad"]) <= 1e-6 * scale)
+
+
+def test_posterior_reuse_keeps_converged_sites(engine):
+    """EP posterior reuse (ep.cu EP_REUSE_FACTOR / oracle.ep_parallel): warm-started at the fixed point the residual at
+    the supplied sites is far below the tolerance, so the evaluation stops after one sweep, returns the sites bit-for-bit
+    and skips the final re-factorisation -- and still reports the same NLML / gradient as a re-factorised evaluation
+    (frozen sites) at those sites.  A batch mixes such an item with one that has to iterate."""
+    X, y = synth(300, 3, 12)
+    prog = orc.KernelProgram.from_tree(TREES["se0xse1"])
+    ep = to_engine_program(prog)
+    th = np.array([1.4, 0.8, 0.9, 1.1])
+    rows = [np.arange(300, dtype=np.int32)]
+    did = engine.dataset(X, y)
+    tight = engine.score_batch(did, [ep], [th], rows, epsilon=1e-18, max_sweeps=300, damping=0.0)
+    l0 = engine.launches
+    again = engine.score_batch(did, [ep], [th], rows, tau=tight["tau"], nu=tight["nu"], damping=0.0)
+    l_reuse = engine.launches - l0
+    l0 = engine.launches
+    frozen = engine.score_batch(did, [ep], [th], rows, tau=tight["tau"], nu=tight["nu"], frozen_sites=True)
+    l_frozen = engine.launches - l0
+    assert again["status"][0] == 0 and again["sweeps"][0] == 1
+    assert np.array_equal(again["tau"][0], tight["tau"][0]) and np.array_equal(again["nu"][0], tight["nu"][0])
+    assert abs(again["nlml"][0] - frozen["nlml"][0]) <= 1e-12 * abs(frozen["nlml"][0])
+    assert np.allclose(again["grad"][0, :4], frozen["grad"][0, :4], rtol=1e-10, atol=1e-12)
+    assert l_reuse <= l_frozen + 8          # one factorisation in either call: the converged sweep's is the final one
+    o = orc.score(prog, th, X, y, damping=0.0, tau0=tight["tau"][0], v0=tight["nu"][0])
+    assert o["sweeps"] == 1 and np.array_equal(o["tau"], tight["tau"][0])
+    assert abs(again["nlml"][0] - o["nlml"]) <= 1e-10 * abs(o["nlml"])
+    # mixed batch: item 0 reuses, item 1 (different theta, same warm sites) must iterate and re-factorise
+    mixed = engine.score_batch(did, [ep, ep], [th, th * 1.3], rows * 2, tau=[tight["tau"][0]] * 2, nu=[tight["nu"][0]] * 2,
+                               damping=0.0)
+    engine.dataset_free(did)
+    assert mixed["sweeps"][0] == 1 and mixed["sweeps"][1] > 1
+    assert np.array_equal(mixed["tau"][0], tight["tau"][0])
+    o1 = orc.score(prog, th * 1.3, X, y, damping=0.0, tau0=tight["tau"][0], v0=tight["nu"][0])
+    assert mixed["sweeps"][1] == o1["sweeps"] and abs(mixed["nlml"][1] - o1["nlml"]) <= 1e-9 * abs(o1["nlml"])
+    assert abs(mixed["nlml"][0] - again["nlml"][0]) <= 1e-12 * abs(again["nlml"][0])

@@ -182,3 +182,21 @@ def test_probit_derivatives_fd():
         assert np.allclose((lpp - lpm) / (2 * h), d1, rtol=1e-7, atol=1e-9)
         assert np.allclose((d1p - d1m) / (2 * h), -W, rtol=1e-7, atol=1e-9)
         assert np.allclose(-(Wp - Wm) / (2 * h), d3, rtol=1e-6, atol=1e-8)
+
+
+def test_parallel_ep_posterior_reuse_rule():
+    """oracle.ep_parallel: sites whose residual is already EP_REUSE_FACTOR below the tolerance are returned untouched
+    (kept = True, the factorisation at those sites is final); otherwise the converged update is applied as in GPy."""
+    X, y = synth(150, 2, 3)
+    prog = orc.KernelProgram.from_tree(TREES["se0xse1"])
+    K = orc.kern_K(prog, np.array([1.2, 0.9, 1.0, 1.1]), X)
+    tight = orc.ep_parallel(K, y, eps=1e-20, max_sweeps=400, damping=0.0)
+    r = orc.ep_parallel(K, y, eps=1e-6, damping=0.0, tau0=tight.tau_t, v0=tight.v_t)
+    assert r.converged and r.kept and r.sweeps == 1
+    assert np.array_equal(r.tau_t, tight.tau_t) and np.array_equal(r.v_t, tight.v_t)
+    cold = orc.ep_parallel(K, y, eps=1e-6, damping=0.0)
+    assert cold.converged and cold.sweeps >= 2
+    # either way the returned sites satisfy the tolerance, and the log marginal agrees with the fixed point to 1e-8
+    lt = orc.ep_log_marginal(K, y, tight.tau_t, tight.v_t)["log_z"]
+    lc = orc.ep_log_marginal(K, y, cold.tau_t, cold.v_t)["log_z"]
+    assert abs(lc - lt) <= 1e-8 * abs(lt)
