@@ -228,7 +228,8 @@ def compile_program(kern: Kern) -> _eng.Program:
         if isinstance(k, Prod):
             acc = [[]]
             for p in k.parts:
-                acc = [a + t for a in acc for t in walk(p)]
+                tp = walk(p)            # once per factor: walking registers the factor's leaves
+                acc = [a + t for a in acc for t in tp]
             return acc
         idx = len(leaf_type)
         leaf_type.append(k.leaf_type)

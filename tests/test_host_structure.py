@@ -161,3 +161,27 @@ def test_param_transforms_roundtrip_and_gradfactor():
     assert q.from_x(q.to_x()) == pytest.approx(2.0)
     fd = (q.from_x(q.to_x() + h) - q.from_x(q.to_x() - h)) / (2 * h)
     assert q.gradfactor() == pytest.approx(fd, rel=1e-6)
+
+
+def test_compile_program_product_of_sums_registers_each_leaf_once():
+    """(SE0 + SE1) * (SE2 + SE3): distribution gives 4 terms over the SAME 4 leaves (8 theta slots = GPy's param_array);
+    K from the flat program equals the product of the two sums."""
+    import numpy as np
+    from autogpc_b200 import gpy_compat as GPy
+    from oracle import gpc_oracle as orc
+    mk = lambda d, v, l: GPy.kern.RBF(1, variance=v, lengthscale=l, active_dims=np.array([d]))
+    k = (mk(0, 1.1, 0.9) + mk(1, 0.7, 1.3)) * (mk(2, 1.5, 0.8) + mk(3, 0.6, 2.0))
+    prog = GPy.compile_program(k)
+    assert prog.n_leaves == 4 and prog.n_theta == 8 == len(k.param_array) and prog.n_terms == 4
+    terms = sorted(tuple(prog.term_leaf[t][:prog.term_len[t]]) for t in range(prog.n_terms))
+    assert terms == [(0, 2), (0, 3), (1, 2), (1, 3)]
+    # three factors, the middle one a sum: still one registration per leaf
+    k3 = mk(0, 1.0, 1.0) * (mk(1, 1.0, 1.0) + mk(2, 1.0, 1.0)) * (mk(3, 1.0, 1.0) + GPy.kern.Bias(1, variance=0.5))
+    p3 = GPy.compile_program(k3)
+    assert p3.n_leaves == 5 and p3.n_theta == len(k3.param_array) == 9 and p3.n_terms == 4
+    X = np.random.default_rng(0).uniform(-2, 2, (30, 4))
+    oprog = orc.KernelProgram([prog.leaf_type[i] for i in range(4)], [prog.leaf_dim[i] for i in range(4)],
+                              [prog.leaf_off[i] for i in range(4)], [list(t) for t in terms], 8)
+    se = lambda d, v, l: v * np.exp(-0.5 * (X[:, d][:, None] - X[:, d][None, :]) ** 2 / l ** 2)
+    dense = (se(0, 1.1, 0.9) + se(1, 0.7, 1.3)) * (se(2, 1.5, 0.8) + se(3, 0.6, 2.0))
+    assert np.allclose(orc.kern_K(oprog, k.param_array, X), dense, rtol=1e-12)
