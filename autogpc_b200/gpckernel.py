@@ -16,6 +16,7 @@ Differences, all called for by SURVEY 7 / BASELINE north_star:
 from __future__ import annotations
 
 import sys
+import warnings
 from typing import List, Optional
 
 import numpy as np
@@ -24,6 +25,7 @@ from . import flexible_function as ff
 from . import gpy_compat as GPy
 from . import grammar
 from . import optim
+from .engine import EngineError as _EngineError
 from .gpcdata import GPCData
 
 _rng = np.random.default_rng(0)
@@ -238,10 +240,21 @@ def train_kernels(kernels: List[GPCKernel], mode="auto", n_folds=5, max_evals=10
     randomise = n_folds is not None
     nf = 1 if n_folds is None else n_folds
     items = []  # (kernel index, fold index, model)
+    over_limit = set()
     for ci, gk in enumerate(kernels):
         gk.isSparse = False
         folds = gk.data.kFoldIndices(k=nf)
         did = device_dataset(gk.data)
+        try:
+            GPy.compile_program(gpss2gpy(gk.kernel, data=gk.data))
+        except _EngineError as e:
+            # a structure beyond the engine's program limits (16 leaves / 16 product terms / 48 hyper-parameters after
+            # distributing products over sums) cannot be scored: it ranks last (error = BIC = inf) instead of aborting
+            # the search.  GPy has no such limit; the reference's grammar reaches it only beyond depth ~5.
+            warnings.warn("candidate %s skipped: %s" % (gk.kernel, e))
+            over_limit.add(ci)
+            gk.model, gk.errorRate = None, None
+            continue
         for fi, (tr, te) in enumerate(folds):
             k = gk.kernel.copy()
             if randomise:
@@ -286,6 +299,8 @@ def train_kernels(kernels: List[GPCKernel], mode="auto", n_folds=5, max_evals=10
         sharding.exchange_models(items, mine, errs, shard)
 
     for ci, gk in enumerate(kernels):
+        if ci in over_limit:
+            continue
         results = [{"model": items[i][2], "error": errs[i]} for i in range(len(items))
                    if items[i][0] == ci and np.isfinite(errs.get(i, float("nan")))]
         if not results:

@@ -185,3 +185,69 @@ def test_compile_program_product_of_sums_registers_each_leaf_once():
     se = lambda d, v, l: v * np.exp(-0.5 * (X[:, d][:, None] - X[:, d][None, :]) ** 2 / l ** 2)
     dense = (se(0, 1.1, 0.9) + se(1, 0.7, 1.3)) * (se(2, 1.5, 0.8) + se(3, 0.6, 2.0))
     assert np.allclose(orc.kern_K(oprog, k.param_array, X), dense, rtol=1e-12)
+
+
+def _dense_K(k, X):
+    """Direct recursive evaluation of the GPy-shaped tree (GPy kern.K semantics), independent of compile_program."""
+    import numpy as np
+    from autogpc_b200 import gpy_compat as GPy
+    if isinstance(k, GPy.kern.Add):
+        return sum(_dense_K(p, X) for p in k.parts)
+    if isinstance(k, GPy.kern.Prod):
+        out = np.ones((X.shape[0], X.shape[0]))
+        for p in k.parts:
+            out = out * _dense_K(p, X)
+        return out
+    v = float(k.variance)
+    if isinstance(k, GPy.kern.Bias):
+        return np.full((X.shape[0], X.shape[0]), v)
+    x = X[:, int(k.active_dims[0])]
+    r = x[:, None] - x[None, :]
+    if isinstance(k, GPy.kern.RBF):
+        return v * np.exp(-0.5 * r ** 2 / float(k.lengthscale) ** 2)
+    if isinstance(k, GPy.kern.StdPeriodic):
+        return v * np.exp(-0.5 * np.sin(np.pi * r / float(k.period)) ** 2 / float(k.lengthscale) ** 2)
+    c = float(k.location)
+    return v * (x[:, None] - c) * (x[None, :] - c)
+
+
+def test_compile_program_matches_tree_on_grammar_candidates():
+    """Every structure the grammar produces to depth 3 (SE / Lin / Per bases, a sample of each level): the flat program
+    has GPy's theta count and leaf count, and K evaluated from the program equals K evaluated from the tree."""
+    import numpy as np
+    from autogpc_b200 import flexible_function as ff, gpckernel as gk, gpy_compat as GPy
+    from autogpc_b200.gpcdata import GPCData
+    from oracle import gpc_oracle as orc
+    rng = np.random.default_rng(5)
+    X = rng.uniform(-2, 2, (40, 3))
+    y = (X[:, 0] > 0).astype(float).reshape(-1, 1)
+    d = GPCData(X, y)
+    gk.set_rng(1)
+    level = [gk.GPCKernel(ff.NoneKernel(), d, depth=0)]
+    checked, seen = 0, set()
+    for depth in range(3):
+        nxt = []
+        for parent in level:
+            for c in parent.expand(base_kernels="SE,Lin,Per"):
+                name = c.kernel.structure() if hasattr(c.kernel, "structure") else str(c.kernel)
+                if name in seen:
+                    continue
+                seen.add(name)
+                nxt.append(c)
+        pick = [nxt[i] for i in rng.permutation(len(nxt))[:60]]
+        for c in pick:
+            kcopy = c.kernel.copy()
+            gk.resetGpssParams(kcopy, data=d)
+            kern = gk.gpss2gpy(kcopy, data=d)
+            prog = GPy.compile_program(kern)
+            assert prog.n_theta == len(kern.param_array), name
+            assert prog.n_leaves == len(kern.leaves()), name
+            oprog = orc.KernelProgram([prog.leaf_type[i] for i in range(prog.n_leaves)],
+                                      [prog.leaf_dim[i] for i in range(prog.n_leaves)],
+                                      [prog.leaf_off[i] for i in range(prog.n_leaves)], prog.terms(), prog.n_theta)
+            Kp = orc.kern_K(oprog, kern.param_array, X)
+            Kt = _dense_K(kern, X)
+            assert np.allclose(Kp, Kt, rtol=1e-11, atol=1e-13), name
+            checked += 1
+        level = pick[:8]
+    assert checked >= 100

@@ -137,3 +137,18 @@ def test_experiment_shim_runs_search_and_baseline(fake):
     assert out["data"].getDim() == 4 and out["data"].getNum() == 60        # dims=(1,5,6,7) as in the reference
     assert len(out["best"]) == 2 and out["best"][1].kernel.structure().startswith("SE")
     assert isinstance(out["baseline"].kernel, ff.ConstKernel) and out["seconds"] > 0
+
+
+def test_candidate_beyond_program_limits_ranks_last_instead_of_aborting(fake):
+    """(SE0+SE1)*(SE0+SE1)*(SE0+SE1)*(SE0+SE1)*(SE0+SE1) distributes to 32 product terms (engine limit 16): the candidate
+    is skipped with a warning and scores inf; the other candidate of the same call trains normally."""
+    gpckernel.set_rng(2)
+    X, y = synth(60, 2, 1)
+    d = GPCData(X, y.reshape(-1, 1))
+    s2 = lambda: ff.SumKernel([ff.SqExpKernel(0, 1.0, 1.0), ff.SqExpKernel(1, 1.0, 1.0)])
+    big = gpckernel.GPCKernel(ff.ProductKernel([s2() for _ in range(5)]), d, depth=5)
+    ok = gpckernel.GPCKernel(ff.SqExpKernel(0, 1.0, 1.0), d, depth=1)
+    with pytest.warns(UserWarning, match="skipped"):
+        gpckernel.train_kernels([big, ok], mode="full", n_folds=2, max_evals=15)
+    assert big.model is None and big.error() == float("inf") and big.bic() == float("inf")
+    assert ok.model is not None and np.isfinite(ok.error()) and np.isfinite(ok.bic())
