@@ -83,6 +83,22 @@ class GPCKernel:
         ret.model = self._untrained_model(k)
         return ret
 
+    def add_many(self, others):
+        """``[self.add(o) for o in others]`` with every un-optimised full-data inference in ONE engine batch and every
+        training-error prediction in one ``predict_batch`` (the loop of gpcreport.py:672-674 asks for exactly this)."""
+        rets = []
+        did = device_dataset(self.data)
+        rows = np.arange(self.data.getNum(), dtype=np.int32)
+        for o in others:
+            k = self.kernel + o.kernel
+            ret = GPCKernel(k, self.data)
+            ret.isSparse = False
+            ret.model = GPy.models.GPClassification(self.data.X, self.data.Y, kernel=gpss2gpy(k, data=self.data),
+                                                    _dataset=did, _rows=rows, _infer=False)
+            rets.append(ret)
+        infer_models_with_errors(rets)
+        return rets
+
     def expand(self, base_kernels="SE"):
         """All single-production rewrites, canonical + simplified + de-duplicated (gpckernel.py:131-147)."""
         ndim = self.data.getDim()
@@ -224,6 +240,51 @@ def _error_on_rows(model, data: GPCData, test_rows) -> float:
     p = model.predict_rows(test_rows)
     y = data.Y[np.asarray(test_rows), 0]
     return float(np.mean((p - 0.5) * (y - 0.5) < 0))
+
+
+def infer_models_with_errors(kernels: List[GPCKernel]) -> None:
+    """One EP inference (no optimisation, no gradient) for the models of ``kernels`` in a single ``score_batch`` and
+    their training-set error rates (``computeError(model, data.X, data.Y)``, gpckernel.py:393-407) in a single
+    ``predict_batch``; fills ``model`` state and ``errorRate``.  Models must share one device dataset."""
+    ms_ = [k.model for k in kernels]
+    if not ms_:
+        return
+    eng, did = ms_[0].engine, ms_[0]._dataset
+    r = eng.score_batch(did, [m._program for m in ms_], [m.kern.param_array for m in ms_], [m._rows for m in ms_],
+                        want_grad=False, **ms_[0].ep)
+    for b, m in enumerate(ms_):
+        m._absorb(r, b)
+    ok = [i for i, m in enumerate(ms_) if m.status not in (2, 4) and np.isfinite(m._nlml)]
+    if ok:
+        p, _ = eng.predict_batch(did, [ms_[i]._program for i in ok], [ms_[i].kern.param_array for i in ok],
+                                 [ms_[i]._rows for i in ok], [ms_[i]._tau for i in ok], [ms_[i]._nu for i in ok],
+                                 [ms_[i]._rows for i in ok])
+        for i, pi in zip(ok, p):
+            y = kernels[i].data.Y[ms_[i]._rows, 0]
+            kernels[i].errorRate = float(np.mean((pi - 0.5) * (y - 0.5) < 0))
+    for i, k in enumerate(kernels):
+        if i not in ok:
+            k.errorRate = float("inf")
+
+
+def cumulateAdditiveKernels(summands: List[GPCKernel]):
+    """Incrementally cumulate the additive components of a kernel, best (lowest training error) first
+    (gpcreport.py:657-680; the report layer itself is out of scope, this is its one caller of the scoring engine).
+    Returns ``(kers, cums)`` like the reference.  Each round scores ``cum + k`` for every remaining ``k`` in one batch
+    instead of one GPy model per candidate; ordering and tie-breaking follow the reference's stable sorts."""
+    terms = sorted(summands, key=lambda k: k.error(), reverse=True)
+    ker = terms.pop()
+    cum = ker
+    kers, cums = [ker], [cum]
+    while len(terms) > 0:
+        added = cum.add_many(terms)
+        order = sorted(range(len(terms)), key=lambda i: added[i].error(), reverse=True)
+        terms = [terms[i] for i in order]
+        ker = terms.pop()
+        cum = cum.add(ker)   # as in the reference: the winner is added again (its GPCKernel re-draws the parameters)
+        kers.append(ker)
+        cums.append(cum)
+    return kers, cums
 
 
 def train_kernels(kernels: List[GPCKernel], mode="auto", n_folds=5, max_evals=1000, shard=None):

@@ -776,3 +776,29 @@ def test_posterior_reuse_keeps_converged_sites(engine):
     o1 = orc.score(prog, th * 1.3, X, y, damping=0.0, tau0=tight["tau"][0], v0=tight["nu"][0])
     assert mixed["sweeps"][1] == o1["sweeps"] and abs(mixed["nlml"][1] - o1["nlml"]) <= 1e-9 * abs(o1["nlml"])
     assert abs(mixed["nlml"][0] - again["nlml"][0]) <= 1e-12 * abs(again["nlml"][0])
+
+
+def test_cumulate_additive_kernels_on_engine_matches_oracle_backed_run(engine):
+    """Second caller of the engine (gpcreport.py:657-680): un-optimised full-data inferences of cum + k for
+    all remaining components in one batch (no gradient), training errors by one predict_batch -- same component order,
+    errors and NLMLs as the identical host code running on the oracle-backed stand-in engine."""
+    from autogpc_b200 import engine as eng_mod, flexible_function as ff, gpckernel
+    from autogpc_b200.gpcdata import GPCData
+    from tests.fake_engine import OracleEngine
+    X, y = synth(220, 3, 6)
+    out = []
+    for e in (engine, OracleEngine()):
+        eng_mod.set_default_engine(e)
+        try:
+            gpckernel.set_rng(4)
+            d = GPCData(X, y.reshape(-1, 1))
+            parent = gpckernel.GPCKernel(ff.SumKernel([ff.SqExpKernel(0, 1.0, 1.2), ff.SqExpKernel(1, 1.5, 0.7),
+                                                       ff.ProductKernel([ff.SqExpKernel(2, 0.8, 1.0),
+                                                                         ff.SqExpKernel(0, 1.0, 2.0)])]), d, depth=3)
+            kers, cums = gpckernel.cumulateAdditiveKernels(parent.toSummands())
+            out.append(([k.kernel.structure() for k in kers], [c.kernel.structure() for c in cums],
+                        [c.error() for c in cums], [c.getNLML() for c in cums]))
+        finally:
+            eng_mod.set_default_engine(None)
+    assert out[0][0] == out[1][0] and out[0][1] == out[1][1]
+    assert np.allclose(out[0][2], out[1][2]) and np.allclose(out[0][3], out[1][3], rtol=1e-8)

@@ -152,3 +152,37 @@ def test_candidate_beyond_program_limits_ranks_last_instead_of_aborting(fake):
         gpckernel.train_kernels([big, ok], mode="full", n_folds=2, max_evals=15)
     assert big.model is None and big.error() == float("inf") and big.bic() == float("inf")
     assert ok.model is not None and np.isfinite(ok.error()) and np.isfinite(ok.bic())
+
+
+def test_cumulate_additive_kernels_matches_the_serial_reference_loop(fake):
+    """gpcreport.py:657-680 transcribed with one ``add`` (one model) per candidate, against the batched version."""
+    gpckernel.set_rng(4)
+    X, y = synth(90, 3, 6)
+    d = GPCData(X, y.reshape(-1, 1))
+    parent = gpckernel.GPCKernel(ff.SumKernel([ff.SqExpKernel(0, 1.0, 1.2), ff.SqExpKernel(1, 1.5, 0.7),
+                                               ff.ProductKernel([ff.SqExpKernel(2, 0.8, 1.0), ff.SqExpKernel(0, 1.0, 2.0)])]),
+                                 d, depth=3)
+    summands = parent.toSummands()
+    assert len(summands) == 3
+
+    def serial(summands):
+        terms = sorted(summands, key=lambda k: k.error(), reverse=True)
+        ker = terms.pop()
+        cum = ker
+        kers, cums = [ker], [cum]
+        while len(terms) > 0:
+            terms = sorted(terms, key=lambda k: cum.add(k).error(), reverse=True)
+            ker = terms.pop()
+            cum = cum.add(ker)
+            kers.append(ker)
+            cums.append(cum)
+        return kers, cums
+
+    gpckernel.set_rng(11)      # GPCKernel.__init__ re-draws hyper-parameters: same stream for both versions
+    k1, c1 = serial(list(summands))
+    gpckernel.set_rng(11)
+    k2, c2 = gpckernel.cumulateAdditiveKernels(list(summands))
+    assert [k.kernel.structure() for k in k1] == [k.kernel.structure() for k in k2]
+    assert [c.kernel.structure() for c in c1] == [c.kernel.structure() for c in c2]
+    assert np.allclose([c.error() for c in c1], [c.error() for c in c2])
+    assert np.allclose([c.getNLML() for c in c1], [c.getNLML() for c in c2], rtol=1e-9)
