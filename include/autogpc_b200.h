@@ -13,6 +13,11 @@
  * pointers are ordinary host memory.  `stream` is a cudaStream_t passed as void*; NULL means the CONTEXT'S OWN stream,
  * which is non-blocking: it is not ordered with the legacy default stream, so a caller that prepared device buffers on
  * another stream must either pass that stream or synchronise before the call (and after it, before reading results).
+ *
+ * Memory: the context owns a workspace arena (grown on demand up to agpc_set_workspace_limit), a grow-only staging
+ * buffer for the host-buffer entry points and a small pool of destroyed datasets' buffers, so the steady-state path
+ * performs no cudaMalloc / cudaFree.  Environment: AGPC_TIMING=1 prints the host-phase wall times of every
+ * agpc_score_batch call on stderr (staging, H2D, device call, D2H + sync).
  */
 #ifndef AUTOGPC_B200_H
 #define AUTOGPC_B200_H
