@@ -65,11 +65,27 @@ def build_workload(world: int, cands_per_gpu: int, n_points: int = N_POINTS):
     root = gk.GPCKernel(ff.NoneKernel(), data, depth=0)
     depth1 = root.expand(base_kernels="SE,Lin,Per")
     depth2 = [k for k in depth1[0].expand(base_kernels="SE,Lin,Per") if len(k.getActiveDims()) > 1]
-    pool = depth1 + depth2
     need = cands_per_gpu * world
-    while len(pool) < need:  # only for very large worlds: further depth-2 expansions
-        pool += [k for k in depth1[len(pool) % len(depth1)].expand(base_kernels="SE,Lin,Per") if len(k.getActiveDims()) > 1]
-    cands = pool[:need]
+    nxt = 1
+    while len(depth2) < need:  # large worlds: depth-2 expansions of further depth-1 members
+        depth2 += [k for k in depth1[nxt % len(depth1)].expand(base_kernels="SE,Lin,Per") if len(k.getActiveDims()) > 1]
+        nxt += 1
+    # Stratified candidate list: every block of 8 holds 3 depth-1 and 5 depth-2 structures (a search to depth 3 scores
+    # 24 / 42 / 72 candidates per level, i.e. mostly composite ones), so that any prefix -- 8 candidates on one GPU, 64 on
+    # eight -- is the same mixture and the per-GPU work stays fixed as the world grows (weak scaling).  (The first
+    # version took depth-1 candidates first: one GPU then scored only the cheap single-leaf kernels and eight GPUs a
+    # heavier mix, which showed up as a 19 % "scaling loss" although no rank ever waits on another.)
+    prng = np.random.default_rng(0)   # fixed shuffle: the expansions come grouped by base kernel (SE.., Lin.., Per..)
+    depth1 = [depth1[i] for i in prng.permutation(len(depth1))]
+    depth2 = [depth2[i] for i in prng.permutation(len(depth2))]
+    cands, i1, i2 = [], 0, 0
+    while len(cands) < need:
+        if len(cands) % 8 in (0, 3, 6):
+            cands.append(depth1[i1 % len(depth1)])
+            i1 += 1
+        else:
+            cands.append(depth2[i2])
+            i2 += 1
     folds = data.kFoldIndices(N_FOLDS)
     items = []
     for ci, c in enumerate(cands):
