@@ -6,9 +6,10 @@
                                                              # GPy path -- GPy itself cannot be installed)
 
 Workload (weak scaling, synthetic): N = 8000 points, D = 8, 5 folds (n = 6400 training points per model).  The
-candidate pool is what gpcsearch generates with SE/LIN/PER bases: the depth-1 expansion followed by the depth-2
-expansion of its first member; every rank owns `--cands` candidates x 5 folds = 40 items by default (round-robin
-by global item id, autogpc_b200/sharding.py).  One STEP = every item of the rank taken through one full cold-start
+candidate pool is what gpcsearch generates with SE/LIN/PER bases: the depth-1 expansion and depth-2 expansions of its
+members, stratified 3 : 5 per block of 8 candidates (fixed-seed shuffle) so that every world size scores the same
+mixture; every rank owns `--cands` candidates x 5 folds = 40 items by default (round-robin by global item id,
+autogpc_b200/sharding.py).  One STEP = every item of the rank taken through one full cold-start
 evaluation -- K build, parallel EP to epsilon = 1e-6, blocked FP64 Cholesky / triangular inverse per sweep, log Z_EP,
 gradient, BIC -- followed (N > 1) by the NCCL all-gather of the (score, theta) records.  A candidate counts as scored
 when its 5 fold models have been evaluated: value = candidates / s over all ranks.
