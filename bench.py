@@ -334,10 +334,13 @@ def main():
     peak_burst, peak_sustained = (0.0, 0.0) if args.kernels_only else measure_dgemm_peak(torch)
     sampler = ClockSampler(local_rank) if rank == 0 else None
 
+    # per-launch event profiling is on during warm-up as well: the engine creates its event pairs on first use, and
+    # those cudaEventCreate calls (2 per launch, ~7.7 k per step) belong to warm-up, not to the timed region
+    eng.profile_enable(True)
     for _ in range(args.warmup):
         step_device()
     barrier()
-    eng.profile_enable(True)
+    eng.profile_enable(True)   # resets the counters and re-uses the pool
     launches0 = eng.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
