@@ -142,6 +142,10 @@ def optimize_models(models, max_evals: int = 1000, warm_start: bool = True):
     engine = models[0].engine
     fails = [0] * len(models)
     evals = [0] * len(models)
+    # L-BFGS-B returns an iterate it has already evaluated: the last few successful evaluations of every model are kept
+    # (keyed by the bytes of x) so that leaving the model "at its optimum" does not cost one more engine evaluation
+    recent = [dict() for _ in models]
+    KEEP = 4
 
     def eval_batch(idx, xs):
         by_ds = {}
@@ -179,6 +183,11 @@ def optimize_models(models, max_evals: int = 1000, warm_start: bool = True):
                 mdl._absorb(r, b)
                 gf = np.array([p.gradfactor() for p in params[b]])
                 res[i] = (mdl._nlml, mdl._grad * gf)
+                rec = recent[i]
+                rec[np.asarray(x, dtype=np.float64).tobytes()] = (mdl._nlml, mdl._grad, mdl.bic, mdl.status,
+                                                                  mdl.ep_sweeps, mdl._tau, mdl._nu)
+                while len(rec) > KEEP:
+                    rec.pop(next(iter(rec)))
         return [res[i] for i in idx]
 
     x0s = [np.array([p.to_x() for p in mdl.kern.flat_params()]) for mdl in models]
@@ -193,7 +202,11 @@ def optimize_models(models, max_evals: int = 1000, warm_start: bool = True):
         ps = mdl.kern.flat_params()
         mdl.kern.set_param_array([p.from_x(float(v)) for p, v in zip(ps, x)])
         mdl.optimization_info = dict(info, evals=evals[i])
-        finals.append(mdl)
+        hit = recent[i].get(np.asarray(x, dtype=np.float64).tobytes())
+        if hit is not None:
+            mdl._nlml, mdl._grad, mdl.bic, mdl.status, mdl.ep_sweeps, mdl._tau, mdl._nu = hit
+        else:
+            finals.append(mdl)
     by_ds = {}
     for mdl in finals:
         by_ds.setdefault(mdl._dataset, []).append(mdl)

@@ -186,3 +186,27 @@ def test_cumulate_additive_kernels_matches_the_serial_reference_loop(fake):
     assert [c.kernel.structure() for c in c1] == [c.kernel.structure() for c in c2]
     assert np.allclose([c.error() for c in c1], [c.error() for c in c2])
     assert np.allclose([c.getNLML() for c in c1], [c.getNLML() for c in c2], rtol=1e-9)
+
+
+def test_optimum_is_taken_from_the_evaluation_cache(fake):
+    """L-BFGS-B returns an iterate it has evaluated: optimize_models restores that evaluation instead of scoring theta*
+    once more (engine items == objective evaluations), and the restored state is the model's state at theta*."""
+    X, y = synth(80, 2, 9)
+    d = GPCData(X, y.reshape(-1, 1))
+    did = gpckernel.device_dataset(d)
+    rows = np.arange(80, dtype=np.int32)
+    ms = []
+    for v in (1.0, 2.0, 0.5):
+        k = ff.ProductKernel([ff.SqExpKernel(0, v, 1.0), ff.SqExpKernel(1, 1.5, 0.8)])
+        ms.append(GPy.models.GPClassification(X, y.reshape(-1, 1), kernel=gpckernel.gpss2gpy(k, data=d), _dataset=did,
+                                              _rows=rows, _infer=False))
+    items0 = fake.items
+    optim.optimize_models(ms, max_evals=30)
+    assert fake.items - items0 == sum(m.optimization_info["evals"] for m in ms)
+    prog = orc.KernelProgram.from_tree(("*", ("SE", 0), ("SE", 1)))
+    for m in ms:
+        o = orc.score(prog, m.kern.param_array, X, y, damping=0.0)
+        # warm-started (cached) vs cold evaluation at GPy's epsilon = 1e-6: both within ~1e-6 of the tight fixed point
+        assert -m.log_likelihood() == pytest.approx(o["nlml"], rel=5e-6)
+        assert m.bic == pytest.approx(o["bic"], rel=5e-6)
+        assert m._tau.shape == (80,) and np.all(np.isfinite(m._grad))
