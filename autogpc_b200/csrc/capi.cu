@@ -220,7 +220,9 @@ int agpc_dataset_create(agpc_ctx* ctx, const double* X_host, const double* y_hos
 int agpc_dataset_destroy(agpc_ctx* ctx, int32_t id) {
   if (!ctx || id < 0 || id >= (int)ctx->datasets.size() || !ctx->datasets[id].X) return fail(ctx, AGPC_E_ARG, "bad dataset id");
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  // the buffers go to the pool instead of cudaFree: keep cudaFree's implicit device-wide synchronisation, so that work
+  // a caller queued on its own stream has finished reading the dataset before a later create re-uses the memory
+  cudaDeviceSynchronize();
   if (ctx->dataset_pool.size() >= 4) {
     cudaFree(ctx->dataset_pool.front().X);
     cudaFree(ctx->dataset_pool.front().y);
