@@ -140,6 +140,12 @@ class GPCKernel:
             cverror = computeError(m, XT, YT)
         return {"model": m, "error": cverror}
 
+    def trainSVGP(self, X, Y, XT=None, YT=None, randomise=False, inducing=10):
+        """Sparse variational GP branch (gpckernel.py:255-293): outside the hot path this engine covers (north_star
+        names full EP / Laplace inference only); present so that the call fails with an explanation."""
+        raise NotImplementedError("SVGP (gpckernel.py:255-293) is out of scope of the B200 scoring engine; "
+                                  "use train(mode='full') / trainFull")
+
     def toSummands(self):
         """Additive components, each with an un-optimised full-data model (gpckernel.py:296-324).  As in the
         reference, constructing the component ``GPCKernel`` re-draws its hyper-parameters (``__init__`` calls
