@@ -6,9 +6,9 @@
                                                              # GPy path -- GPy itself cannot be installed)
 
 Workload (weak scaling, synthetic): N = 8000 points, D = 8, 5 folds (n = 6400 training points per model).  The
-candidate pool is what gpcsearch generates with SE/LIN/PER bases: the depth-1 expansion and depth-2 expansions of its
-members, stratified 3 : 5 per block of 8 candidates (fixed-seed shuffle) so that every world size scores the same
-mixture; every rank owns `--cands` candidates x 5 folds = 40 items by default (round-robin by global item id,
+candidate pool is what gpcsearch generates with SE/LIN/PER bases (depth-1 and depth-2 expansions): one block of 8
+candidates, one per structure shape, and per additional GPU the same block with the input dimensions shifted -- distinct
+candidates, identical composition, fixed per-GPU work; every rank owns `--cands` candidates x 5 folds = 40 items by default (round-robin by global item id,
 autogpc_b200/sharding.py).  One STEP = every item of the rank taken through one full cold-start
 evaluation -- K build, parallel EP to epsilon = 1e-6, blocked FP64 Cholesky / triangular inverse per sweep, log Z_EP,
 gradient, BIC -- followed (N > 1) by the NCCL all-gather of the (score, theta) records.  A candidate counts as scored
@@ -66,27 +66,57 @@ def build_workload(world: int, cands_per_gpu: int, n_points: int = N_POINTS):
     root = gk.GPCKernel(ff.NoneKernel(), data, depth=0)
     depth1 = root.expand(base_kernels="SE,Lin,Per")
     depth2 = [k for k in depth1[0].expand(base_kernels="SE,Lin,Per") if len(k.getActiveDims()) > 1]
-    need = cands_per_gpu * world
-    nxt = 1
-    while len(depth2) < need:  # large worlds: depth-2 expansions of further depth-1 members
-        depth2 += [k for k in depth1[nxt % len(depth1)].expand(base_kernels="SE,Lin,Per") if len(k.getActiveDims()) > 1]
-        nxt += 1
-    # Stratified candidate list: every block of 8 holds 3 depth-1 and 5 depth-2 structures (a search to depth 3 scores
-    # 24 / 42 / 72 candidates per level, i.e. mostly composite ones), so that any prefix -- 8 candidates on one GPU, 64 on
-    # eight -- is the same mixture and the per-GPU work stays fixed as the world grows (weak scaling).  (The first
-    # version took depth-1 candidates first: one GPU then scored only the cheap single-leaf kernels and eight GPUs a
-    # heavier mix, which showed up as a 19 % "scaling loss" although no rank ever waits on another.)
-    prng = np.random.default_rng(0)   # fixed shuffle: the expansions come grouped by base kernel (SE.., Lin.., Per..)
-    depth1 = [depth1[i] for i in prng.permutation(len(depth1))]
-    depth2 = [depth2[i] for i in prng.permutation(len(depth2))]
-    cands, i1, i2 = [], 0, 0
-    while len(cands) < need:
-        if len(cands) % 8 in (0, 3, 6):
-            cands.append(depth1[i1 % len(depth1)])
-            i1 += 1
-        else:
-            cands.append(depth2[i2])
-            i2 += 1
+    # One BLOCK of `cands_per_gpu` candidates is a stratified sample of what a search to depth 3 scores (24 / 42 / 72
+    # candidates per level, i.e. mostly composite ones): 3 depth-1 and 5 depth-2 structures per 8, both strata shuffled
+    # with a fixed seed (the expansions come grouped by base kernel: SE.., Lin.., Per..).  The candidates of world rank
+    # block j > 0 are the SAME structures with every input dimension shifted by j (mod D): distinct candidates, identical
+    # structure-type composition, so the per-GPU work stays fixed as the world grows -- weak scaling.  (Earlier versions
+    # took "the next 8 candidates of the pool" per added GPU: the cost of a candidate depends on its structure type --
+    # EP sweeps 3 to 9 -- so one GPU happened to score a lighter sample than two or eight, which read as a 15-20 %
+    # scaling loss although no rank ever waits on another.)
+    prng = np.random.default_rng(0)
+    d1 = [depth1[i] for i in prng.permutation(len(depth1))]
+    d2 = [depth2[i] for i in prng.permutation(len(depth2))]
+    import re
+
+    def shape(c):   # structure with the dimensions removed: "Per", "SE*SE", "Lin+SE", ...
+        return re.sub(r"\d+", "", c.kernel.structure())
+
+    def shift_safe(c):   # a two-leaf kernel of one type on dimensions 4 apart maps onto itself under a shift by 4
+        dims = [int(x) for x in re.findall(r"\d+", c.kernel.structure())]
+        return len(dims) < 2 or (dims[0] - dims[1]) % N_DIM != N_DIM // 2
+
+    def pick(pool, n, taken):
+        out = []
+        while len(out) < n:   # one candidate per shape class per round, so that dimension shifts never collide
+            progress = False
+            for c in pool:
+                if len(out) < n and shape(c) not in taken and shift_safe(c):
+                    taken.add(shape(c))
+                    out.append(c)
+                    progress = True
+            if not progress:
+                taken.clear()
+        return out
+
+    n1 = sum(1 for i in range(cands_per_gpu) if i % 8 in (0, 3, 6))
+    p1, p2 = pick(d1, n1, set()), pick(d2, cands_per_gpu - n1, set())
+    block = [(p1.pop(0) if i % 8 in (0, 3, 6) else p2.pop(0)) for i in range(cands_per_gpu)]
+
+    def shifted(gk_kernel, j):
+        k = gk_kernel.kernel.copy()
+        stack = [k]
+        while stack:
+            node = stack.pop()
+            if getattr(node, "is_operator", False):
+                stack.extend(node.operands)
+            elif getattr(node, "dimension", None) is not None:
+                node.dimension = (node.dimension + j) % N_DIM
+        return gk.GPCKernel(k.canonical(), data, depth=gk_kernel.depth)
+
+    cands = []
+    for j in range(world):
+        cands += block if j % N_DIM == 0 and j == 0 else [shifted(c, j % N_DIM) for c in block]
     folds = data.kFoldIndices(N_FOLDS)
     items = []
     for ci, c in enumerate(cands):
