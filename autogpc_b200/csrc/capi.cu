@@ -2,6 +2,7 @@
 // The scoring pipeline itself is in score.cu.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <utility>
 #include <cstring>
 #include <new>
@@ -69,6 +70,10 @@ int agpc_create(int device, agpc_ctx** out) {
   if (!c) return AGPC_E_NOMEM;
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("AGPC_OZAKI")) {
+    const int v = atoi(e);
+    c->oz_S = (v == 6 || v == 7) ? v : 0;
+  }
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // the look-ahead (panel) stream outranks the bulk updates
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -250,6 +255,42 @@ int agpc_gemm_nt(agpc_ctx* ctx, const double* A, const double* B, double* C, int
   return AGPC_OK;
 }
 
+int agpc_gemm_nt_i8x(agpc_ctx* ctx, const double* A, const double* B, double* C, int32_t M, int32_t N, int32_t K,
+                     double alpha, double beta, int32_t batch, int32_t n_slices, void* stream) {
+  if (!ctx || !A || !B || !C || M <= 0 || N <= 0 || K <= 0 || batch <= 0 || M % TILE || N % TILE || K % OZ_KB)
+    return fail(ctx, AGPC_E_ARG, "gemm_nt_i8x: M,N must be multiples of 128 and K of 32");
+  if (n_slices != 6 && n_slices != 7) return fail(ctx, AGPC_E_ARG, "gemm_nt_i8x: n_slices must be 6 or 7");
+  CK(ctx, cudaSetDevice(ctx->device));
+  const size_t sa_bytes = (size_t)n_slices * M * K, sb_bytes = (size_t)n_slices * N * K;
+  const size_t need = (sa_bytes + sb_bytes) * batch + sizeof(double) * (size_t)(M + N) * batch + 8192;
+  int rc = ctx->ensure_arena(need);
+  if (rc) return rc;
+  char* p = (char*)ctx->arena;
+  int8_t* SA = (int8_t*)p; p += (sa_bytes * batch + 1023) / 1024 * 1024;
+  int8_t* SB = (int8_t*)p; p += (sb_bytes * batch + 1023) / 1024 * 1024;
+  double* scA = (double*)p; p += sizeof(double) * (size_t)M * batch;
+  double* scB = (double*)p;
+  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches, &ctx->prof, ctx->side, ctx->ev_panel, ctx->ev_rest};
+  OzSliceArgs sa{};
+  sa.X = A; sa.ld = K; sa.x_batch = (long long)M * K; sa.S = SA; sa.scale = scA; sa.s_batch = (long long)sa_bytes; sa.sc_batch = M;
+  sa.nkc = K / OZ_KB; sa.row_blocks = M / TILE; sa.col_chunks = K / OZ_KB;
+  CK(ctx, oz_slice_launch(L, sa, M / TILE, 1, batch, n_slices));
+  OzSliceArgs sb = sa;
+  sb.X = B; sb.x_batch = (long long)N * K; sb.S = SB; sb.scale = scB; sb.s_batch = (long long)sb_bytes; sb.sc_batch = N;
+  sb.row_blocks = N / TILE;
+  CK(ctx, oz_slice_launch(L, sb, N / TILE, 1, batch, n_slices));
+  OzGemmArgs g{};
+  g.A = OzOperand{SA, scA, (long long)sa_bytes, M, K / OZ_KB};
+  g.B = OzOperand{SB, scB, (long long)sb_bytes, N, K / OZ_KB};
+  g.C = C; g.ldc = N; g.c_batch = (long long)M * N;
+  g.m_tiles = M / TILE; g.n_tiles = N / TILE; g.k_chunks = K / OZ_KB;
+  g.alpha = alpha; g.beta = beta;
+  L.add_work(CLS_GEMM, 2.0 * M * N * (double)K * batch);
+  L.add_work(CLS_SLICE, 8.0 * ((double)M + N) * K * batch);
+  CK(ctx, oz_gemm_launch(L, g, g.m_tiles * g.n_tiles, 1, batch, n_slices));
+  return AGPC_OK;
+}
+
 int agpc_potrf(agpc_ctx* ctx, double* A, int32_t n, int32_t batch, double* Minv, double* Uinv, int32_t* info,
                void* stream) {
   if (!ctx || !A || n <= 0 || batch <= 0 || n % TILE) return fail(ctx, AGPC_E_ARG, "potrf: n must be a multiple of 128");
@@ -260,6 +301,9 @@ int agpc_potrf(agpc_ctx* ctx, double* A, int32_t n, int32_t batch, double* Minv,
   if (!Minv) need += mat;
   if (!Uinv) need += mat;
   if (want_inv) need += mat;  // T
+  const int oz_S = ctx->oz_S;
+  const size_t oz_bytes = (size_t)oz_S * n * n * batch, sc_bytes = sizeof(double) * (size_t)n * batch;
+  if (oz_S) need += 2 * (oz_bytes + 1024) + 2 * sc_bytes;
   int rc = ctx->ensure_arena(need + 4096);
   if (rc) return rc;
   char* p = (char*)ctx->arena;
@@ -269,6 +313,15 @@ int agpc_potrf(agpc_ctx* ctx, double* A, int32_t n, int32_t batch, double* Minv,
   ms.M = Minv ? Minv : (double*)p; if (!Minv) p += mat;
   ms.U = Uinv ? Uinv : (double*)p; if (!Uinv) p += mat;
   ms.T = want_inv ? (double*)p : nullptr;
+  if (want_inv) p += mat;
+  if (oz_S) {
+    ms.oz_S = oz_S;
+    ms.scA = (double*)p; p += sc_bytes;
+    ms.scB = (double*)p; p += sc_bytes;
+    p = (char*)(((uintptr_t)p + 1023) & ~(uintptr_t)1023);
+    ms.SA = (int8_t*)p; p += (oz_bytes + 1023) / 1024 * 1024;
+    ms.SB = (int8_t*)p;
+  }
   if (make_tensor_map(&ms.mapA, ms.A, n, n, batch, n, ms.stride) || make_tensor_map(&ms.mapM, ms.M, n, n, batch, n, ms.stride) ||
       make_tensor_map(&ms.mapU, ms.U, n, n, batch, n, ms.stride) ||
       make_tensor_map(&ms.mapA32, ms.A, n, n, batch, n, ms.stride, 32) ||

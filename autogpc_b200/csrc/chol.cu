@@ -259,7 +259,7 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ M, double* __restr
 cudaError_t potf2_inv_launch(const Launch& L, double* A, double* M, double* U, long long ld, long long batch_stride,
                              int diag_block, int batch, const int* active, int* info) {
   ProfScope prof_scope(L, CLS_POTF2);
-  static bool configured = false;
+  bool& configured = func_attr_done(__LINE__);  // per device: the attribute belongs to the device's context
   if (!configured) {
     AGPC_CUDA_TRY(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM));
     configured = true;
@@ -298,6 +298,36 @@ static cudaError_t copy_panel_launch(const Launch& L, const double* src, double*
 constexpr int POTRF_OUTER = 4;
 // one-tile-wide launches with fewer CTAs than this run as 128 x 32 tiles (4x the CTAs, a quarter of the latency)
 constexpr int THIN_CTA_LIMIT = 160;
+
+// ---- int8 tensor-core path (ozaki.cu) -----------------------------------------------------------------------------
+// Products with a long K extent run as sliced-integer GEMMs when the MatSet carries slice buffers (ms.oz_S = 6 / 7):
+// the operands are re-sliced from their FP64 source right before each product (row scale = exact row maximum over the
+// K range that product uses), SA serves the A operand and SB the B operand.
+static inline bool oz_on(const MatSet& ms) { return ms.oz_S > 0 && ms.SA != nullptr; }
+static inline OzOperand oz_operand(const MatSet& ms, bool second) {
+  return OzOperand{second ? ms.SB : ms.SA, second ? ms.scB : ms.scA, (long long)ms.oz_S * ms.np * ms.np, (long long)ms.np,
+                   ms.np / OZ_KB};
+}
+static inline OzSliceArgs oz_slice_args(const MatSet& ms, const double* X, bool second, const int* active) {
+  OzSliceArgs a{};
+  a.X = X; a.ld = ms.np; a.x_batch = ms.stride;
+  a.S = second ? ms.SB : ms.SA; a.scale = second ? ms.scB : ms.scA;
+  a.s_batch = (long long)ms.oz_S * ms.np * ms.np; a.sc_batch = ms.np; a.nkc = ms.np / OZ_KB;
+  a.active = active;
+  return a;
+}
+constexpr int OZ_CPB = TILE / OZ_KB;   // K chunks per 128-block
+constexpr int OZ_TRTRI_MIN_H = 2;      // trtri levels below this half-size (K = 128) stay on the DMMA kernel
+
+// slices the factored panel columns [k0, k0 + kb) for the rows from block r0 down: both operands of the trailing update
+static cudaError_t potrf_slice_panel(const Launch& L, const MatSet& ms, const int* active, int k0, int kb, int r0) {
+  const int nblk = ms.np / TILE;
+  if (nblk - r0 <= 0) return cudaSuccess;
+  OzSliceArgs a = oz_slice_args(ms, ms.A, false, active);
+  a.row0 = r0 * TILE; a.col0 = k0 * TILE; a.row_blocks = nblk - r0; a.col_chunks = kb * OZ_CPB;
+  L.add_work(CLS_SLICE, 8.0 * (double)(nblk - r0) * TILE * kb * TILE * L.work_items);
+  return oz_slice_launch(L, a, nblk - r0, 1, ms.batch, ms.oz_S);
+}
 
 // panels k0 .. k0 + kb of one outer block: in-block left-looking update, diagonal block, panel solve
 // first_staged: the head update of the previous outer block already duplicated panel k0 (rows > k0) into M
@@ -359,6 +389,24 @@ static cudaError_t potrf_trailing(const Launch& L, const MatSet& ms, const int* 
   const int nblk = ms.np / TILE;
   const int rows = nblk - r0;
   if (rows <= 0 || ncols == 0) return cudaSuccess;
+  if (oz_on(ms)) {  // the panel was sliced into SA by potrf_slice_panel
+    OzGemmArgs z{};
+    z.A = oz_operand(ms, false); z.B = z.A;
+    z.C = ms.A; z.Ct = nullptr; z.ldc = ms.np; z.c_batch = ms.stride;
+    z.a_row0 = r0 * TILE; z.a_col0 = k0 * TILE; z.b_row0 = r0 * TILE; z.b_col0 = k0 * TILE;
+    z.c_row0 = r0 * TILE; z.c_col0 = r0 * TILE;
+    z.k_chunks = kb * OZ_CPB; z.k_rule = KRULE_FULL; z.alpha = -1.0; z.beta = 1.0; z.active = active;
+    if (ncols < 0) {
+      z.m_tiles = rows; z.n_tiles = rows; z.lower_only = 1;
+      return oz_gemm_launch(L, z, rows * (rows + 1) / 2, 1, ms.batch, ms.oz_S);
+    }
+    const int nc = ncols < rows ? ncols : rows;
+    z.m_tiles = rows; z.n_tiles = nc; z.lower_only = 0; z.skip_upper = 1;
+    AGPC_CUDA_TRY(oz_gemm_launch(L, z, rows * nc, 1, ms.batch, ms.oz_S));
+    if (stage_first_col && rows > 1)  // the thin panel solve reads its panel from the M scratch
+      AGPC_CUDA_TRY(copy_panel_launch(L, ms.A, ms.M, ms.np, ms.stride, (r0 + 1) * TILE, r0 * TILE, (rows - 1) * TILE, ms.batch, active));
+    return cudaSuccess;
+  }
   GemmArgs s{};
   s.C = ms.A; s.Ct = nullptr; s.ldc = ms.np; s.c_batch = ms.stride;
   s.a_row0 = r0 * TILE; s.a_col0 = k0 * TILE;
@@ -393,7 +441,10 @@ cudaError_t potrf_blocked(const Launch& L, const MatSet& ms, const int* active, 
     for (int k0 = 0; k0 < nblk; k0 += POTRF_OUTER) {
       const int kb = nblk - k0 < POTRF_OUTER ? nblk - k0 : POTRF_OUTER;
       AGPC_CUDA_TRY(potrf_panels(L, ms, active, info, k0, kb, false));
-      if (k0 + kb < nblk) AGPC_CUDA_TRY(potrf_trailing(L, ms, active, k0, kb, k0 + kb, -1));
+      if (k0 + kb < nblk) {
+        if (oz_on(ms)) AGPC_CUDA_TRY(potrf_slice_panel(L, ms, active, k0, kb, k0 + kb));
+        AGPC_CUDA_TRY(potrf_trailing(L, ms, active, k0, kb, k0 + kb, -1));
+      }
     }
     return cudaSuccess;
   }
@@ -409,6 +460,11 @@ cudaError_t potrf_blocked(const Launch& L, const MatSet& ms, const int* active, 
     AGPC_CUDA_TRY(potrf_panels(H, ms, active, info, k0, kb, first_staged));
     const int r0 = k0 + kb;
     if (r0 >= nblk) break;
+    if (oz_on(ms)) {
+      // the slices of this block's panel replace those of the previous one, which rest(i-1) may still be reading
+      if (rest_pending) AGPC_CUDA_TRY(cudaStreamWaitEvent(H.stream, L.ev_rest, 0));
+      AGPC_CUDA_TRY(potrf_slice_panel(H, ms, active, k0, kb, r0));
+    }
     AGPC_CUDA_TRY(cudaEventRecord(L.ev_panel, H.stream));
     if (rest_pending) AGPC_CUDA_TRY(cudaStreamWaitEvent(H.stream, L.ev_rest, 0));  // rest(i-1) wrote the head's columns
     AGPC_CUDA_TRY(potrf_trailing(H, ms, active, k0, kb, r0, POTRF_OUTER, (nblk - r0 - 1) * ms.batch <= THIN_CTA_LIMIT));
@@ -435,6 +491,49 @@ cudaError_t trtri_blocked(const Launch& L, const MatSet& ms, const int* active) 
   for (int h = 1; h < nblk; h *= 2) {
     const int G = 2 * h;
     const int groups = (nblk + G - 1) / G;
+    if (oz_on(ms) && h >= OZ_TRTRI_MIN_H) {
+      const double blk = (double)TILE * TILE * 8.0 * Lt.work_items;
+      // step 1: T[left rows, right cols] = U11 * L21^T  (U11 upper triangular: K from the tile row on)
+      OzSliceArgs su = oz_slice_args(ms, ms.U, false, active);
+      su.row0 = 0; su.col0 = 0; su.row_blocks = h; su.col_chunks = h * OZ_CPB; su.tri = 2;
+      su.grp_blocks = G; su.half_blocks = h; su.nblk = nblk; su.need_h2 = 1;
+      AGPC_CUDA_TRY(oz_slice_launch(Lt, su, h, groups, ms.batch, ms.oz_S));
+      OzSliceArgs sl = oz_slice_args(ms, ms.A, true, active);
+      sl.row0 = h * TILE; sl.col0 = 0; sl.rows_kind = EXT_H2; sl.col_chunks = h * OZ_CPB;
+      sl.grp_blocks = G; sl.half_blocks = h; sl.nblk = nblk; sl.need_h2 = 1;
+      AGPC_CUDA_TRY(oz_slice_launch(Lt, sl, h, groups, ms.batch, ms.oz_S));
+      Lt.add_work(CLS_SLICE, blk * 1.5 * h * h * groups);
+      OzGemmArgs a{};
+      a.A = oz_operand(ms, false); a.B = oz_operand(ms, true);
+      a.C = ms.T; a.Ct = nullptr; a.ldc = ms.np; a.c_batch = ms.stride;
+      a.a_row0 = 0; a.a_col0 = 0; a.b_row0 = h * TILE; a.b_col0 = 0; a.c_row0 = 0; a.c_col0 = h * TILE;
+      a.m_tiles = h; a.n_tiles = 0; a.k_chunks = h * OZ_CPB;
+      a.m_kind = EXT_FIXED; a.n_kind = EXT_H2; a.k_kind = EXT_FIXED;
+      a.grp_blocks = G; a.half_blocks = h; a.nblk = nblk;
+      a.k_rule = KRULE_BEGIN_AT_ROW; a.alpha = 1.0; a.beta = 0.0; a.active = active;
+      AGPC_CUDA_TRY(oz_gemm_launch(Lt, a, h * h, groups, ms.batch, ms.oz_S));
+      // step 2: M21 = -M22 * T^T ; U12 = M21^T  (M22 lower triangular: K up to the tile row)
+      OzSliceArgs sm = oz_slice_args(ms, ms.M, false, active);
+      sm.row0 = h * TILE; sm.col0 = h * TILE; sm.rows_kind = EXT_H2; sm.cols_kind = EXT_H2; sm.tri = 1;
+      sm.grp_blocks = G; sm.half_blocks = h; sm.nblk = nblk; sm.need_h2 = 1;
+      AGPC_CUDA_TRY(oz_slice_launch(Lt, sm, h, groups, ms.batch, ms.oz_S));
+      OzSliceArgs st = oz_slice_args(ms, ms.T, true, active);
+      st.row0 = 0; st.col0 = h * TILE; st.row_blocks = h; st.cols_kind = EXT_H2;
+      st.grp_blocks = G; st.half_blocks = h; st.nblk = nblk; st.need_h2 = 1;
+      AGPC_CUDA_TRY(oz_slice_launch(Lt, st, h, groups, ms.batch, ms.oz_S));
+      Lt.add_work(CLS_SLICE, blk * 1.5 * h * h * groups);
+      OzGemmArgs c{};
+      c.A = oz_operand(ms, false); c.B = oz_operand(ms, true);
+      c.C = ms.M; c.Ct = ms.U; c.ldc = ms.np; c.c_batch = ms.stride;
+      c.a_row0 = h * TILE; c.a_col0 = h * TILE; c.b_row0 = 0; c.b_col0 = h * TILE;
+      c.c_row0 = h * TILE; c.c_col0 = 0; c.ct_row0 = 0; c.ct_col0 = h * TILE;
+      c.m_tiles = 0; c.n_tiles = h; c.k_chunks = 0;
+      c.m_kind = EXT_H2; c.n_kind = EXT_FIXED; c.k_kind = EXT_H2;
+      c.grp_blocks = G; c.half_blocks = h; c.nblk = nblk;
+      c.k_rule = KRULE_END_AT_ROW; c.alpha = -1.0; c.beta = 0.0; c.active = active;
+      AGPC_CUDA_TRY(oz_gemm_launch(Lt, c, h * h, groups, ms.batch, ms.oz_S));
+      continue;
+    }
     // step 1: T[left rows, right cols] = U11 * L21^T
     GemmArgs a{};
     a.C = ms.T; a.Ct = nullptr; a.ldc = ms.np; a.c_batch = ms.stride;
@@ -469,6 +568,18 @@ cudaError_t lauum_blocked(const Launch& L, const MatSet& ms, double* dst, const 
   L.add_work(CLS_GEMM_LAUUM, (double)L.work_items * wn * wn * wn / 3.0);  // dlauum
   Launch Ll = L;
   Ll.gemm_cls = CLS_GEMM_LAUUM;
+  if (oz_on(ms)) {
+    OzSliceArgs su = oz_slice_args(ms, ms.U, false, active);
+    su.row_blocks = nblk; su.col_chunks = nblk * OZ_CPB; su.tri = 2;
+    Ll.add_work(CLS_SLICE, 4.0 * wn * wn * Ll.work_items);
+    AGPC_CUDA_TRY(oz_slice_launch(Ll, su, nblk, 1, ms.batch, ms.oz_S));
+    OzGemmArgs z{};
+    z.A = oz_operand(ms, false); z.B = z.A;
+    z.C = dst; z.Ct = nullptr; z.ldc = ms.np; z.c_batch = ms.stride;
+    z.m_tiles = nblk; z.n_tiles = nblk; z.k_chunks = nblk * OZ_CPB;
+    z.k_rule = KRULE_BEGIN_AT_ROW; z.lower_only = 1; z.alpha = 1.0; z.beta = 0.0; z.active = active;
+    return oz_gemm_launch(Ll, z, nblk * (nblk + 1) / 2, 1, ms.batch, ms.oz_S);
+  }
   GemmArgs a{};
   a.C = dst; a.Ct = nullptr; a.ldc = ms.np; a.c_batch = ms.stride;
   a.m_tiles = nblk; a.n_tiles = nblk; a.k_tiles = nblk * (TILE / GEMM_BK);

@@ -40,7 +40,8 @@ struct GemmArgs {
 
 // Kernel classes of the optional per-launch event timing (agpc_profile_*): bench.py's roofline and the share table.
 enum : int { CLS_KBUILD = 0, CLS_GEMM, CLS_POTF2, CLS_MATVEC, CLS_EP, CLS_GRAD, CLS_FORMB, CLS_MISC, CLS_GEMM_TRTRI, CLS_GEMM_LAUUM,
-              CLS_COUNT };  // CLS_GEMM = the tile GEMM inside potrf (and predict); _TRTRI / _LAUUM = the same kernel in those phases
+              CLS_SLICE, CLS_COUNT };  // CLS_GEMM = the tile GEMM inside potrf (and predict); _TRTRI / _LAUUM = the same kernel in
+                                       // those phases; CLS_SLICE = operand slicing for the int8 tensor-core GEMM (ozaki.cu)
 
 // When enabled, every launcher brackets its kernel with a cudaEvent pair on the launching stream; the pairs are
 // summed per class by agpc_profile_read.  `work` is the ALGORITHMIC work the drivers attribute to a class
@@ -109,6 +110,51 @@ int make_tensor_map(CUtensorMap* out, const double* base, long long cols, long l
 cudaError_t gemm_nt_thin_launch(const Launch& L, const CUtensorMap& mapA, const CUtensorMap& mapB32,
                                 const GemmArgs& args, int tiles_x, int groups, int batch);
 
+// ---- ozaki.cu: FP64-accurate tile GEMM on tcgen05 kind::i8 (operands as S signed 8-bit digit slices) ---------------
+constexpr int OZ_KB = 32;  // K extent (= bytes) of one operand tile: one 32-byte swizzle span, one kind::i8 MMA deep
+constexpr int OZ_BN = 64;  // C tile is 128 x 64: S accumulators x 64 columns must fit the 512 TMEM columns
+// Sliced image of one FP64 operand matrix: tile (rb, kc, p) -- rows 128 rb .. +128, columns 32 kc .. +32, digit slice p --
+// is the 4 KB block at S + ((rb * nkc + kc) * n_slices + p) * 4096, already in the swizzled K-major layout the MMA
+// reads; scale[row] = 2^(e_row - 8).  Tiles are addressed by the coordinates of the source matrix.
+struct OzOperand {
+  const int8_t* S;
+  const double* scale;
+  long long s_batch, sc_batch;  // batch strides (bytes / elements)
+  int nkc;                      // K chunks per row block = columns of the source matrix / 32
+};
+struct OzGemmArgs {  // same tile / group / K-range semantics as GemmArgs; n_tiles counts 128-wide tile columns
+  OzOperand A, B;
+  double* C;
+  double* Ct;
+  long long ldc, c_batch;
+  int a_row0, a_col0, b_row0, b_col0, c_row0, c_col0, ct_row0, ct_col0;
+  int m_tiles, n_tiles, k_chunks;  // k_chunks: K / 32
+  int m_kind, n_kind, k_kind;
+  int grp_blocks, half_blocks, nblk;
+  int k_rule, lower_only, skip_upper;
+  double alpha, beta;
+  const int* active;
+};
+struct OzSliceArgs {
+  const double* X;  // source region: rows row0 .. , columns col0 .. (group g adds g * grp_blocks * 128 to both)
+  long long ld, x_batch;
+  int8_t* S;
+  double* scale;
+  long long s_batch, sc_batch;
+  int nkc;
+  int row0, col0;
+  int row_blocks, col_chunks;  // extent (128-row blocks, 32-column chunks) when the kinds are EXT_FIXED
+  int rows_kind, cols_kind;    // EXT_H2: right-half size of trtri group g
+  int grp_blocks, half_blocks, nblk;
+  int need_h2;  // grouped launches: skip groups without a right half (their left half may lie outside the matrix)
+  int tri;  // 0: whole rectangle; 1: chunks up to the end of the row block's own diagonal block (lower triangular
+            // region); 2: chunks from the start of it (upper triangular).  The row scale covers exactly that range.
+  const int* active;
+};
+struct Launch;
+cudaError_t oz_gemm_launch(const Launch& L, const OzGemmArgs& a, int tiles128, int groups, int batch, int S);
+cudaError_t oz_slice_launch(const Launch& L, const OzSliceArgs& a, int row_blocks, int groups, int batch, int S);
+
 // One lock-step batch of padded np x np matrices (np % 128 == 0, ld == np, matrix b at base + b*stride) and the
 // tensor maps the GEMM kernel reads them through.
 //   K: kernel matrix            A: B = I + S^1/2 K S^1/2 -> L (lower)        M: L^-1 (lower)
@@ -117,6 +163,11 @@ struct MatSet {
   int np = 0, batch = 0;
   long long stride = 0;
   double *K = nullptr, *A = nullptr, *M = nullptr, *U = nullptr, *T = nullptr;
+  // int8 tensor-core path (ozaki.cu): two slice buffers of oz_S * np * np bytes per item + their row scales; oz_S = 0
+  // keeps every product on the FP64 DMMA kernel
+  int oz_S = 0;
+  int8_t *SA = nullptr, *SB = nullptr;
+  double *scA = nullptr, *scB = nullptr;
   CUtensorMap mapA, mapM, mapU, mapT;
   CUtensorMap mapA32, mapM32;  // 32-row boxes: B operands of the thin GEMM variant
 };
@@ -212,6 +263,17 @@ cudaError_t axpy_launch(const Launch& L, const double* x, const double* y, doubl
 cudaError_t predict_prob_launch(const Launch& L, const double* mu_s, const double* kss, const double* vsq, double* p,
                                 double* var, long long total);
 
+}  // namespace agpc
+
+namespace agpc {
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device context: one "done" flag per (call site, device), so
+// a second Engine(device = k) in the same process configures its own context instead of failing at launch
+inline bool& func_attr_done(int site) {
+  static bool done[64][2048] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return done[dev & 63][site & 2047];
+}
 }  // namespace agpc
 
 #define AGPC_CUDA_TRY(expr)                         \

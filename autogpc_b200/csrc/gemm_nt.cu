@@ -235,7 +235,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 cudaError_t gemm_nt_launch(const Launch& L, const CUtensorMap& mapA, const CUtensorMap& mapB, const GemmArgs& args,
                            int tiles_x, int groups, int batch) {
   ProfScope prof_scope(L, L.gemm_cls);
-  static bool configured = false;
+  bool& configured = func_attr_done(__LINE__);  // per device: the attribute belongs to the device's context
   if (!configured) {
     AGPC_CUDA_TRY(cudaFuncSetAttribute(gemm_nt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     AGPC_CUDA_TRY(cudaFuncSetAttribute(gemm_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -252,7 +252,7 @@ cudaError_t gemm_nt_launch(const Launch& L, const CUtensorMap& mapA, const CUten
 cudaError_t gemm_nt_thin_launch(const Launch& L, const CUtensorMap& mapA, const CUtensorMap& mapB32,
                                 const GemmArgs& args, int tiles_x, int groups, int batch) {
   ProfScope prof_scope(L, L.gemm_cls);
-  static bool configured = false;
+  bool& configured = func_attr_done(__LINE__);  // per device: the attribute belongs to the device's context
   if (!configured) {
     AGPC_CUDA_TRY(cudaFuncSetAttribute(gemm_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     configured = true;

@@ -750,7 +750,7 @@ build_KdK_tiled_kernel(const BuildArgs a, const int symmetric, const int tiles_n
 cudaError_t build_K_launch(const Launch& L, const BuildArgs& a, int batch, bool grad) {
   ProfScope prof_scope(L, CLS_KBUILD);
   if (grad && a.dk_tiled) {
-    static bool configured = false;
+    bool& configured = func_attr_done(__LINE__);
     const size_t smem = sizeof(double) * (2 * (size_t)a.D * KT + KT * KT_LD);
     if (!configured || smem > 48 * 1024) {
       AGPC_CUDA_TRY(cudaFuncSetAttribute(build_KdK_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -773,7 +773,7 @@ cudaError_t build_K_launch(const Launch& L, const BuildArgs& a, int batch, bool 
     L.bump();
     return cudaGetLastError();
   }
-  static bool configured = false;
+  bool& configured = func_attr_done(__LINE__);
   const size_t smem = sizeof(double) * (2 * (size_t)a.D * KT + KT * KT_LD);
   if (!configured || smem > 48 * 1024) {
     AGPC_CUDA_TRY(cudaFuncSetAttribute(build_K_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -1,0 +1,406 @@
+// FP64-accurate tile GEMM  C = alpha * A * B^T + beta * C  on the Blackwell tensor core proper: operands cut into S
+// signed 8-bit digit slices, products formed by tcgen05.mma kind::i8 with exact int32 accumulation in TMEM, recombined
+// in FP64 in the epilogue (Ozaki-style error-free slicing).
+//
+// Same role as gemm_nt.cu (the dsyrk / dgemm / dtrtri / dlauum calls GPy reaches through util/linalg.py jitchol, dtrtrs,
+// pdinv from EP.inference, for gpckernel.py:245-246) for the products whose K extent amortises the slicing: the
+// K = 512 trailing updates of potrf, the upper levels of trtri, lauum.  The DMMA pipe that gemm_nt.cu runs on tops out
+// at 37 TFLOP/s on B200 and that kernel already fills it to 90 %; kind::i8 runs at 4.5 POP/s, so S (S + 1) / 2 = 28
+// integer MMAs per FP64 product still come out 3x ahead.
+//
+// Numerics.  Per operand row i one power-of-two scale 2^e_i with |a_ik| 2^-e_i < 1/4 over the K range the product
+// uses; X_ik = rint(a_ik 2^(8S - e_i)) is an integer below 2^(8S-2) (exact for S = 7 wherever a_ik is within 2^-1 of the
+// row scale: 53 bits fit), written as sum_p d_p 256^(S-1-p) with round-to-nearest signed digits d_p in [-128, 127]
+// (bytes of (X + BIAS) ^ BIAS, BIAS = 0x80 in every byte).  Then
+//     (A B^T)_ij = 2^(ea_i + eb_j - 16) sum_{p+q <= S-1} 256^-(p+q) (D_p^A D_q^B^T)_ij   + O(S 2^(-8 S + 4)) |a_i|_max |b_j|_max K
+// and the integer products of equal weight p + q share ONE int32 accumulator (|.| <= (p+q+1) 2^14 K: exact for
+// K < 18 k).  tools/probe/ozaki_prototype.py: with S = 7 potrf / trtri / lauum of B = I + S^1/2 K S^1/2 agree with
+// LAPACK to 7e-15 / 5e-14 / 1e-14 (native blocked FP64: 4e-15 / 2e-15 / 7e-15); S = 6 to 3e-12 / 2e-11 / 1e-11.
+//
+// sm_100a design (profiles/r02_i8mma_probe.txt).  One CTA owns a 128 x 64 tile of C and all S accumulators for it:
+// S x 64 TMEM columns (448 of 512 for S = 7) -- that, not shared memory, is what fixes the tile width; the MMA then
+// runs shared-memory-bound at 48 cycles per 128 x 64 x 32 instruction (4 KB of A + 2 KB of B at 128 B/clk), 67 % of
+// the kind::i8 peak.  Operand slices live in HBM already in the shared-memory image the MMA wants (K-major, 32-byte
+// swizzle, one 4 KB tile per slice per 128 rows x 32 k), so a stage is filled by S + 1 plain bulk copies
+// (cp.async.bulk, mbarrier complete_tx) with no tensor map; 5-stage ring, one producer thread, one MMA-issuing
+// thread, 8 epilogue warps that read TMEM (tcgen05.ld), run the FP64 Horner recombination, and go through a padded
+// shared-memory transposition so that every global access of C is a full-line row access.
+#include "common.cuh"
+
+namespace agpc {
+namespace oz {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded: a protocol error must surface as a launch failure (trap), never as a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  uint32_t spins = 0;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1u << 26)) __trap();
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// mode 0: A operand discarded after the MMA; 1 / 2 / 3: collector::a::fill / use / lastuse -- consecutive MMAs that share
+// their A slice keep it in the tensor core's operand collector (SASS A_KEEP / A_REUSE)
+#define AGPC_UMMA_I8(MOD)                                                                              \
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"                                             \
+               "tcgen05.mma.cta_group::1.kind::i8" MOD " [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}\n" \
+               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum), "r"(0u) : "memory")
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum, int mode) {
+  if (mode == 1) AGPC_UMMA_I8(".collector::a::fill");
+  else if (mode == 2) AGPC_UMMA_I8(".collector::a::use");
+  else if (mode == 3) AGPC_UMMA_I8(".collector::a::lastuse");
+  else AGPC_UMMA_I8("");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+}  // namespace oz
+
+constexpr int OZ_STAGES = 5;
+constexpr int OZ_THREADS = 320;  // warp 0: bulk-copy producer, warp 1: TMEM owner + MMA issuer, warps 2-9: epilogue
+constexpr int OZ_EPI_LD = OZ_BN + 1;  // padded row pitch (doubles) of the epilogue transposition buffer
+template <int S>
+constexpr int oz_stage_bytes() {
+  return S * (TILE + OZ_BN) * OZ_KB;
+}
+template <int S>
+constexpr int oz_smem_bytes() {
+  return OZ_STAGES * oz_stage_bytes<S>() + 1024 /*align slack*/ + 256 /*barriers*/;
+}
+static_assert(TILE * OZ_EPI_LD * 8 <= OZ_STAGES * oz_stage_bytes<6>(), "epilogue buffer must fit the ring");
+
+// K-major 32-byte-swizzled tile image: 16-byte chunk index XOR-ed with bit 7 of the byte offset (Swizzle<1,4,3>)
+__device__ __forceinline__ uint32_t oz_swz(uint32_t row, uint32_t kbyte) {
+  const uint32_t a = row * OZ_KB + kbyte;
+  return a ^ (((a >> 7) & 1u) << 4);
+}
+
+template <int S>
+__global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzGemmArgs args) {
+  using namespace oz;
+  constexpr int CPB = TILE / OZ_KB;  // K chunks per 128-block
+  const int b = blockIdx.z;
+  if (args.active != nullptr && args.active[b] == 0) return;
+  const int g = blockIdx.y;
+  int h2 = 0;
+  if (args.grp_blocks > 0) {
+    h2 = args.nblk - g * args.grp_blocks - args.half_blocks;
+    h2 = h2 < 0 ? 0 : (h2 > args.half_blocks ? args.half_blocks : h2);
+  }
+  const int shift = g * args.grp_blocks * TILE;
+  const int mt = args.m_kind == EXT_H2 ? h2 : args.m_tiles;
+  const int nt = args.n_kind == EXT_H2 ? h2 : args.n_tiles;
+  const int kt = args.k_kind == EXT_H2 ? h2 * CPB : args.k_chunks;
+  if (mt <= 0 || nt <= 0) return;
+  const int half = blockIdx.x & 1;  // which 64-column half of the 128-wide tile column
+  const int t = blockIdx.x >> 1;
+  int ti, tj;
+  if (args.lower_only) {
+    if (t >= mt * (mt + 1) / 2) return;
+    ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while (ti * (ti + 1) / 2 > t) --ti;
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    tj = t - ti * (ti + 1) / 2;
+  } else {
+    ti = t / nt;
+    tj = t % nt;
+    if (ti >= mt) return;
+    if (args.skip_upper && tj > ti) return;
+  }
+  int k_begin = 0, k_end = kt;
+  if (args.k_rule == KRULE_BEGIN_AT_ROW) k_begin = ti * CPB;
+  if (args.k_rule == KRULE_END_AT_ROW) k_end = min(kt, (ti + 1) * CPB);
+  if (args.k_rule == KRULE_END_AT_COL) k_end = min(kt, (2 * tj + half + 1) * (OZ_BN / OZ_KB));
+  const int n_iter = k_end - k_begin;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  constexpr uint32_t STAGE = oz_stage_bytes<S>();
+  constexpr uint32_t A_SLICE = TILE * OZ_KB, B_SLICE = OZ_BN * OZ_KB;
+  const uint32_t bars = smem_base + OZ_STAGES * STAGE;  // full[0..ST), empty[0..ST), accf
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + OZ_STAGES * STAGE + 8 * (2 * OZ_STAGES + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2 * OZ_STAGES + 1; ++s) mbar_init(bars + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  const int a_row = args.a_row0 + shift + ti * TILE;
+  const int b_row = args.b_row0 + shift + tj * TILE + half * OZ_BN;
+
+  if (warp == 0) {
+    // ---------------- producer: S + 1 bulk copies per stage ----------------
+    if (lane == 0) {
+      const long long tileA = (long long)(a_row >> 7) * args.A.nkc + ((args.a_col0 + shift) / OZ_KB) + k_begin;
+      const long long tileB = (long long)(b_row >> 7) * args.B.nkc + ((args.b_col0 + shift) / OZ_KB) + k_begin;
+      const int8_t* srcA = args.A.S + (long long)b * args.A.s_batch + tileA * (S * (long long)A_SLICE);
+      const int8_t* srcB = args.B.S + (long long)b * args.B.s_batch + tileB * (S * (long long)A_SLICE) + ((b_row >> 6) & 1) * B_SLICE;
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % OZ_STAGES;
+        const uint32_t ph = (uint32_t)(it / OZ_STAGES) & 1u;
+        mbar_wait(bars + 8 * (OZ_STAGES + s), ph ^ 1u);
+        const uint32_t full = bars + 8 * s;
+        mbar_expect_tx(full, STAGE);
+        const uint32_t dst = smem_base + s * STAGE;
+        bulk_g2s(dst, srcA + (long long)it * (S * (long long)A_SLICE), S * A_SLICE, full);
+#pragma unroll
+        for (int q = 0; q < S; ++q)
+          bulk_g2s(dst + S * A_SLICE + q * B_SLICE, srcB + (long long)it * (S * (long long)A_SLICE) + q * (long long)A_SLICE, B_SLICE, full);
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      // instruction descriptor: D = S32, A = B = signed 8 bit, both K-major, N = 64, M = 128
+      constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+      // shared-memory descriptor: 32-byte swizzle (6), 8-row group pitch 256 B, LBO field 1, version 1
+      constexpr uint64_t DESC_HI = (1ull << 16) | ((uint64_t)((8 * OZ_KB) >> 4) << 32) | (1ull << 46) | (6ull << 61);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % OZ_STAGES;
+        const uint32_t ph = (uint32_t)(it / OZ_STAGES) & 1u;
+        mbar_wait(bars + 8 * s, ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_base + s * STAGE, sb = sa + S * A_SLICE;
+#pragma unroll
+        for (int p = 0; p < S; ++p) {
+          const uint64_t da = DESC_HI | (uint64_t)(((sa + p * A_SLICE) >> 4) & 0x3FFF);
+#pragma unroll
+          for (int q = 0; q < S - p; ++q) {
+            const uint64_t db = DESC_HI | (uint64_t)(((sb + q * B_SLICE) >> 4) & 0x3FFF);
+            const int nq = S - p;
+            const int mode = nq == 1 ? 0 : q == 0 ? 1 : q == nq - 1 ? 3 : 2;
+            // accumulator p + q: overwritten by its first product of the tile (it == 0, p == 0), accumulated after
+            umma_i8(tmem + (uint32_t)(p + q) * OZ_BN, da, db, IDESC, (it == 0 && p == 0) ? 0u : 1u, mode);
+          }
+        }
+        umma_commit(bars + 8 * (OZ_STAGES + s));  // frees the stage when these MMAs have read it
+      }
+      if (n_iter > 0) umma_commit(bars + 8 * (2 * OZ_STAGES));  // accumulators complete
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> FP64 Horner -> padded smem -> global ----------------
+    const int ew = warp - 2;           // 0..7
+    const int q4 = warp & 3;           // TMEM lane quarter this warp may read
+    const int ch = ew >> 2;            // column half (32 columns) of the 64-wide tile
+    const int row = q4 * 32 + lane;
+    double* stage = reinterpret_cast<double*>(smem_gen);
+    if (n_iter > 0) {
+      mbar_wait(bars + 8 * (2 * OZ_STAGES), 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    const double sa = args.A.scale[(long long)b * args.A.sc_batch + a_row + row] * args.alpha;
+    const uint32_t taddr = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(ch * 32);
+#pragma unroll 1
+    for (int c0 = 0; c0 < 32; c0 += 16) {
+      double sum[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) sum[j] = 0.0;
+      if (n_iter > 0) {
+#pragma unroll
+        for (int d = S - 1; d >= 0; --d) {
+          uint32_t v[16];
+          tmem_ld16(taddr + (uint32_t)(d * OZ_BN + c0), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sum[j] = fma(sum[j], 0.00390625, (double)(int)v[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) stage[row * OZ_EPI_LD + ch * 32 + c0 + j] = sum[j] * sa;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const long long c_row = (long long)args.c_row0 + shift + ti * TILE;
+    const long long c_col = (long long)args.c_col0 + shift + tj * TILE + half * OZ_BN;
+    const double2 sb2 = *reinterpret_cast<const double2*>(args.B.scale + (long long)b * args.B.sc_batch + b_row + 2 * lane);
+    double* Cb = args.C + (long long)b * args.c_batch;
+    const double beta = args.beta;
+    for (int rr = ew; rr < TILE; rr += 8) {
+      double2 v;
+      v.x = stage[rr * OZ_EPI_LD + 2 * lane] * sb2.x;
+      v.y = stage[rr * OZ_EPI_LD + 2 * lane + 1] * sb2.y;
+      double2* dst = reinterpret_cast<double2*>(Cb + (c_row + rr) * args.ldc + c_col + 2 * lane);
+      if (beta != 0.0) {
+        const double2 old = *dst;
+        v.x = fma(beta, old.x, v.x);
+        v.y = fma(beta, old.y, v.y);
+      }
+      *dst = v;
+    }
+    if (args.Ct != nullptr) {
+      const long long t_row = (long long)args.ct_row0 + shift + tj * TILE + half * OZ_BN;
+      const long long t_col = (long long)args.ct_col0 + shift + ti * TILE;
+      double* Tb = args.Ct + (long long)b * args.c_batch;
+      for (int cc = ew; cc < OZ_BN; cc += 8) {
+        const double sbc = args.B.scale[(long long)b * args.B.sc_batch + b_row + cc];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) Tb[(t_row + cc) * args.ldc + t_col + lane + 32 * i] = stage[(lane + 32 * i) * OZ_EPI_LD + cc] * sbc;
+      }
+    }
+  }
+  __syncwarp();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+  }
+}
+
+// ---- slicing: FP64 region -> S int8 digit tiles (shared-memory image) + one scale per row --------------------------
+// One CTA per 128-row block of the region.  Pass 1: row maxima over the K range (8 warps x 16 rows, coalesced row reads)
+// -> e_i, 2^(8S - e_i) kept in shared memory, 2^(e_i - 8) written out for the GEMM epilogue.  Pass 2: per K chunk one
+// (row, 16-byte chunk) unit per thread: 16 doubles in, X = rint(a 2^(8S-e)) as int64, bytes of (X + BIAS) ^ BIAS are the
+// signed digits, gathered by PRMT into one 16-byte store per slice -- a warp writes 512 contiguous bytes per slice.
+template <int S>
+__global__ void __launch_bounds__(256) ozaki_slice_kernel(const OzSliceArgs a) {
+  constexpr int CPB = TILE / OZ_KB;
+  const int rbi = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
+  if (a.active != nullptr && a.active[b] == 0) return;
+  int h2 = 0;
+  if (a.grp_blocks > 0) {
+    h2 = a.nblk - g * a.grp_blocks - a.half_blocks;
+    h2 = h2 < 0 ? 0 : (h2 > a.half_blocks ? a.half_blocks : h2);
+  }
+  if (a.need_h2 && h2 <= 0) return;
+  const int nrb = a.rows_kind == EXT_H2 ? h2 : a.row_blocks;
+  const int ncc = a.cols_kind == EXT_H2 ? h2 * CPB : a.col_chunks;
+  if (rbi >= nrb || ncc <= 0) return;
+  const int shift = g * a.grp_blocks * TILE;
+  int c_lo = 0, c_hi = ncc;
+  if (a.tri == 1) c_hi = min(ncc, (rbi + 1) * CPB);
+  if (a.tri == 2) c_lo = min(ncc, rbi * CPB);
+  const int row_base = a.row0 + shift + rbi * TILE, col_base = a.col0 + shift;
+  const double* Xb = a.X + (long long)b * a.x_batch;
+  __shared__ double s_mult[TILE];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int rr = 0; rr < 16; ++rr) {
+    const int r = warp * 16 + rr;
+    const double* p = Xb + (long long)(row_base + r) * a.ld + col_base;
+    double amax = 0.0;
+    int bad = 0;
+    for (int c = c_lo * OZ_KB + 2 * lane; c < c_hi * OZ_KB; c += 64) {
+      const double2 v = *reinterpret_cast<const double2*>(p + c);
+      const double m = fmax(fabs(v.x), fabs(v.y));
+      bad |= !(fabs(v.x) <= 1.7976931348623157e308) | !(fabs(v.y) <= 1.7976931348623157e308);
+      amax = fmax(amax, m);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if (lane == 0) {
+      const int e = amax > 0.0 ? ilogb(amax) + 3 : 0;  // |a| 2^-e < 1/4
+      double mult = scalbn(1.0, 8 * S - e), sc = scalbn(1.0, e - 8);
+      if (bad) {  // a non-finite entry poisons the row, as it would in FP64
+        mult = 0.0;
+        sc = __longlong_as_double(0x7ff8000000000000LL);
+      }
+      s_mult[r] = mult;
+      a.scale[(long long)b * a.sc_batch + row_base + r] = sc;
+    }
+  }
+  __syncthreads();
+  constexpr unsigned long long BIAS = S == 7 ? 0x0080808080808080ull : S == 6 ? 0x0000808080808080ull : 0x8080808080808080ull;
+  const int r = tid >> 1, c16 = tid & 1;
+  const double mult = s_mult[r];
+  const double* src = Xb + (long long)(row_base + r) * a.ld + col_base + c16 * 16;
+  int8_t* tile0 = a.S + (long long)b * a.s_batch +
+                  ((long long)(row_base >> 7) * a.nkc + (col_base / OZ_KB)) * (S * (long long)(TILE * OZ_KB)) + oz_swz(r, c16 * 16);
+  for (int kc = c_lo; kc < c_hi; ++kc) {
+    uint32_t w[S][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double2 v0 = *reinterpret_cast<const double2*>(src + kc * OZ_KB + 4 * j);
+      const double2 v1 = *reinterpret_cast<const double2*>(src + kc * OZ_KB + 4 * j + 2);
+      const double x[4] = {v0.x, v0.y, v1.x, v1.y};
+      uint32_t lo[4], hi[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const unsigned long long z = ((unsigned long long)__double2ll_rn(x[i] * mult) + BIAS) ^ BIAS;
+        lo[i] = (uint32_t)z;
+        hi[i] = (uint32_t)(z >> 32);
+      }
+#pragma unroll
+      for (int p = 0; p < S; ++p) {
+        const int k = S - 1 - p;  // byte k of z is digit p (p = 0 most significant)
+        const uint32_t* srcw = k < 4 ? lo : hi;
+        const uint32_t sel = (uint32_t)(k & 3) | ((uint32_t)(4 + (k & 3)) << 4);
+        const uint32_t t0 = __byte_perm(srcw[0], srcw[1], sel), t1 = __byte_perm(srcw[2], srcw[3], sel);
+        w[p][j] = __byte_perm(t0, t1, 0x5410);
+      }
+    }
+    int8_t* dst = tile0 + (long long)kc * (S * (long long)(TILE * OZ_KB));
+#pragma unroll
+    for (int p = 0; p < S; ++p)
+      *reinterpret_cast<uint4*>(dst + p * (TILE * OZ_KB)) = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
+  }
+}
+
+// ---- launchers ---------------------------------------------------------------------------------------------------
+template <int S>
+static cudaError_t oz_gemm_launch_t(const Launch& L, const OzGemmArgs& a, int tiles128, int groups, int batch) {
+  bool& configured = func_attr_done(__LINE__ + S);
+  if (!configured) {
+    AGPC_CUDA_TRY(cudaFuncSetAttribute(ozaki_gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz_smem_bytes<S>()));
+    configured = true;
+  }
+  dim3 grid(2 * tiles128, groups, batch);
+  ozaki_gemm_kernel<S><<<grid, OZ_THREADS, oz_smem_bytes<S>(), L.stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t oz_gemm_launch(const Launch& L, const OzGemmArgs& a, int tiles128, int groups, int batch, int S) {
+  ProfScope prof_scope(L, L.gemm_cls);
+  if (tiles128 <= 0 || groups <= 0 || batch <= 0) return cudaSuccess;
+  L.bump();
+  return S == 6 ? oz_gemm_launch_t<6>(L, a, tiles128, groups, batch) : oz_gemm_launch_t<7>(L, a, tiles128, groups, batch);
+}
+
+cudaError_t oz_slice_launch(const Launch& L, const OzSliceArgs& a, int row_blocks, int groups, int batch, int S) {
+  ProfScope prof_scope(L, CLS_SLICE);
+  if (row_blocks <= 0 || groups <= 0 || batch <= 0) return cudaSuccess;
+  dim3 grid(row_blocks, groups, batch);
+  if (S == 6)
+    ozaki_slice_kernel<6><<<grid, 256, 0, L.stream>>>(a);
+  else
+    ozaki_slice_kernel<7><<<grid, 256, 0, L.stream>>>(a);
+  L.bump();
+  return cudaGetLastError();
+}
+
+}  // namespace agpc

@@ -59,13 +59,18 @@ struct Chunk {
   double* theta;
   double *nlml, *nlml_gauss, *bic, *grad, *partial;
 
-  size_t carve(char* base, int nb_, int np_, int D_, int theta_stride_, bool with_rows) {
+  size_t carve(char* base, int nb_, int np_, int D_, int theta_stride_, bool with_rows, int oz_S) {
     nb = nb_; np = np_; D = D_; theta_stride = theta_stride_;
     Carver c{base};
     const size_t mat = (size_t)nb * np * np, vec = (size_t)nb * np;
     ms.np = np; ms.batch = nb; ms.stride = (long long)np * np;
     ms.K = c.take<double>(mat); ms.A = c.take<double>(mat); ms.M = c.take<double>(mat);
     ms.U = c.take<double>(mat); ms.T = c.take<double>(mat);
+    ms.oz_S = oz_S;
+    if (oz_S > 0) {  // digit-slice images of the two operands of the int8 tensor-core GEMM + their row scales
+      ms.SA = c.take<int8_t>(mat * oz_S); ms.SB = c.take<int8_t>(mat * oz_S);
+      ms.scA = c.take<double>(vec); ms.scB = c.take<double>(vec);
+    }
     tau = c.take<double>(vec); nu = c.take<double>(vec); s = c.take<double>(vec); sig = c.take<double>(vec);
     mu = c.take<double>(vec); w = c.take<double>(vec); u = c.take<double>(vec); t = c.take<double>(vec);
     z = c.take<double>(vec); kv = c.take<double>(vec); dB = c.take<double>(vec); alpha = c.take<double>(vec);
@@ -150,10 +155,10 @@ cudaError_t posterior(const Launch& L, Chunk& c, const int* active) {
   return cudaSuccess;
 }
 
-size_t per_item_bytes(int np, int D, int theta_stride) {
+size_t per_item_bytes(int np, int D, int theta_stride, int oz_S) {
   Chunk tmp;
-  const size_t one = tmp.carve(nullptr, 1, np, D, theta_stride, true);
-  const size_t two = tmp.carve(nullptr, 2, np, D, theta_stride, true);
+  const size_t one = tmp.carve(nullptr, 1, np, D, theta_stride, true, oz_S);
+  const size_t two = tmp.carve(nullptr, 2, np, D, theta_stride, true, oz_S);
   return two - one + 4096;
 }
 
@@ -357,12 +362,13 @@ int agpc_score_batch_dev(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, con
 
   // chunking: consecutive items, as many as the arena budget allows at the padded size of the largest item
   const int np_all = (int)align_up((size_t)n_max, TILE);
-  const size_t per_item = per_item_bytes(np_all, ds.D, theta_stride);
+  const size_t per_item = per_item_bytes(np_all, ds.D, theta_stride, ctx->oz_S);
   const size_t budget = ctx->workspace_budget();
   int chunk_cap = (int)std::min<size_t>((size_t)n_items, std::max<size_t>(1, budget / per_item));
+  chunk_cap = std::min(chunk_cap, 65535);  // the batch index is gridDim.y / gridDim.z of most launches
   if (per_item > budget) return fail(ctx, AGPC_E_NOMEM, "score_batch: one item does not fit the workspace budget");
   Chunk probe;
-  const size_t need = probe.carve(nullptr, chunk_cap, np_all, ds.D, theta_stride, false);
+  const size_t need = probe.carve(nullptr, chunk_cap, np_all, ds.D, theta_stride, false, ctx->oz_S);
   int rc = ctx->ensure_arena(need);
   if (rc) return rc;
 
@@ -379,7 +385,7 @@ int agpc_score_batch_dev(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, con
     off[nb] = row_off[first + nb];
     np = (int)align_up((size_t)np, TILE);
     Chunk c;
-    c.carve((char*)ctx->arena, nb, np, ds.D, theta_stride, false);
+    c.carve((char*)ctx->arena, nb, np, ds.D, theta_stride, false, ctx->oz_S);
     if (c.make_maps()) return fail(ctx, AGPC_E_CUDA, "cuTensorMapEncodeTiled failed");
     const int tb = 256;
     dim3 gvec((np + tb - 1) / tb, nb);
@@ -565,11 +571,12 @@ static int predict_impl(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, cons
   }
   if (n_max <= 0 || m_max <= 0 || site_stride < n_max) return fail(ctx, AGPC_E_ARG, "predict_batch: bad sizes");
   const int np_all = (int)align_up((size_t)n_max, TILE), mp_all = (int)align_up((size_t)m_max, TILE);
-  const size_t extra_item = sizeof(double) * ((size_t)2 * mp_all * np_all + (size_t)mp_all * (ds.D + 6)) + sizeof(int) * (size_t)(mp_all + np_all) + 16384;
-  const size_t per_item = per_item_bytes(np_all, ds.D, theta_stride) + extra_item;
+  const size_t extra_item = sizeof(double) * ((size_t)2 * mp_all * np_all + (size_t)mp_all * (ds.D + 6)) + sizeof(int) * (size_t)(mp_all + np_all) +
+                            sizeof(double) * (size_t)site_stride + 16384;
+  const size_t per_item = per_item_bytes(np_all, ds.D, theta_stride, 0) + extra_item;
   const size_t budget = ctx->workspace_budget();
   if (per_item > budget) return fail(ctx, AGPC_E_NOMEM, "predict_batch: one item does not fit the workspace budget");
-  const int chunk_cap = (int)std::min<size_t>((size_t)n_items, std::max<size_t>(1, budget / per_item));
+  const int chunk_cap = std::min((int)std::min<size_t>((size_t)n_items, std::max<size_t>(1, budget / per_item)), 65535);
   int rc = ctx->ensure_arena(per_item * chunk_cap + (1 << 20));
   if (rc) return rc;
 
@@ -591,7 +598,7 @@ static int predict_impl(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, cons
     np = (int)align_up((size_t)np, TILE);
     mp = (int)align_up((size_t)mp, TILE);
     Chunk c;
-    const size_t used = c.carve((char*)ctx->arena, nb, np, ds.D, theta_stride, true);
+    const size_t used = c.carve((char*)ctx->arena, nb, np, ds.D, theta_stride, true, 0);
     Carver x{(char*)ctx->arena};
     x.off = used;
     double* Ks = x.take<double>((size_t)nb * mp * np);

@@ -210,7 +210,8 @@ class Engine:
                                                  vp(stream)))
 
     # ---- per-launch event timing (bench.py roofline) ----
-    CLASSES = ("kbuild", "gemm_potrf", "potf2", "matvec", "ep", "grad", "formB", "misc", "gemm_trtri", "gemm_lauum")
+    CLASSES = ("kbuild", "gemm_potrf", "potf2", "matvec", "ep", "grad", "formB", "misc", "gemm_trtri", "gemm_lauum",
+               "slice")
 
     def profile_enable(self, on: bool = True):
         self._check(self._L.agpc_profile_enable(self._ctx, 1 if on else 0))
@@ -302,6 +303,14 @@ class Engine:
         self._check(self._L.agpc_gemm_nt(self._ctx, C.c_void_p(A_ptr), C.c_void_p(B_ptr), C.c_void_p(C_ptr), M, N, K,
                                          C.c_double(alpha), C.c_double(beta), batch,
                                          C.c_void_p(stream) if stream else None))
+
+
+    def gemm_nt_i8x(self, A_ptr: int, B_ptr: int, C_ptr: int, M: int, N: int, K: int, alpha=1.0, beta=0.0, batch=1,
+                    n_slices: int = 7, stream: int = 0):
+        """``agpc_gemm_nt_i8x``: the same product through int8 digit slices on tcgen05 (csrc/ozaki.cu)."""
+        self._check(self._L.agpc_gemm_nt_i8x(self._ctx, C.c_void_p(A_ptr), C.c_void_p(B_ptr), C.c_void_p(C_ptr), M, N, K,
+                                             C.c_double(alpha), C.c_double(beta), batch, n_slices,
+                                             C.c_void_p(stream) if stream else None))
 
 
 _default: Optional[Engine] = None

@@ -114,7 +114,8 @@ int64_t agpc_launch_count(agpc_ctx* ctx);
 #define AGPC_CLS_MISC 7
 #define AGPC_CLS_GEMM_TRTRI 8 /* the tile GEMM inside trtri (AGPC_CLS_GEMM: inside potrf / predict) */
 #define AGPC_CLS_GEMM_LAUUM 9 /* ... inside lauum */
-#define AGPC_CLS_COUNT 10
+#define AGPC_CLS_SLICE 10     /* operand slicing for the int8 tensor-core GEMM (bytes of FP64 read) */
+#define AGPC_CLS_COUNT 11
 int agpc_profile_enable(agpc_ctx* ctx, int32_t on);
 int agpc_profile_read(agpc_ctx* ctx, double* ms, double* work, int64_t* launches);
 
@@ -179,6 +180,14 @@ int agpc_potrf(agpc_ctx* ctx, double* A_dev, int32_t n, int32_t batch, double* M
 /* C = alpha * A * B^T + beta * C on the TMA + DMMA tile kernel (M, N % 128 == 0, K % 16 == 0, contiguous) */
 int agpc_gemm_nt(agpc_ctx* ctx, const double* A_dev, const double* B_dev, double* C_dev, int32_t M, int32_t N,
                  int32_t K, double alpha, double beta, int32_t batch, void* stream);
+
+/* The same product on the Blackwell tensor core proper (tcgen05.mma kind::i8, accumulators in TMEM): both operands are
+ * cut into n_slices (6 or 7) signed 8-bit digit planes with one power-of-two scale per row, the integer products are
+ * accumulated exactly in int32 and recombined in FP64 (csrc/ozaki.cu).  n_slices = 7 is accurate to the FP64 rounding
+ * level of a DGEMM, 6 to ~1e-12 of |a_i|max |b_j|max K^1/2.  M, N % 128 == 0, K % 32 == 0, contiguous.  This is the
+ * kernel behind the K = 512 trailing updates of agpc_potrf, the upper levels of its triangular inverse and lauum. */
+int agpc_gemm_nt_i8x(agpc_ctx* ctx, const double* A_dev, const double* B_dev, double* C_dev, int32_t M, int32_t N,
+                     int32_t K, double alpha, double beta, int32_t batch, int32_t n_slices, void* stream);
 
 #ifdef __cplusplus
 }

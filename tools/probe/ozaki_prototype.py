@@ -1,15 +1,21 @@
-"""CPU prototype (NumPy, no GPU): how many 7-bit integer slices does an Ozaki-style emulation of the FP64 tile GEMM need
-before the blocked Cholesky of B = I + S^1/2 K S^1/2 keeps this engine's parity bar?
+"""CPU prototype (NumPy, no GPU) of the sliced-integer FP64 GEMM behind csrc/ozaki.cu: how many 8-bit signed-digit
+slices does the emulation need before potrf / trtri / lauum of B = I + S^1/2 K S^1/2 keep this engine's parity bar
+(NLML 1e-9, gradients 1e-7 relative)?
 
-Scheme (error-free operand slicing, one power-of-two scale per row): a row of A is scaled into (-1, 1) by 2^-e_i and cut
-into `s` signed slices of BETA = 7 bits (int8 range); A ~= sum_p 2^(e_i - BETA (p+1)) S_p.  A B^T is then the sum of the
-INTEGER products S_p^A (S_q^B)^T with p + q < s (exact in int32 for K <= 133 k), rescaled and accumulated in FP64 --
-s (s + 1) / 2 int8 GEMMs per DGEMM.  Here the integer products are formed in float64 on integer-valued arrays (exact),
-so the arithmetic is the one tcgen05 kind::i8 would perform.
+Scheme -- exactly what the slicing kernel does on the device:
+  * one power-of-two scale per operand row: e_i with |a_ik| 2^-e_i < 1/4 for every k of the row;
+  * X_ik = rint(a_ik 2^(8 s - e_i)) as a 64-bit integer (exact for the entries within 2^-(8s-53) of the row scale),
+    cut into s signed bytes d_0 (most significant) ... d_(s-1) by the carry-propagating split
+    d = ((X + 128) & 255) - 128, X = (X - d) >> 8   -- round-to-nearest digits, so the truncation error of the product
+    is unbiased (the round-1 prototype truncated toward zero: 7 bits per slice and a systematic bias);
+  * A B^T = 2^(ea_i + eb_j) sum_{p+q < s} 2^(-8 (p + q + 2)) D_p^A (D_q^B)^T: s (s + 1) / 2 int8 GEMMs whose products of
+    equal weight p + q share one int32 accumulator (|.| <= 2^14 K (p+q+1): exact for K < 18 k), then one FP64 Horner
+    pass over the s accumulators.
+Integer products are formed in float64 on integer-valued arrays (exact), i.e. the arithmetic tcgen05 kind::i8 performs.
 
-The trailing updates of a right-looking blocked Cholesky (128-column panels; panel factorisation and solve in native
-FP64, as the design keeps them) are run through that GEMM and compared with LAPACK: relative error of L, of log det B and
-of a solve -- for s = 4 ... 8.  Usage: python tools/probe/ozaki_prototype.py [n]
+The three GEMM-shaped phases of one posterior evaluation are run through that GEMM -- right-looking blocked Cholesky
+(panel factorisation and solve stay native FP64, as in csrc/chol.cu), L^-1 by recursive doubling, B^-1 = L^-T L^-1 --
+and compared with LAPACK.   Usage: python tools/probe/ozaki_prototype.py [n]
 """
 import os
 import sys
@@ -21,47 +27,72 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 from oracle import gpc_oracle as orc  # noqa: E402
 from tests.util import random_theta, synth  # noqa: E402
 
-BETA = 7
-
 
 def slices(A, s):
-    """Row-scaled error-free slicing: returns (list of integer-valued float arrays, exponent vector e)."""
+    """Row-scaled signed-digit slicing: (list of s integer-valued float arrays in [-128, 127], exponent vector e)."""
     amax = np.max(np.abs(A), axis=1)
-    e = np.where(amax > 0, np.ceil(np.log2(np.where(amax > 0, amax, 1.0))) + 1, 0.0)
-    R = A * np.exp2(-e)[:, None]                 # |R| < 1/2: exact (power-of-two scaling)
+    _, ex = np.frexp(amax)                      # amax = m 2^ex, m in [0.5, 1)
+    e = np.where(amax > 0, ex + 2, 0).astype(np.int64)   # |a| 2^-e < 1/4
+    X = np.rint(np.ldexp(A, (8 * s - e)[:, None].astype(np.int32))).astype(np.int64)
     out = []
     for _ in range(s):
-        R = R * (1 << BETA)
-        S = np.trunc(R)                          # |S| <= 2^(BETA-1) = 64 fits int8; remainder keeps the sign
-        out.append(S)
-        R = R - S                                # exact
-    return out, e
+        d = ((X + 128) & 255) - 128
+        out.append(d.astype(np.float64))
+        X = (X - d) >> 8
+    assert np.all(X == 0), "top digit overflow"
+    return out[::-1], e
 
 
 def gemm_nt_emulated(A, B, s):
-    """A @ B.T with s slices per operand, integer products for p + q < s."""
-    SA, ea = slices(A, s)
-    SB, eb = slices(B, s)
-    C = np.zeros((A.shape[0], B.shape[0]))
-    for d in range(s):                           # d = p + q, smallest contributions first
-        dd = s - 1 - d
-        acc = np.zeros_like(C)
-        for p in range(dd + 1):
-            acc += SA[p] @ SB[dd - p].T          # integer-valued, exact in FP64 (and in int32 on the tensor core)
-        C += acc * 2.0 ** (-BETA * (dd + 2))
-    return C * np.exp2(ea)[:, None] * np.exp2(eb)[None, :]
+    """A @ B.T with s slices per operand, integer products for p + q < s, Horner accumulation from the smallest weight."""
+    DA, ea = slices(A, s)
+    DB, eb = slices(B, s)
+    acc = np.zeros((A.shape[0], B.shape[0]))
+    for d in range(s - 1, -1, -1):
+        g = np.zeros_like(acc)
+        for p in range(d + 1):
+            g += DA[p] @ DB[d - p].T            # integer-valued, exact (int32 on the tensor core)
+        acc = acc * 2.0 ** -8 + g
+    return np.ldexp(acc, (ea[:, None] + eb[None, :] - 16).astype(np.int32))
 
 
-def blocked_cholesky(A, nb, gemm):
+def blocked_cholesky(A, nb, gemm, outer=4):
+    """Two-level right-looking Cholesky as chol.cu: panels of nb inside outer blocks (native FP64), K = outer*nb
+    trailing updates through `gemm`."""
     A = A.copy()
     n = A.shape[0]
+    for k0 in range(0, n, nb * outer):
+        e0 = min(k0 + nb * outer, n)
+        for k in range(k0, e0, nb):
+            e = min(k + nb, n)
+            if k > k0:
+                A[k:, k:e] -= A[k:, k0:k] @ A[k:e, k0:k].T
+            A[k:e, k:e] = sla.cholesky(A[k:e, k:e], lower=True)
+            if e < n:
+                A[e:, k:e] = sla.solve_triangular(A[k:e, k:e], A[e:, k:e].T, lower=True).T
+        if e0 < n:
+            A[e0:, e0:] -= gemm(A[e0:, k0:e0], A[e0:, k0:e0])
+    return np.tril(A)
+
+
+def trtri_doubling(L, nb, gemm):
+    """M = L^-1 by recursive doubling (chol.cu trtri_blocked): M21 = -M22 (L21 M11)."""
+    n = L.shape[0]
+    M = np.zeros_like(L)
     for k in range(0, n, nb):
         e = min(k + nb, n)
-        A[k:e, k:e] = sla.cholesky(A[k:e, k:e], lower=True)
-        if e < n:
-            A[e:, k:e] = sla.solve_triangular(A[k:e, k:e], A[e:, k:e].T, lower=True).T
-            A[e:, e:] -= gemm(A[e:, k:e], A[e:, k:e])
-    return np.tril(A)
+        M[k:e, k:e] = sla.solve_triangular(L[k:e, k:e], np.eye(e - k), lower=True)
+    h = nb
+    while h < n:
+        for g0 in range(0, n, 2 * h):
+            m = min(g0 + h, n)
+            e = min(g0 + 2 * h, n)
+            if m >= e:
+                continue
+            T = gemm(M[g0:m, g0:m].T, L[m:e, g0:m])           # U11 L21^T  (h1 x h2)
+            M[m:e, g0:m] = -gemm(M[m:e, m:e], T)               # M22 T^T
+        h *= 2
+    return M
 
 
 if __name__ == "__main__":
@@ -74,15 +105,17 @@ if __name__ == "__main__":
     sq = np.sqrt(ep.tau_t)
     Bm = np.eye(n) + sq[:, None] * K * sq[None, :]
     L_ref = sla.cholesky(Bm, lower=True)
-    rhs = np.random.default_rng(2).standard_normal(n)
-    x_ref = sla.cho_solve((L_ref, True), rhs)
+    Binv_ref = sla.cho_solve((L_ref, True), np.eye(n))
+    ld_ref = 2 * np.sum(np.log(np.diag(L_ref)))
     print("n = %d, cond(B) = %.2e, EP sweeps %d" % (n, np.linalg.cond(Bm), ep.sweeps))
-    L_nat = blocked_cholesky(Bm, 128, lambda a, b: a @ b.T)
-    print("native FP64 blocked:   |L - L_ref| / |L_ref| = %.2e" % (np.abs(L_nat - L_ref).max() / np.abs(L_ref).max()))
-    for s in range(4, 9):
-        L = blocked_cholesky(Bm, 128, lambda a, b: gemm_nt_emulated(a, b, s))
-        x = sla.cho_solve((L, True), rhs)
-        ld, ld_ref = 2 * np.sum(np.log(np.diag(L))), 2 * np.sum(np.log(np.diag(L_ref)))
-        print("s = %d (%2d int8 GEMMs): max|L - L_ref| / max|L_ref| = %.2e   |logdet diff| / |logdet| = %.2e   "
-              "solve rel err = %.2e" % (s, s * (s + 1) // 2, np.abs(L - L_ref).max() / np.abs(L_ref).max(),
-                                        abs(ld - ld_ref) / abs(ld_ref), np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref)))
+    nat = lambda a, b: a @ b.T
+    for name, gemm in [("native FP64", nat)] + [("s = %d (%2d int8 GEMMs)" % (s, s * (s + 1) // 2),
+                                                 (lambda s_: (lambda a, b: gemm_nt_emulated(a, b, s_)))(s))
+                                                for s in range(4, 9)]:
+        L = blocked_cholesky(Bm, 128, gemm)
+        M = trtri_doubling(L, 128, gemm)
+        Binv = gemm(M.T, M.T)
+        ld = 2 * np.sum(np.log(np.diag(L)))
+        print("%-24s max|L-Lref|/max|L| = %.2e  |logdet diff|/|logdet| = %.2e  max|ML-I| = %.2e  max|Binv-ref|/max|Binv| = %.2e"
+              % (name, np.abs(L - L_ref).max() / np.abs(L_ref).max(), abs(ld - ld_ref) / abs(ld_ref),
+                 np.abs(M @ L - np.eye(n)).max(), np.abs(Binv - Binv_ref).max() / np.abs(Binv_ref).max()))
