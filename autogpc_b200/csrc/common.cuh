@@ -40,8 +40,9 @@ struct GemmArgs {
 
 // Kernel classes of the optional per-launch event timing (agpc_profile_*): bench.py's roofline and the share table.
 enum : int { CLS_KBUILD = 0, CLS_GEMM, CLS_POTF2, CLS_MATVEC, CLS_EP, CLS_GRAD, CLS_FORMB, CLS_MISC, CLS_GEMM_TRTRI, CLS_GEMM_LAUUM,
-              CLS_SLICE, CLS_COUNT };  // CLS_GEMM = the tile GEMM inside potrf (and predict); _TRTRI / _LAUUM = the same kernel in
-                                       // those phases; CLS_SLICE = operand slicing for the int8 tensor-core GEMM (ozaki.cu)
+              CLS_SLICE, CLS_OZ_POTRF, CLS_OZ_TRTRI, CLS_OZ_LAUUM, CLS_COUNT };  // CLS_GEMM = the tile GEMM inside potrf (and predict); _TRTRI / _LAUUM = the same kernel in
+                                       // those phases; CLS_SLICE = operand slicing for the int8 tensor-core GEMM (ozaki.cu);
+                                       // CLS_OZ_* = that GEMM per phase: event time, work = EXECUTED int8 operations (2 x MACs)
 
 // When enabled, every launcher brackets its kernel with a cudaEvent pair on the launching stream; the pairs are
 // summed per class by agpc_profile_read.  `work` is the ALGORITHMIC work the drivers attribute to a class

@@ -282,9 +282,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzGemmA
 
 // ---- slicing: FP64 region -> S int8 digit tiles (shared-memory image) + one scale per row --------------------------
 // One CTA per 128-row block of the region.  Pass 1: row maxima over the K range (8 warps x 16 rows, coalesced row reads)
-// -> e_i, 2^(8S - e_i) kept in shared memory, 2^(e_i - 8) written out for the GEMM epilogue.  Pass 2: per K chunk one
-// (row, 16-byte chunk) unit per thread: 16 doubles in, X = rint(a 2^(8S-e)) as int64, bytes of (X + BIAS) ^ BIAS are the
-// signed digits, gathered by PRMT into one 16-byte store per slice -- a warp writes 512 contiguous bytes per slice.
+// -> e_i, 2^(8S - e_i) kept in shared memory, 2^(e_i - 8) written out for the GEMM epilogue.  Pass 2: per K chunk every
+// thread converts 4 x 4 elements: X = rint(a 2^(8S-e)) as int64, bytes of (X + BIAS) ^ BIAS are the signed digits,
+// gathered by PRMT into one 32-bit word per slice.
 template <int S>
 __global__ void __launch_bounds__(256) ozaki_slice_kernel(const OzSliceArgs a) {
   constexpr int CPB = TILE / OZ_KB;
@@ -310,14 +310,25 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const OzSliceArgs a) {
   for (int rr = 0; rr < 16; ++rr) {
     const int r = warp * 16 + rr;
     const double* p = Xb + (long long)(row_base + r) * a.ld + col_base;
-    double amax = 0.0;
+    double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;  // four independent chains: the loads of a row are all in flight
     int bad = 0;
-    for (int c = c_lo * OZ_KB + 2 * lane; c < c_hi * OZ_KB; c += 64) {
-      const double2 v = *reinterpret_cast<const double2*>(p + c);
-      const double m = fmax(fabs(v.x), fabs(v.y));
-      bad |= !(fabs(v.x) <= 1.7976931348623157e308) | !(fabs(v.y) <= 1.7976931348623157e308);
-      amax = fmax(amax, m);
+    const int c_end = c_hi * OZ_KB;
+    int c = c_lo * OZ_KB + 2 * lane;
+    for (; c + 192 < c_end; c += 256) {
+      const double2 v0 = *reinterpret_cast<const double2*>(p + c), v1 = *reinterpret_cast<const double2*>(p + c + 64);
+      const double2 v2 = *reinterpret_cast<const double2*>(p + c + 128), v3 = *reinterpret_cast<const double2*>(p + c + 192);
+      m0 = fmax(m0, fmax(fabs(v0.x), fabs(v0.y)));
+      m1 = fmax(m1, fmax(fabs(v1.x), fabs(v1.y)));
+      m2 = fmax(m2, fmax(fabs(v2.x), fabs(v2.y)));
+      m3 = fmax(m3, fmax(fabs(v3.x), fabs(v3.y)));
+      bad |= !(fabs(v0.x) + fabs(v0.y) + fabs(v1.x) + fabs(v1.y) + fabs(v2.x) + fabs(v2.y) + fabs(v3.x) + fabs(v3.y) <= 1.7976931348623157e308);
     }
+    for (; c < c_end; c += 64) {
+      const double2 v = *reinterpret_cast<const double2*>(p + c);
+      m0 = fmax(m0, fmax(fabs(v.x), fabs(v.y)));
+      bad |= !(fabs(v.x) + fabs(v.y) <= 1.7976931348623157e308);
+    }
+    double amax = fmax(fmax(m0, m1), fmax(m2, m3));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
@@ -335,39 +346,45 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const OzSliceArgs a) {
     }
   }
   __syncthreads();
+  // pass 2.  A warp takes 4 rows x 32 columns per step: lane l -> row l / 8, columns 4 (l % 8) .. + 4 (32 contiguous
+  // bytes in, 256 contiguous bytes per row); it writes ONE 32-bit word per slice, so a warp store is 128 contiguous
+  // bytes of the tile image (the 32-byte swizzle only permutes 16-byte chunks inside such a block).
   constexpr unsigned long long BIAS = S == 7 ? 0x0080808080808080ull : S == 6 ? 0x0000808080808080ull : 0x8080808080808080ull;
-  const int r = tid >> 1, c16 = tid & 1;
-  const double mult = s_mult[r];
-  const double* src = Xb + (long long)(row_base + r) * a.ld + col_base + c16 * 16;
-  int8_t* tile0 = a.S + (long long)b * a.s_batch +
-                  ((long long)(row_base >> 7) * a.nkc + (col_base / OZ_KB)) * (S * (long long)(TILE * OZ_KB)) + oz_swz(r, c16 * 16);
+  const int lr = lane >> 3, lc = (lane & 7) * 4;
+  int8_t* tiles = a.S + (long long)b * a.s_batch +
+                  ((long long)(row_base >> 7) * a.nkc + (col_base / OZ_KB)) * (S * (long long)(TILE * OZ_KB));
   for (int kc = c_lo; kc < c_hi; ++kc) {
-    uint32_t w[S][4];
+    double2 v[4][2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const double2 v0 = *reinterpret_cast<const double2*>(src + kc * OZ_KB + 4 * j);
-      const double2 v1 = *reinterpret_cast<const double2*>(src + kc * OZ_KB + 4 * j + 2);
-      const double x[4] = {v0.x, v0.y, v1.x, v1.y};
+    for (int i = 0; i < 4; ++i) {
+      const int r = warp * 16 + i * 4 + lr;
+      const double* src = Xb + (long long)(row_base + r) * a.ld + col_base + kc * OZ_KB + lc;
+      v[i][0] = *reinterpret_cast<const double2*>(src);
+      v[i][1] = *reinterpret_cast<const double2*>(src + 2);
+    }
+    int8_t* dst = tiles + (long long)kc * (S * (long long)(TILE * OZ_KB));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = warp * 16 + i * 4 + lr;
+      const double mult = s_mult[r];
+      const double x[4] = {v[i][0].x, v[i][0].y, v[i][1].x, v[i][1].y};
       uint32_t lo[4], hi[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const unsigned long long z = ((unsigned long long)__double2ll_rn(x[i] * mult) + BIAS) ^ BIAS;
-        lo[i] = (uint32_t)z;
-        hi[i] = (uint32_t)(z >> 32);
+      for (int e = 0; e < 4; ++e) {
+        const unsigned long long z = ((unsigned long long)__double2ll_rn(x[e] * mult) + BIAS) ^ BIAS;
+        lo[e] = (uint32_t)z;
+        hi[e] = (uint32_t)(z >> 32);
       }
+      const uint32_t off = oz_swz(r, lc);
 #pragma unroll
       for (int p = 0; p < S; ++p) {
         const int k = S - 1 - p;  // byte k of z is digit p (p = 0 most significant)
         const uint32_t* srcw = k < 4 ? lo : hi;
         const uint32_t sel = (uint32_t)(k & 3) | ((uint32_t)(4 + (k & 3)) << 4);
         const uint32_t t0 = __byte_perm(srcw[0], srcw[1], sel), t1 = __byte_perm(srcw[2], srcw[3], sel);
-        w[p][j] = __byte_perm(t0, t1, 0x5410);
+        *reinterpret_cast<uint32_t*>(dst + p * (TILE * OZ_KB) + off) = __byte_perm(t0, t1, 0x5410);
       }
     }
-    int8_t* dst = tile0 + (long long)kc * (S * (long long)(TILE * OZ_KB));
-#pragma unroll
-    for (int p = 0; p < S; ++p)
-      *reinterpret_cast<uint4*>(dst + p * (TILE * OZ_KB)) = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
   }
 }
 
@@ -384,9 +401,42 @@ static cudaError_t oz_gemm_launch_t(const Launch& L, const OzGemmArgs& a, int ti
   return cudaGetLastError();
 }
 
+// int8 MACs one launch executes per batch item: the kernel's own tile / K-range rules, evaluated on the host
+static double oz_executed_macs(const OzGemmArgs& a, int tiles128, int groups, int S) {
+  constexpr int CPB = TILE / OZ_KB;
+  double chunks = 0.0;  // sum over 128 x 64 tiles of their K chunks
+  for (int g = 0; g < groups; ++g) {
+    int h2 = 0;
+    if (a.grp_blocks > 0) {
+      h2 = a.nblk - g * a.grp_blocks - a.half_blocks;
+      h2 = h2 < 0 ? 0 : (h2 > a.half_blocks ? a.half_blocks : h2);
+    }
+    const int mt = a.m_kind == EXT_H2 ? h2 : a.m_tiles, nt = a.n_kind == EXT_H2 ? h2 : a.n_tiles;
+    const int kt = a.k_kind == EXT_H2 ? h2 * CPB : a.k_chunks;
+    if (mt <= 0 || nt <= 0) continue;
+    for (int ti = 0; ti < mt; ++ti) {
+      const int tj_end = a.lower_only ? ti + 1 : (a.skip_upper ? (ti + 1 < nt ? ti + 1 : nt) : nt);
+      if (!a.lower_only && ti * nt >= tiles128) break;
+      for (int tj = 0; tj < tj_end; ++tj)
+        for (int half = 0; half < 2; ++half) {
+          int kb = 0, ke = kt;
+          if (a.k_rule == KRULE_BEGIN_AT_ROW) kb = ti * CPB;
+          if (a.k_rule == KRULE_END_AT_ROW) ke = ke < (ti + 1) * CPB ? ke : (ti + 1) * CPB;
+          if (a.k_rule == KRULE_END_AT_COL) ke = ke < (2 * tj + half + 1) * (OZ_BN / OZ_KB) ? ke : (2 * tj + half + 1) * (OZ_BN / OZ_KB);
+          if (ke > kb) chunks += ke - kb;
+        }
+    }
+  }
+  return chunks * (S * (S + 1) / 2) * (double)TILE * OZ_BN * OZ_KB;
+}
+
 cudaError_t oz_gemm_launch(const Launch& L, const OzGemmArgs& a, int tiles128, int groups, int batch, int S) {
   ProfScope prof_scope(L, L.gemm_cls);
+  const int oz_cls = L.gemm_cls == CLS_GEMM_TRTRI ? CLS_OZ_TRTRI : L.gemm_cls == CLS_GEMM_LAUUM ? CLS_OZ_LAUUM : CLS_OZ_POTRF;
+  ProfScope oz_scope(L, oz_cls);
   if (tiles128 <= 0 || groups <= 0 || batch <= 0) return cudaSuccess;
+  if (L.prof && L.prof->enabled)
+    L.add_work(oz_cls, 2.0 * oz_executed_macs(a, tiles128, groups, S) * (a.active ? (double)(L.work_items < batch ? L.work_items : batch) : (double)batch));
   L.bump();
   return S == 6 ? oz_gemm_launch_t<6>(L, a, tiles128, groups, batch) : oz_gemm_launch_t<7>(L, a, tiles128, groups, batch);
 }

@@ -211,7 +211,7 @@ class Engine:
 
     # ---- per-launch event timing (bench.py roofline) ----
     CLASSES = ("kbuild", "gemm_potrf", "potf2", "matvec", "ep", "grad", "formB", "misc", "gemm_trtri", "gemm_lauum",
-               "slice")
+               "slice", "oz_potrf", "oz_trtri", "oz_lauum")
 
     def profile_enable(self, on: bool = True):
         self._check(self._L.agpc_profile_enable(self._ctx, 1 if on else 0))
@@ -224,6 +224,9 @@ class Engine:
         # "gemm" = the tile GEMM over all three phases (the phases never overlap in time: a plain sum is the union)
         parts = [out[k] for k in ("gemm_potrf", "gemm_trtri", "gemm_lauum")]
         out["gemm"] = {k: sum(p[k] for p in parts) for k in ("ms", "work", "launches")}
+        # the int8 tensor-core GEMM (csrc/ozaki.cu) over the three phases: event time, launches, EXECUTED int8 operations
+        parts = [out[k] for k in ("oz_potrf", "oz_trtri", "oz_lauum")]
+        out["oz_gemm"] = {k: sum(p[k] for p in parts) for k in ("ms", "work", "launches")}
         return out
 
     def predict_batch(self, dataset: int, programs: Sequence[Program], thetas: Sequence[np.ndarray],

@@ -295,8 +295,9 @@ def cumulateAdditiveKernels(summands: List[GPCKernel]):
 
 def train_kernels(kernels: List[GPCKernel], mode="auto", n_folds=5, max_evals=1000, shard=None):
     """``for k in kernels: k.train()`` (gpcsearch.py:44-45) as ONE lock-step optimisation over every
-    (candidate, fold) item.  With ``shard=(rank, world)`` this rank optimises only items ``i % world == rank``
-    and results are exchanged with one all-gather (autogpc_b200/sharding.py)."""
+    (candidate, fold) item.  With ``shard=(rank, world)`` this rank optimises only its share of the items -- dealt by
+    estimated cost, longest first (``sharding.deal_items``) -- and results are exchanged with one all-gather
+    (autogpc_b200/sharding.py)."""
     mode = mode.lower()
     assert mode in ("full", "svgp", "auto"), "mode must be 'full', 'svgp' or 'auto'"
     assert n_folds is None or (isinstance(n_folds, int) and n_folds > 0), "n_folds must be None or positive integer"
@@ -334,8 +335,14 @@ def train_kernels(kernels: List[GPCKernel], mode="auto", n_folds=5, max_evals=10
     if shard is None:
         mine = list(range(len(items)))
     else:
+        from . import sharding
         rank, world = shard
-        mine = [i for i in range(len(items)) if i % world == rank]
+        costs = []
+        for _, _, m in items:
+            prog = m._program
+            types = [prog.leaf_type[l] for l in range(prog.n_leaves)]
+            costs.append(sharding.item_cost(len(m._rows), prog.n_leaves, sum(1 for t in types if t == 1)))
+        mine = sharding.shard_indices(len(items), rank, world, costs)
     my_models = [items[i][2] for i in mine]
     if my_models:
         optim.optimize_models(my_models, max_evals=max_evals)

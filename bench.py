@@ -213,6 +213,21 @@ def oracle_item_seconds(data, folds, item):
     return time.perf_counter() - t, o
 
 
+def host_cores():
+    """Host cores this process may run on (the BLAS pool is sized to this, whatever OMP_NUM_THREADS says)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def all_host_threads():
+    """Context manager: BLAS / LAPACK pools of the CPU arm on every core of the box.  torchrun exports
+    OMP_NUM_THREADS=1 to its workers, which would otherwise pin the oracle to ONE thread (round-1 SCALE record)."""
+    from threadpoolctl import threadpool_limits
+    return threadpool_limits(limits=host_cores())
+
+
 def host_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -228,13 +243,14 @@ def run_reference(args, rank, world):
         return
     data, cands, folds, items = build_workload(world, args.cands, args.points)
     times = []
-    for s in range(args.warmup + args.steps):
-        dt, _ = oracle_item_seconds(data, folds, items[s % len(items)])
-        if s >= args.warmup:
-            times.append(dt)
+    with all_host_threads():
+        for s in range(args.warmup + args.steps):
+            dt, _ = oracle_item_seconds(data, folds, items[s % len(items)])
+            if s >= args.warmup:
+                times.append(dt)
+        cores = host_threads()
     total = float(np.sum(times))
     value = (len(times) / N_FOLDS) / total
-    cores = host_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
@@ -256,7 +272,9 @@ def workload_config(args, world, n_items):
                         "evaluation (K build, parallel EP eps=1e-6, FP64 potrf+trtri per sweep, logZ, gradient, BIC)"
                         % (args.points, args.points - args.points // N_FOLDS),
             "candidates_per_gpu": args.cands, "folds": N_FOLDS, "items_total": n_items,
-            "parallelism": "items sharded round-robin over %d GPU(s); all-gather of (score, theta) records per step" % world,
+            "parallelism": ("one lock-step batch on 1 GPU" if world == 1 else
+                            "chunks of %d items claimed dynamically by %d GPUs from a shared counter; one all-gather of "
+                            "(score, theta) records per step" % (args.chunk, world)),
             "l2": "inputs larger than L2 (per-step working set >> 126 MB: %d x 5 n^2 FP64 matrices per rank)" % (args.cands * N_FOLDS)}
 
 
@@ -268,6 +286,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cands", type=int, default=8, help="candidate structures per GPU (x5 folds = items per step)")
     ap.add_argument("--points", type=int, default=N_POINTS)
+    ap.add_argument("--chunk", type=int, default=8, help="items per dynamically dealt chunk when N > 1")
+    ap.add_argument("--train-evals", type=int, default=50,
+                    help="objective-evaluation budget per fold of the train_e2e leg (SURVEY 8d: 5 x 50 = 250 per candidate); 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernels-only", action="store_true",
                     help="profiling aid (ncu passes): skip the DGEMM peak probe, the e2e leg and the CPU baseline")
@@ -306,14 +327,20 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     data, cands, folds, items = build_workload(world, args.cands, args.points)
-    mine = sharding.shard_indices(len(items), rank, world)
     eng = Engine(local_rank)
-    progs = [GPy.compile_program(items[i][2]) for i in mine]
-    thetas = [items[i][2].param_array for i in mine]
-    rows = [folds[items[i][1]][0] for i in mine]
-    B = len(mine)
+    n_items = len(items)
+    progs = [GPy.compile_program(it[2]) for it in items]
+    thetas = [it[2].param_array for it in items]
+    rows = [folds[it[1]][0] for it in items]
     stride = max(p.n_theta for p in progs)
     n_max = max(len(r) for r in rows)
+    # Work distribution.  One GPU: the rank's 40 items are ONE lock-step batch.  Several GPUs: the global item list is cut
+    # into chunks of `--chunk` consecutive items which the ranks CLAIM from a shared counter as they go
+    # (sharding.WorkQueue) -- a rank whose items converge in fewer EP sweeps simply takes more chunks, so nobody idles at
+    # the all-gather; every rank keeps the (small) inputs of ALL items resident so that any chunk can run anywhere.
+    G = n_items if world == 1 else max(1, args.chunk)
+    chunks = [(lo, min(lo + G, n_items)) for lo in range(0, n_items, G)]
+    B = n_items   # rows of the device tables
 
     # ---- device-resident inputs / outputs for `value` ----
     th_h = np.zeros((B, stride))
@@ -332,7 +359,7 @@ def main():
     gauss_d = torch.zeros_like(nlml_d)
     sweeps_d = torch.zeros(B, dtype=torch.int32, device=dev)
     status_d = torch.zeros(B, dtype=torch.int32, device=dev)
-    prog_arr = (Program * B)(*progs)
+    prog_arrs = [(Program * (hi - lo))(*progs[lo:hi]) for lo, hi in chunks]
     opt = EPOptions(1e-6, 0.0, 100, 0, 0, 0)   # damping 0 = the engine's automatic schedule (production default)
     did = eng.dataset(data.X, data.Y)
     # one explicit stream for torch, the timing events and the engine's launches (a NULL stream would make the engine use
@@ -340,21 +367,44 @@ def main():
     side = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(side)
     stream = side.cuda_stream
+    chunks_done_total = [0]
+    rank_busy_ms = []   # per step: this rank's time from the start of the step until its last chunk finished
 
-    def exchange(nlml_np, bic_np, status_np):
+    def exchange(done, nlml_np, bic_np, status_np):
+        """All-gather of the (score, theta) records of the chunks this rank processed."""
         if world == 1:
             return
-        local = np.zeros((B, sharding.RECORD_WIDTH))
-        for j, i in enumerate(mine):
-            local[j] = sharding.pack_record(i, nlml_np[j], bic_np[j], 0.0, int(status_np[j]), thetas[j])
-        sharding.allgather_records(local, len(items))
+        ids = [i for c in done for i in range(*chunks[c])]
+        local = np.zeros((len(ids), sharding.RECORD_WIDTH))
+        for j, i in enumerate(ids):
+            local[j] = sharding.pack_record(i, nlml_np[i], bic_np[i], 0.0, int(status_np[i]), thetas[i])
+        sharding.allgather_records(local, n_items, per_rank_max=n_items)
+
+    def claim_loop(run_chunk):
+        q = sharding.WorkQueue(len(chunks), tag="bench")
+        done = []
+        while True:
+            c = q.claim()
+            if c is None:
+                return done
+            run_chunk(c)
+            done.append(c)
+
+    def run_chunk_device(c):
+        lo, hi = chunks[c]
+        eng.score_batch_dev(did, prog_arrs[c], hi - lo, th_d[lo].data_ptr(), stride, rows_d.data_ptr(), row_off[lo:hi + 1].copy(),
+                            opt, tau_d[lo].data_ptr(), nu_d[lo].data_ptr(), n_max, nlml_d[lo:].data_ptr(),
+                            grad_d[lo].data_ptr(), bic_d[lo:].data_ptr(), gauss_d[lo:].data_ptr(), sweeps_d[lo:].data_ptr(),
+                            status_d[lo:].data_ptr(), stream)
 
     def step_device():
-        eng.score_batch_dev(did, prog_arr, B, th_d.data_ptr(), stride, rows_d.data_ptr(), row_off, opt,
-                            tau_d.data_ptr(), nu_d.data_ptr(), n_max, nlml_d.data_ptr(), grad_d.data_ptr(),
-                            bic_d.data_ptr(), gauss_d.data_ptr(), sweeps_d.data_ptr(), status_d.data_ptr(), stream)
+        t0 = time.perf_counter()
+        done = claim_loop(run_chunk_device)
+        chunks_done_total[0] += len(done)
         if world > 1:
-            exchange(nlml_d.cpu().numpy(), bic_d.cpu().numpy(), status_d.cpu().numpy())
+            torch.cuda.synchronize()
+            rank_busy_ms.append(1e3 * (time.perf_counter() - t0))
+            exchange(done, nlml_d.cpu().numpy(), bic_d.cpu().numpy(), status_d.cpu().numpy())
 
     def barrier():
         if world > 1:
@@ -373,13 +423,17 @@ def main():
     eng.profile_enable(True)   # resets the counters and re-uses the pool
     launches0 = eng.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     t_wall0 = time.time()
     e0.record()
-    for _ in range(args.steps):
+    step_ev[0].record()
+    for k in range(args.steps):
         step_device()
+        step_ev[k + 1].record()
     e1.record()
     barrier()
     t_wall1 = time.time()
+    ms_each = [step_ev[k].elapsed_time(step_ev[k + 1]) for k in range(args.steps)]
     clocks = None
     if sampler is not None:   # the samples of the timed region are in; stop nvidia-smi before the host-path leg
         clocks = sampler.window(t_wall0, t_wall1)
@@ -409,19 +463,28 @@ def main():
         t0 = time.perf_counter()
         d = eng.dataset(Xp, yp)
         t1 = time.perf_counter()
-        r = eng.score_batch(d, progs, thetas_p, rows_p, damping=0.0)
+        r = {"nlml": np.full(n_items, np.nan), "bic": np.full(n_items, np.nan), "status": np.zeros(n_items, dtype=np.int32)}
+
+        def run_chunk_host(c):
+            lo, hi = chunks[c]
+            rc = eng.score_batch(d, progs[lo:hi], thetas_p[lo:hi], rows_p[lo:hi], damping=0.0)
+            for k in r:
+                r[k][lo:hi] = rc[k]
+        done = claim_loop(run_chunk_host)
         t2 = time.perf_counter()
         eng.dataset_free(d)
         t3 = time.perf_counter()
-        exchange(r["nlml"], r["bic"], r["status"])
+        exchange(done, r["nlml"], r["bic"], r["status"])
+        r["done"] = done
         t4 = time.perf_counter()
         for k, v in zip(host_ms, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
             host_ms[k] += 1e3 * v
         return r
 
-    h2d = Xp.nbytes + yp.nbytes + B * stride * 8 + rows_cat.nbytes + B * 8 + B * 784
-    d2h = B * (8 * 3 + 4 * 2 + stride * 8) + 2 * B * n_max * 8
-    e2e_steps = max(1, min(args.steps, 3))
+    Bm = n_items // world   # items per rank and step (on average, with dynamic dealing)
+    h2d = Xp.nbytes + yp.nbytes + Bm * stride * 8 + rows_cat.nbytes // world + Bm * 8 + Bm * 784
+    d2h = Bm * (8 * 3 + 4 * 2 + stride * 8) + 2 * Bm * n_max * 8
+    e2e_steps = max(1, min(args.steps, 5))
     if args.kernels_only:
         if rank == 0:
             emit({"kernels_only": True, "ms_per_step": ms / args.steps, "gpu_launches": int(launches),
@@ -435,6 +498,10 @@ def main():
     barrier()
     for k in host_ms:
         host_ms[k] = 0.0
+    sampler2 = ClockSampler(local_rank) if rank == 0 else None
+    if sampler2 is not None:
+        time.sleep(0.3)
+    t_e2e0 = time.time()
     t0 = time.perf_counter()
     e2e_each = []
     for _ in range(e2e_steps):
@@ -443,19 +510,96 @@ def main():
         e2e_each.append(1e3 * (time.perf_counter() - t_s))
     barrier()
     e2e_s = time.perf_counter() - t0
+    e2e_clocks = sampler2.window(t_e2e0, time.time()) if sampler2 is not None else None
+    if sampler2 is not None:
+        sampler2.stop()
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = n_cands_total * e2e_steps / e2e_s
-    same = bool(np.allclose(r["nlml"], nlml_d.cpu().numpy(), rtol=1e-9, atol=0, equal_nan=True))
+    mine_ids = [i for c in r["done"] for i in range(*chunks[c])]
+    same = bool(np.allclose(r["nlml"][mine_ids], nlml_d.cpu().numpy()[mine_ids], rtol=1e-9, atol=0, equal_nan=True))
 
+
+    # ---- train_e2e (SURVEY 8d "candidate scored"): the SAME candidates through GPCKernel.train semantics -- 5 folds, one
+    #      random restart each, L-BFGS-B with a fixed budget of `--train-evals` objective evaluations per fold, warm-started
+    #      EP, held-out error by predict -- via the public API (gpckernel.train_kernels, the call GPCSearch.search makes).
+    train = None
+    if args.train_evals > 0:
+        from autogpc_b200 import engine as eng_mod
+        from autogpc_b200 import gpckernel as gk
+        eng_mod.set_default_engine(eng)
+        gk.set_rng(1)
+        l0 = eng.launches
+        barrier()
+        t0 = time.perf_counter()
+        gk.train_kernels(cands, mode="full", n_folds=N_FOLDS, max_evals=args.train_evals, shard=(rank, world) if world > 1 else None)
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        evals = sum(int(m.optimization_info.get("evals", 0)) for c in cands for m in getattr(c, "foldModels", [])
+                    if getattr(m, "optimization_info", None))
+        train = {"value": len(cands) / dt, "unit": UNIT, "seconds": dt, "evals_budget_per_fold": args.train_evals,
+                 "folds": N_FOLDS, "candidates": len(cands), "evaluations_this_rank": evals,
+                 "gpu_launches": int(eng.launches - l0),
+                 "ranking": [(c.kernel.structure(), round(float(c.bic()), 3), round(float(c.error()), 4))
+                             for c in sorted(cands, key=lambda k: (k.bic(), k.kernel.structure()))][:8],
+                 "note": "gpckernel.train_kernels(mode='full', n_folds=5, max_evals=%d): every (candidate, fold) model "
+                         "optimised in lock-step by L-BFGS-B from a random restart with warm-started EP, then predict on the "
+                         "held-out fold; host buffers, wall clock, max over ranks" % args.train_evals}
+
+    busy = None
+    if world > 1:
+        mine_ms = float(np.mean(rank_busy_ms[-args.steps:])) if rank_busy_ms else 0.0
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = mine_ms
+        dist.all_reduce(t)
+        busy = {"per_rank_ms_per_step": [round(x, 1) for x in t.tolist()], "min": float(t.min()), "max": float(t.max()),
+                "note": "time from the start of a step until the rank's last claimed chunk finished (device path, mean over "
+                        "the timed steps); the step ends with the all-gather, i.e. at the max"}
 
     if rank == 0:
         g = prof["gemm"]
-        total_kernel_ms = sum(v["ms"] for k, v in prof.items() if k != "gemm") or 1.0   # "gemm" is the sum of its phases
-        achieved = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+        oz = prof["oz_gemm"]
+        total_kernel_ms = sum(v["ms"] for k, v in prof.items() if k != "gemm" and not k.startswith("oz_")) or 1.0
+        fp64_eq = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
         chol_ms = g["ms"] + prof["potf2"]["ms"]
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        if oz["ms"] > 0.5 * g["ms"]:
+            # dominant kernel: the int8 tcgen05 GEMM.  achieved = int8 operations it EXECUTED (S(S+1)/2 integer MMAs per
+            # FP64 product, counted per launch from its tile / K-range rules) / its event time; peak = 2 x the measured
+            # dense bf16 rate (kind::i8 issues at twice the kind::f16 rate on tcgen05), sustained figure: the kernel runs
+            # inside a long step
+            bf16 = peaks.get("bf16_tflops_sustained") or 1400.0
+            peak = 2.0 * bf16
+            achieved = oz["work"] / (oz["ms"] * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "ozaki_gemm_kernel<S> (tcgen05.mma kind::i8, accumulators in TMEM, bulk-copy "
+                                                 "fed; sliced-integer FP64 GEMM behind potrf trailing updates, trtri, lauum)",
+                    "achieved": achieved, "peak": peak, "unit": "TOP/s (int8)", "frac": achieved / peak, "traffic": None,
+                    "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (%s); the same kernel's MMA loop on "
+                                   "resident operands sustains 4.4-4.5 POP/s at N >= 128 and 2.9 POP/s at its own N = 64 tile "
+                                   "(TMEM holds S x 64 accumulator columns), profiles/r02_i8mma_probe.txt"
+                                   % ("measured" if peaks else "fallback 1400"),
+                    "executed_int8_ops": oz["work"], "kernel_ms": oz["ms"], "launches": oz["launches"],
+                    "share_of_kernel_time": oz["ms"] / total_kernel_ms,
+                    "fp64_equivalent_tflops": fp64_eq,
+                    "fp64_equivalent_note": "algorithmic FP64 flops of potrf + trtri + lauum (n^3/3 each) / event time of ALL "
+                                            "tile-GEMM launches (int8 and DMMA); the FP64 DMMA pipe peaks at %.1f TFLOP/s "
+                                            "(cuBLAS DGEMM measured live)" % peak_sustained}
+        else:
+            roof = {"bound": "tensor", "kernel": "gemm_nt_kernel (TMA + FP64 DMMA; AGPC_OZAKI=0)", "achieved": fp64_eq,
+                    "peak": peak_sustained, "unit": "TFLOP/s", "frac": fp64_eq / peak_sustained if peak_sustained else None,
+                    "traffic": None, "peak_source": "cuBLAS DGEMM 8192^3 measured live (MEASURED_PEAKS.json has no FP64 entry)",
+                    "algorithmic_flops": g["work"], "kernel_ms": g["ms"], "launches": g["launches"],
+                    "share_of_kernel_time": g["ms"] / total_kernel_ms}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -463,26 +607,14 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "matches_device_path": same,
                     "host_ms_per_step": {k: v / e2e_steps for k, v in host_ms.items()},
-                    "ms_each_step": e2e_each},
+                    "ms_each_step": e2e_each, "clocks": e2e_clocks},
+            "ms_each_step": ms_each,
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "gemm_nt_kernel (TMA + FP64 DMMA; potrf trailing/panel updates, "
-                                                     "trtri, lauum)",
-                         "achieved": achieved, "peak": peak_sustained, "unit": "TFLOP/s",
-                         "frac": achieved / peak_sustained if peak_sustained else None, "traffic": None,
-                         "peak_source": "cuBLAS DGEMM 8192^3 measured live, sustained %.1f / burst %.1f TFLOP/s "
-                                        "(MEASURED_PEAKS.json has no FP64 entry; DMMA issue ceiling 37.1 TFLOP/s, "
-                                        "profiles/r01_fp64_peak.md)" % (peak_sustained, peak_burst),
-                         "traffic_ncu_example": {"launch": "K = 512 trailing update, grid (253,1,10) = 2530 tiles",
-                                                 "dram_bytes": 7.355e8, "algorithmic_bytes": 6.63e8,
-                                                 "dmma_pipe_pct_elapsed": 87.9,
-                                                 "source": "profiles/r01_gemm_nt_final_ncu_raw.csv (ncu --set full; the "
-                                                           "launches of a step differ in size, so no single per-launch "
-                                                           "figure is quoted in `traffic`)"},
-                         "algorithmic_flops": g["work"], "kernel_ms": g["ms"], "launches": g["launches"],
-                         "share_of_kernel_time": g["ms"] / total_kernel_ms},
+            "roofline": roof,
+            "fp64_dgemm_peak_tflops": {"sustained": peak_sustained, "burst": peak_burst},
             "cholesky": {"tflops": g["work"] / (chol_ms * 1e-3) / 1e12 if chol_ms > 0 else None,
-                         "note": "potrf+trtri+lauum algorithmic flops / (gemm_nt + potf2_inv) event time",
+                         "note": "potrf+trtri+lauum algorithmic flops / (tile GEMM + potf2_inv) event time",
                          "phases_tflops": {ph: (prof[k]["work"] / (((prof[k]["ms"] + (prof["potf2"]["ms"] if ph == "potrf" else 0.0))
                                                                    or 1.0) * 1e-3) / 1e12)
                                            for ph, k in (("potrf", "gemm_potrf"), ("trtri", "gemm_trtri"), ("lauum", "gemm_lauum"))},
@@ -490,20 +622,57 @@ def main():
                                         "so the sum overstates its wall time)"},
             "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
             "evals_per_s": len(items) * args.steps / (ms * 1e-3),
-            "ep_sweeps_mean": sweeps_mean, "items_ok": status_ok, "items_per_gpu": B,
+            "ep_sweeps_mean": sweeps_mean, "items_ok": status_ok, "items_per_gpu": n_items // world,
+            "chunks_this_rank_per_step": chunks_done_total[0] / float(args.warmup + args.steps),
+            "int8_slices": int(os.environ.get("AGPC_OZAKI", "7") or 0),
         }
+        if busy is not None:
+            line["rank_busy"] = busy
+        if train is not None:
+            line["train_e2e"] = train
         kb = prof["kbuild"]
         if kb["ms"] > 0:
             line["kbuild_gbs"] = kb["work"] / (kb["ms"] * 1e-3) / 1e9
+            line["kbuild_frac_of_hbm"] = line["kbuild_gbs"] / (peaks.get("hbm_gbs") or 6650.0)
+        sl = prof["slice"]
+        if sl["ms"] > 0:
+            line["slice_gbs_read"] = sl["work"] / (sl["ms"] * 1e-3) / 1e9
         if not args.no_cpu_baseline:
-            dt, o = oracle_item_seconds(data, folds, items[0])
-            cores = host_threads()
-            line["cpu_baseline"] = {"value": (1.0 / N_FOLDS) / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            # CPU arm on a bounded sample: three of the step's items (one single-leaf, one periodic, one composite) through
+            # the oracle on every host core; the first one is the timed baseline, all three are the parity check at scale
+            import re as _re
+            gpu = {"nlml": nlml_d.cpu().numpy(), "bic": bic_d.cpu().numpy(), "grad": grad_d.cpu().numpy()}
+            done_ids = set(int(i) for i in np.nonzero(gpu["nlml"])[0])   # items this rank scored on the device path
+            structs = [cands[it[0]].kernel.structure() for it in items]
+            pick = []
+            for want in (lambda st: not _re.search(r"[+*]", st) and "Per" not in st, lambda st: "Per" in st,
+                         lambda st: bool(_re.search(r"[+*]", st)) and "Per" not in st):
+                for i in sorted(done_ids):
+                    if want(structs[i]) and i not in pick:
+                        pick.append(i)
+                        break
+            par, dt0, o0 = [], None, None
+            with all_host_threads():
+                cores = host_threads()
+                for i in pick:
+                    dt, o = oracle_item_seconds(data, folds, items[i])
+                    if dt0 is None:
+                        dt0, o0 = dt, o
+                    P = progs[i].n_theta
+                    gerr = float(np.max(np.abs(gpu["grad"][i, :P] - o["grad"])) / max(np.max(np.abs(o["grad"])), 1e-300))
+                    par.append({"item": int(i), "structure": structs[i], "n": len(rows[i]), "cpu_seconds": dt,
+                                "nlml_rel": float(abs(gpu["nlml"][i] - o["nlml"]) / abs(o["nlml"])),
+                                "bic_rel": float(abs(gpu["bic"][i] - o["bic"]) / abs(o["bic"])),
+                                "grad_rel_of_max": gerr, "sweeps_cpu": int(o["sweeps"]), "sweeps_gpu": int(sweeps_d[i].item())})
+            line["cpu_baseline"] = {"value": (1.0 / N_FOLDS) / dt0, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "1 of the step's %d items (one fold model, n=%d, %d EP sweeps), NumPy/"
                                               "LAPACK oracle, parallel-EP mode, %d host threads: %.1f s"
-                                              % (B, len(rows[0]), o["sweeps"], cores, dt)}
-            gn = float(nlml_d[0].item())
-            line["cpu_baseline"]["nlml_rel_diff_vs_gpu"] = abs(gn - o["nlml"]) / abs(o["nlml"])
+                                              % (n_items, len(rows[pick[0]]), o0["sweeps"], cores, dt0)}
+            line["parity_at_scale"] = {"items": par, "max_nlml_rel": max(p["nlml_rel"] for p in par),
+                                       "max_bic_rel": max(p["bic_rel"] for p in par),
+                                       "max_grad_rel": max(p["grad_rel_of_max"] for p in par),
+                                       "note": "GPU (device path, last timed step) vs the CPU oracle on the same items at the "
+                                               "benchmark size; gradient error relative to the largest gradient component"}
         emit(line)
     eng.dataset_free(did)
     eng.close()

@@ -115,7 +115,10 @@ int64_t agpc_launch_count(agpc_ctx* ctx);
 #define AGPC_CLS_GEMM_TRTRI 8 /* the tile GEMM inside trtri (AGPC_CLS_GEMM: inside potrf / predict) */
 #define AGPC_CLS_GEMM_LAUUM 9 /* ... inside lauum */
 #define AGPC_CLS_SLICE 10     /* operand slicing for the int8 tensor-core GEMM (bytes of FP64 read) */
-#define AGPC_CLS_COUNT 11
+#define AGPC_CLS_OZ_POTRF 11  /* the int8 tensor-core GEMM (csrc/ozaki.cu) inside potrf / trtri / lauum: its event time is  */
+#define AGPC_CLS_OZ_TRTRI 12  /* ALSO part of AGPC_CLS_GEMM / _TRTRI / _LAUUM (whose work stays the algorithmic FP64 flop   */
+#define AGPC_CLS_OZ_LAUUM 13  /* count of the phase); work here = int8 operations the kernel EXECUTED (2 x MACs)           */
+#define AGPC_CLS_COUNT 14
 int agpc_profile_enable(agpc_ctx* ctx, int32_t on);
 int agpc_profile_read(agpc_ctx* ctx, double* ms, double* work, int64_t* launches);
 

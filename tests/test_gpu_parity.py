@@ -333,7 +333,7 @@ def test_profile_counters_book_the_launches(engine):
     prof = engine.profile_read()
     engine.profile_enable(False)
     engine.dataset_free(did)
-    assert sum(v["launches"] for k, v in prof.items() if k != "gemm") <= engine.launches - l0
+    assert sum(v["launches"] for k, v in prof.items() if k != "gemm" and not k.startswith("oz_")) <= engine.launches - l0
     assert prof["kbuild"]["launches"] == 1 and prof["kbuild"]["work"] == pytest.approx(8.0 * 300 * 300)
     assert prof["potf2"]["launches"] >= 3 and prof["gemm"]["launches"] > 0 and prof["gemm"]["ms"] > 0
     assert prof["gemm"]["work"] == pytest.approx(prof["gemm_potrf"]["work"] + prof["gemm_trtri"]["work"] + prof["gemm_lauum"]["work"])

@@ -76,3 +76,56 @@ def test_shard_indices_and_records():
     r = sharding.pack_record(5, 1.5, 2.5, 0.25, 0, [1.0, 2.0, 3.0])
     assert r.shape == (sharding.RECORD_WIDTH,) and r[5] == 3 and r[6:9].tolist() == [1.0, 2.0, 3.0]
     assert sharding.world() == (0, 1)
+
+
+def test_cost_aware_dealing_balances_and_is_deterministic():
+    costs = [sharding.item_cost(6400, nl, npr) for nl, npr in [(1, 0), (1, 1), (2, 0), (2, 1), (3, 1), (1, 0), (2, 0), (3, 0)] * 5]
+    parts = sharding.deal_items(costs, 8)
+    assert sorted(sum(parts, [])) == list(range(len(costs)))
+    load = [sum(costs[i] for i in p) for p in parts]
+    assert max(load) <= 1.10 * (sum(costs) / 8)          # LPT: within 10 % of the mean on this mix
+    rr = [sum(costs[i] for i in range(len(costs)) if i % 8 == r) for r in range(8)]
+    assert max(load) <= max(rr)                          # never worse than round-robin
+    assert parts == sharding.deal_items(costs, 8)
+    assert sharding.shard_indices(len(costs), 3, 8, costs) == parts[3]
+
+
+def _queue_worker(rank, world, port, q):
+    import time
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        out = []
+        for n in (7, 13):                        # two queues in a row: keys must not collide
+            wq = sharding.WorkQueue(n, tag="test")
+            mine = []
+            while True:
+                c = wq.claim()
+                if c is None:
+                    break
+                mine.append(c)
+                time.sleep(0.002 * (rank + 1))   # rank 1 is slower: it must end up with fewer chunks
+            out.append(mine)
+            dist.barrier()
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_work_queue_deals_every_chunk_exactly_once():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_queue_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for k, n in enumerate((7, 13)):
+        assert sorted(got[0][k] + got[1][k]) == list(range(n))
+    assert len(got[0][1]) >= len(got[1][1])
+    wq = sharding.WorkQueue(3)                   # single process: a plain counter
+    assert [wq.claim() for _ in range(4)] == [0, 1, 2, None]
