@@ -70,6 +70,7 @@ int agpc_create(int device, agpc_ctx** out) {
   if (!c) return AGPC_E_NOMEM;
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("AGPC_JITTER")) c->jitter = atoi(e) != 0;
   if (const char* e = getenv("AGPC_OZAKI")) {
     const int v = atoi(e);
     c->oz_S = (v == 6 || v == 7) ? v : 0;
@@ -335,6 +336,61 @@ int agpc_potrf(agpc_ctx* ctx, double* A, int32_t n, int32_t batch, double* Minv,
   return AGPC_OK;
 }
 
+
+int agpc_jitchol(agpc_ctx* ctx, double* A, int32_t n, int32_t batch, double* jitter_out, int32_t* info_out, void* stream) {
+  if (!ctx || !A || n <= 0 || batch <= 0 || n % TILE) return fail(ctx, AGPC_E_ARG, "jitchol: n must be a multiple of 128");
+  CK(ctx, cudaSetDevice(ctx->device));
+  const size_t mat = sizeof(double) * (size_t)n * n * batch;
+  const int oz_S = ctx->oz_S;
+  const size_t oz_bytes = (size_t)oz_S * n * n * batch, sc_bytes = sizeof(double) * (size_t)n * batch;
+  size_t need = 3 * mat + (oz_S ? 2 * (oz_bytes + 1024) + 2 * sc_bytes : 0) + (sizeof(double) + 3 * sizeof(int)) * (size_t)batch + 16384;
+  int rc = ctx->ensure_arena(need);
+  if (rc) return rc;
+  char* p = (char*)ctx->arena;
+  MatSet ms;
+  ms.np = n; ms.batch = batch; ms.stride = (long long)n * n;
+  ms.A = A;
+  ms.M = (double*)p; p += mat;
+  ms.U = (double*)p; p += mat;
+  double* A0 = (double*)p; p += mat;
+  double* jit = (double*)p; p += sizeof(double) * (size_t)batch;
+  int* info = (int*)p; p += sizeof(int) * (size_t)batch;
+  int* tries = (int*)p; p += sizeof(int) * (size_t)batch;
+  int* retry = (int*)p; p += sizeof(int) * (size_t)batch;
+  if (oz_S) {
+    p = (char*)(((uintptr_t)p + 1023) & ~(uintptr_t)1023);
+    ms.oz_S = oz_S;
+    ms.scA = (double*)p; p += sc_bytes;
+    ms.scB = (double*)p; p += sc_bytes;
+    p = (char*)(((uintptr_t)p + 1023) & ~(uintptr_t)1023);
+    ms.SA = (int8_t*)p; p += (oz_bytes + 1023) / 1024 * 1024;
+    ms.SB = (int8_t*)p;
+  }
+  if (make_tensor_map(&ms.mapA, ms.A, n, n, batch, n, ms.stride) || make_tensor_map(&ms.mapM, ms.M, n, n, batch, n, ms.stride) ||
+      make_tensor_map(&ms.mapU, ms.U, n, n, batch, n, ms.stride) ||
+      make_tensor_map(&ms.mapA32, ms.A, n, n, batch, n, ms.stride, 32) ||
+      make_tensor_map(&ms.mapM32, ms.M, n, n, batch, n, ms.stride, 32))
+    return fail(ctx, AGPC_E_CUDA, "cuTensorMapEncodeTiled failed");
+  Launch L{stream ? (cudaStream_t)stream : ctx->stream, &ctx->launches, &ctx->prof, ctx->side, ctx->ev_panel, ctx->ev_rest};
+  CK(ctx, cudaMemcpyAsync(A0, A, mat, cudaMemcpyDeviceToDevice, L.stream));
+  CK(ctx, cudaMemsetAsync(info, 0, sizeof(int) * batch, L.stream));
+  CK(ctx, cudaMemsetAsync(tries, 0, sizeof(int) * batch, L.stream));
+  CK(ctx, cudaMemsetAsync(jit, 0, sizeof(double) * batch, L.stream));
+  CK(ctx, potrf_blocked(L, ms, nullptr, info));
+  std::vector<int> h(batch);
+  for (int attempt = 0; attempt <= 5; ++attempt) {
+    CK(ctx, cudaMemcpyAsync(h.data(), info, sizeof(int) * batch, cudaMemcpyDeviceToHost, L.stream));
+    CK(ctx, cudaStreamSynchronize(L.stream));
+    int n_bad = 0;
+    for (int b = 0; b < batch; ++b) n_bad += h[b] == AGPC_ST_NOT_PD;
+    if (n_bad == 0 || attempt == 5) break;
+    CK(ctx, jitter_step_mat_launch(L, A0, A, n, ms.stride, batch, info, jit, tries, retry));
+    CK(ctx, potrf_blocked(L, ms, retry, info));
+  }
+  if (jitter_out) CK(ctx, cudaMemcpyAsync(jitter_out, jit, sizeof(double) * batch, cudaMemcpyDeviceToDevice, L.stream));
+  if (info_out) CK(ctx, cudaMemcpyAsync(info_out, info, sizeof(int) * batch, cudaMemcpyDeviceToDevice, L.stream));
+  return AGPC_OK;
+}
 
 // small persistent device scratch for a program + theta (building-block entry points)
 static int param_scratch(agpc_ctx* ctx, const agpc_program* prog, const double* theta_host, cudaStream_t st,

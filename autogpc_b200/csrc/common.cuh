@@ -224,7 +224,11 @@ cudaError_t gather_rows_launch(const Launch& L, const double* X, const double* y
                                const long long* row_off, const int* n_of, int D, int np, int batch, double* Xf,
                                double* yf);
 cudaError_t form_B_launch(const Launch& L, const double* K, const double* s, double* A, int np, long long stride,
-                          int batch, const int* active);
+                          int batch, const int* active, const double* jitter = nullptr);
+cudaError_t jitter_step_mat_launch(const Launch& L, const double* A0, double* A, int n, long long stride, int batch, int* info,
+                                   double* jitter, int* tries, int* retry);
+cudaError_t jitter_step_launch(const Launch& L, const double* kdiag, const double* s, const int* n_of, int np, int batch,
+                               int* info, double* jitter, int* tries, int* retry, int* used, const int* active);
 cudaError_t scale_cols_launch(const Launch& L, double* Ks, const double* s, int rows, int np, int batch);
 cudaError_t grad_contract_launch(const Launch& L, const GradArgs& a, int batch, double scale, double* grad,
                                  int grad_stride);

@@ -14,6 +14,7 @@ struct Dataset {
 struct agpc_ctx {
   int device = 0;
   int sm_count = 148;
+  int jitter = 1;  // jitchol's jitter ladder on a failed factorisation (AGPC_JITTER=0 disables: failures stay NOT_PD)
   int oz_S = 7;  // digit slices of the int8 tensor-core GEMM path (ozaki.cu); 0 = FP64 DMMA kernel only.  AGPC_OZAKI=0|6|7
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;  // look-ahead stream of potrf_blocked

@@ -811,7 +811,7 @@ cudaError_t gather_rows_launch(const Launch& L, const double* X, const double* y
 
 // ---- B = I + S^1/2 K S^1/2 (lower tiles only) ---------------------------------------------------------------
 __global__ void form_B_kernel(const double* __restrict__ K, const double* __restrict__ s, double* __restrict__ A,
-                              int np, long long stride, const int* __restrict__ active) {
+                              int np, long long stride, const int* __restrict__ active, const double* __restrict__ jitter) {
   const int b = blockIdx.z;
   if (active != nullptr && active[b] == 0) return;
   const int ti = blockIdx.y, tj = blockIdx.x;  // 32 x 128 tiles
@@ -829,17 +829,117 @@ __global__ void form_B_kernel(const double* __restrict__ K, const double* __rest
       const int j = col0 + tx + 64 * h;
       const long long o = (long long)i * np + j;
       double v = si * Kb[o] * sb[j];
-      if (i == j) v += 1.0;
+      if (i == j) v += 1.0 + (jitter != nullptr ? jitter[b] : 0.0);  // jitchol's retry: B + jitter I
       Ab[o] = v;
     }
   }
 }
 
 cudaError_t form_B_launch(const Launch& L, const double* K, const double* s, double* A, int np, long long stride,
-                          int batch, const int* active) {
+                          int batch, const int* active, const double* jitter) {
   ProfScope prof_scope(L, CLS_FORMB);
   dim3 grid(np / 128, np / 32, batch);
-  form_B_kernel<<<grid, 256, 0, L.stream>>>(K, s, A, np, stride, active);
+  form_B_kernel<<<grid, 256, 0, L.stream>>>(K, s, A, np, stride, active, jitter);
+  L.bump();
+  return cudaGetLastError();
+}
+
+// ---- jitchol's jitter ladder (GPy util/linalg.py, reached from EP.inference for gpckernel.py:245-246) --------------
+// One CTA per item whose factorisation failed (info == NOT_PD).  First failure of this factorisation (tries == 0):
+// jitter = mean(diag B) 1e-6 with B_ii = 1 + s_i^2 K_ii over the item's true rows; later failures: jitter *= 10; after
+// 5 jittered attempts, or with a non-positive / non-finite diagonal, the item stays NOT_PD.  retry[b] = 1 marks the
+// items to re-form and re-factorise (their info is cleared), used[b] records that the result carries jitter.
+__global__ void __launch_bounds__(256)
+jitter_step_kernel(const double* __restrict__ kdiag, const double* __restrict__ s, const int* __restrict__ n_of, int np,
+                   int* __restrict__ info, double* __restrict__ jitter, int* __restrict__ tries, int* __restrict__ retry,
+                   int* __restrict__ used, const int* __restrict__ active) {
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) retry[b] = 0;
+  if ((active != nullptr && active[b] == 0) || info[b] != AGPC_ST_NOT_PD) return;
+  __shared__ double red[256];
+  __shared__ int bad;
+  if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
+  const int n = n_of[b];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const double si = s[(long long)b * np + i];
+    const double d = 1.0 + si * si * kdiag[(long long)b * np + i];
+    if (!(d > 0.0) || !isfinite(d)) bad = 1;
+    acc += d;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int t = tries[b];
+    if (bad || t >= 5) return;  // gives up: info stays NOT_PD
+    jitter[b] = t == 0 ? red[0] / n * 1e-6 : jitter[b] * 10.0;
+    tries[b] = t + 1;
+    retry[b] = 1;
+    used[b] = 1;
+    info[b] = 0;
+  }
+}
+// the same ladder step for a plain matrix (agpc_jitchol): diagonal read from the untouched copy A0; retried items get
+// A = A0 + jitter I written back (lower triangle + diagonal; the factorisation reads nothing else)
+__global__ void __launch_bounds__(256)
+jitter_step_mat_kernel(const double* __restrict__ A0, int n, long long stride, int* __restrict__ info,
+                       double* __restrict__ jitter, int* __restrict__ tries, int* __restrict__ retry) {
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) retry[b] = 0;
+  if (info[b] != AGPC_ST_NOT_PD) return;
+  __shared__ double red[256];
+  __shared__ int bad;
+  if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const double d = A0[(long long)b * stride + (long long)i * n + i];
+    if (!(d > 0.0) || !isfinite(d)) bad = 1;
+    acc += d;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int t = tries[b];
+    if (bad || t >= 5) return;
+    jitter[b] = t == 0 ? red[0] / n * 1e-6 : jitter[b] * 10.0;
+    tries[b] = t + 1;
+    retry[b] = 1;
+    info[b] = 0;
+  }
+}
+__global__ void restore_jitter_kernel(const double* __restrict__ A0, double* __restrict__ A, int n, long long stride,
+                                      const double* __restrict__ jitter, const int* __restrict__ retry) {
+  const int b = blockIdx.y;
+  if (retry[b] == 0) return;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * n) return;
+  const int i = (int)(idx / n), j = (int)(idx % n);
+  A[(long long)b * stride + idx] = A0[(long long)b * stride + idx] + (i == j ? jitter[b] : 0.0);
+}
+cudaError_t jitter_step_mat_launch(const Launch& L, const double* A0, double* A, int n, long long stride, int batch, int* info,
+                                   double* jitter, int* tries, int* retry) {
+  ProfScope prof_scope(L, CLS_MISC);
+  jitter_step_mat_kernel<<<batch, 256, 0, L.stream>>>(A0, n, stride, info, jitter, tries, retry);
+  dim3 grid((unsigned)(((long long)n * n + 255) / 256), batch);
+  restore_jitter_kernel<<<grid, 256, 0, L.stream>>>(A0, A, n, stride, jitter, retry);
+  L.bump(2);
+  return cudaGetLastError();
+}
+
+cudaError_t jitter_step_launch(const Launch& L, const double* kdiag, const double* s, const int* n_of, int np, int batch,
+                               int* info, double* jitter, int* tries, int* retry, int* used, const int* active) {
+  ProfScope prof_scope(L, CLS_MISC);
+  jitter_step_kernel<<<batch, 256, 0, L.stream>>>(kdiag, s, n_of, np, info, jitter, tries, retry, used, active);
   L.bump();
   return cudaGetLastError();
 }

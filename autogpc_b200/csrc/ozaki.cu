@@ -25,6 +25,8 @@
 // (cp.async.bulk, mbarrier complete_tx) with no tensor map; 5-stage ring, one producer thread, one MMA-issuing
 // thread, 8 epilogue warps that read TMEM (tcgen05.ld), run the FP64 Horner recombination, and go through a padded
 // shared-memory transposition so that every global access of C is a full-line row access.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace agpc {
@@ -54,6 +56,21 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+// the same copy delivered to the same CTA-relative address (and mbarrier) of every CTA in cta_mask of the cluster
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // mode 0: A operand discarded after the MMA; 1 / 2 / 3: collector::a::fill / use / lastuse -- consecutive MMAs that share
 // their A slice keep it in the tensor core's operand collector (SASS A_KEEP / A_REUSE)
@@ -99,7 +116,10 @@ __device__ __forceinline__ uint32_t oz_swz(uint32_t row, uint32_t kbyte) {
   return a ^ (((a >> 7) & 1u) << 4);
 }
 
-template <int S>
+// PAIR = true: launched as clusters of two CTAs -- the two 64-column halves of one 128 x 128 tile.  They need the same A
+// stage, so each loads half of it and multicasts it into both shared memories (a third less L2 -> SM traffic per MMA,
+// which is what the single-CTA form is bound by at 6.3 TB/s); a stage is released when BOTH CTAs' MMAs have read it.
+template <int S, bool PAIR>
 __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzGemmArgs args) {
   using namespace oz;
   constexpr int CPB = TILE / OZ_KB;  // K chunks per 128-block
@@ -147,7 +167,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzGemmA
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2 * OZ_STAGES + 1; ++s) mbar_init(bars + 8 * s, 1);
+    for (int s = 0; s < 2 * OZ_STAGES + 1; ++s)
+      mbar_init(bars + 8 * s, (PAIR && s >= OZ_STAGES && s < 2 * OZ_STAGES) ? 2 : 1);  // empty[]: one commit per CTA of the pair
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -156,6 +177,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzGemmA
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers exist before anything of ours can land on them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
 
@@ -176,7 +198,13 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzGemmA
         const uint32_t full = bars + 8 * s;
         mbar_expect_tx(full, STAGE);
         const uint32_t dst = smem_base + s * STAGE;
-        bulk_g2s(dst, srcA + (long long)it * (S * (long long)A_SLICE), S * A_SLICE, full);
+        if (PAIR) {  // my half of the A stage, into both CTAs
+          constexpr uint32_t HALF_A = (S * A_SLICE / 2 + 15u) & ~15u;
+          const uint32_t off = half ? HALF_A : 0u, len = half ? S * A_SLICE - HALF_A : HALF_A;
+          bulk_g2s_mc(dst + off, srcA + (long long)it * (S * (long long)A_SLICE) + off, len, full, (uint16_t)3);
+        } else {
+          bulk_g2s(dst, srcA + (long long)it * (S * (long long)A_SLICE), S * A_SLICE, full);
+        }
 #pragma unroll
         for (int q = 0; q < S; ++q)
           bulk_g2s(dst + S * A_SLICE + q * B_SLICE, srcB + (long long)it * (S * (long long)A_SLICE) + q * (long long)A_SLICE, B_SLICE, full);
@@ -207,7 +235,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzGemmA
             umma_i8(tmem + (uint32_t)(p + q) * OZ_BN, da, db, IDESC, (it == 0 && p == 0) ? 0u : 1u, mode);
           }
         }
-        umma_commit(bars + 8 * (OZ_STAGES + s));  // frees the stage when these MMAs have read it
+        if (PAIR) umma_commit_mc(bars + 8 * (OZ_STAGES + s), (uint16_t)3);  // frees the stage in both CTAs of the pair ...
+        else umma_commit(bars + 8 * (OZ_STAGES + s));                       // ... when these MMAs have read it
       }
       if (n_iter > 0) umma_commit(bars + 8 * (2 * OZ_STAGES));  // accumulators complete
     }
@@ -274,6 +303,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzGemmA
   }
   __syncwarp();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer may still arrive on our barriers / multicast until it is done as well
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
@@ -389,16 +419,26 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const OzSliceArgs a) {
 }
 
 // ---- launchers ---------------------------------------------------------------------------------------------------
-template <int S>
+template <int S, bool PAIR>
 static cudaError_t oz_gemm_launch_t(const Launch& L, const OzGemmArgs& a, int tiles128, int groups, int batch) {
-  bool& configured = func_attr_done(__LINE__ + S);
+  bool& configured = func_attr_done(__LINE__ + 2 * S + (PAIR ? 1 : 0));
   if (!configured) {
-    AGPC_CUDA_TRY(cudaFuncSetAttribute(ozaki_gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz_smem_bytes<S>()));
+    AGPC_CUDA_TRY(cudaFuncSetAttribute(ozaki_gemm_kernel<S, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz_smem_bytes<S>()));
     configured = true;
   }
-  dim3 grid(2 * tiles128, groups, batch);
-  ozaki_gemm_kernel<S><<<grid, OZ_THREADS, oz_smem_bytes<S>(), L.stream>>>(a);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * tiles128, groups, batch);
+  cfg.blockDim = dim3(OZ_THREADS);
+  cfg.dynamicSmemBytes = oz_smem_bytes<S>();
+  cfg.stream = L.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, ozaki_gemm_kernel<S, PAIR>, a);
 }
 
 // int8 MACs one launch executes per batch item: the kernel's own tile / K-range rules, evaluated on the host
@@ -438,7 +478,11 @@ cudaError_t oz_gemm_launch(const Launch& L, const OzGemmArgs& a, int tiles128, i
   if (L.prof && L.prof->enabled)
     L.add_work(oz_cls, 2.0 * oz_executed_macs(a, tiles128, groups, S) * (a.active ? (double)(L.work_items < batch ? L.work_items : batch) : (double)batch));
   L.bump();
-  return S == 6 ? oz_gemm_launch_t<6>(L, a, tiles128, groups, batch) : oz_gemm_launch_t<7>(L, a, tiles128, groups, batch);
+  // pairs need both halves of a tile to run the same K range (KRULE_END_AT_COL clips per half); AGPC_OZ_PAIR=0: single CTAs
+  static const bool pair_env = !(getenv("AGPC_OZ_PAIR") && atoi(getenv("AGPC_OZ_PAIR")) == 0);
+  const bool pair = pair_env && a.k_rule != KRULE_END_AT_COL;
+  if (S == 6) return pair ? oz_gemm_launch_t<6, true>(L, a, tiles128, groups, batch) : oz_gemm_launch_t<6, false>(L, a, tiles128, groups, batch);
+  return pair ? oz_gemm_launch_t<7, true>(L, a, tiles128, groups, batch) : oz_gemm_launch_t<7, false>(L, a, tiles128, groups, batch);
 }
 
 cudaError_t oz_slice_launch(const Launch& L, const OzSliceArgs& a, int row_blocks, int groups, int batch, int S) {

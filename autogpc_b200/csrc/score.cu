@@ -53,6 +53,8 @@ struct Chunk {
   double *tau, *nu, *s, *sig, *mu, *w, *u, *t, *z, *kv, *dB, *alpha, *kdiag, *yf, *tmp;
   double* Xf;
   int *n_of, *active, *sweeps, *status, *converged, *info, *ones;
+  int *jit_tries, *jit_retry, *jit_used;  // jitchol ladder state per item
+  double* jitter;
   long long* row_off;
   int* rows;
   agpc_program* progs;
@@ -78,6 +80,7 @@ struct Chunk {
     Xf = c.take<double>(vec * D);
     n_of = c.take<int>(nb); active = c.take<int>(nb); sweeps = c.take<int>(nb); status = c.take<int>(nb);
     converged = c.take<int>(nb); info = c.take<int>(nb); ones = c.take<int>(nb);
+    jit_tries = c.take<int>(nb); jit_retry = c.take<int>(nb); jit_used = c.take<int>(nb); jitter = c.take<double>(nb);
     row_off = c.take<long long>(nb + 1);
     rows = with_rows ? c.take<int>(vec) : nullptr;
     progs = c.take<agpc_program>(nb);
@@ -124,6 +127,11 @@ __global__ void mark_unconverged_kernel(const int* __restrict__ active, int* __r
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < nb && active[b] != 0 && status[b] == AGPC_ST_OK) status[b] = AGPC_ST_EP_NOT_CONVERGED;
 }
+// a result whose factorisation needed jitter is flagged (GPy would only log a warning; SURVEY 8b item 4 status 1)
+__global__ void jitter_status_kernel(const int* __restrict__ used, int* __restrict__ status, int nb) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < nb && used[b] != 0 && status[b] == AGPC_ST_OK) status[b] = AGPC_ST_JITTER;
+}
 // need[b] = 1 unless the EP update left the item's sites untouched (converged[b] == 2, ep.cu): then the
 // factorisation, inverse and marginals in its buffers already belong to the final sites
 __global__ void need_final_kernel(const int* __restrict__ converged, int* __restrict__ need, int nb) {
@@ -131,9 +139,52 @@ __global__ void need_final_kernel(const int* __restrict__ converged, int* __rest
   if (b < nb) need[b] = converged[b] == 2 ? 0 : 1;
 }
 
+int count_flags(agpc_ctx* ctx, const Launch& L, const int* flags_dev, int nb, int value, int* n_out);
+
+// jitchol (GPy util/linalg.py): a factorisation that fails is retried on B + jitter I with jitter = mean(diag B) 1e-6,
+// x 10 per further failure, at most 5 times; every factorisation starts its own ladder.  One poll of info[] per
+// factorisation (a 4 nb byte copy) finds the failures; the common case costs nothing else.
+// fault injection for the tests (a B = I + S^1/2 K S^1/2 built from PSD kernels cannot be made to fail reliably):
+// AGPC_FAULT_NOT_PD=k makes the plain attempt and the first k - 1 jittered attempts of item 0 of every factorisation
+// report NOT_PD
+int fault_budget() {
+  static const int fault = getenv("AGPC_FAULT_NOT_PD") ? atoi(getenv("AGPC_FAULT_NOT_PD")) : 0;
+  return fault;
+}
+cudaError_t inject_fault(const Launch& L, Chunk& c, int* fault_left) {
+  static const int not_pd = AGPC_ST_NOT_PD;
+  if ((*fault_left)-- > 0) return cudaMemcpyAsync(c.info, &not_pd, sizeof(int), cudaMemcpyHostToDevice, L.stream);
+  return cudaSuccess;
+}
+
+int jitter_ladder(agpc_ctx* ctx, const Launch& L, Chunk& c, const int* active, int* fault_left) {
+  const int np = c.np, nb = c.nb;
+  int n_bad = 0;
+  int rc = count_flags(ctx, L, c.info, nb, AGPC_ST_NOT_PD, &n_bad);
+  if (rc) return rc;
+  if (n_bad == 0) return AGPC_OK;
+  if (cudaMemsetAsync(c.jit_tries, 0, sizeof(int) * nb, L.stream) != cudaSuccess) return AGPC_E_CUDA;
+  for (int attempt = 0; attempt < 5 && n_bad > 0; ++attempt) {
+    if (jitter_step_launch(L, c.kdiag, c.s, c.n_of, np, nb, c.info, c.jitter, c.jit_tries, c.jit_retry, c.jit_used, active) != cudaSuccess)
+      return AGPC_E_CUDA;
+    int n_retry = 0;
+    rc = count_flags(ctx, L, c.jit_retry, nb, 1, &n_retry);
+    if (rc) return rc;
+    if (n_retry == 0) break;
+    Launch Lr = L;
+    Lr.work_items = n_retry;
+    if (form_B_launch(Lr, c.ms.K, c.s, c.ms.A, np, c.ms.stride, nb, c.jit_retry, c.jitter) != cudaSuccess) return AGPC_E_CUDA;
+    if (potrf_blocked(Lr, c.ms, c.jit_retry, c.info) != cudaSuccess) return AGPC_E_CUDA;
+    if (inject_fault(L, c, fault_left) != cudaSuccess) return AGPC_E_CUDA;
+    rc = count_flags(ctx, L, c.info, nb, AGPC_ST_NOT_PD, &n_bad);
+    if (rc) return rc;
+  }
+  return AGPC_OK;
+}
+
 // posterior at the current sites for the items flagged in `active` (nullptr = all):
 // s, A = chol(B), M, U, w = K nu, z = B^-1 (s o w), dB = diag(B^-1), kv = K (s o z), then sig / mu.
-cudaError_t posterior(const Launch& L, Chunk& c, const int* active) {
+cudaError_t posterior(agpc_ctx* ctx, const Launch& L, Chunk& c, const int* active) {
   const int np = c.np, nb = c.nb;
   const long long st = c.ms.stride;
   {
@@ -144,6 +195,9 @@ cudaError_t posterior(const Launch& L, Chunk& c, const int* active) {
   AGPC_CUDA_TRY(sqrt_scale_launch(L, c.tau, nullptr, c.s, nullptr, np, nb, active));
   AGPC_CUDA_TRY(form_B_launch(L, c.ms.K, c.s, c.ms.A, np, st, nb, active));
   AGPC_CUDA_TRY(potrf_blocked(L, c.ms, active, c.info));
+  int fault_left = fault_budget();
+  AGPC_CUDA_TRY(inject_fault(L, c, &fault_left));
+  if (ctx->jitter && jitter_ladder(ctx, L, c, active, &fault_left) != AGPC_OK) return cudaErrorUnknown;
   AGPC_CUDA_TRY(trtri_blocked(L, c.ms, active));
   AGPC_CUDA_TRY(rowdot_launch(L, 0, false, c.ms.K, c.nu, c.w, nullptr, np, np, st, np, np, nb, active));
   AGPC_CUDA_TRY(mul_launch(L, c.s, c.w, c.u, np, nb, active));
@@ -179,6 +233,24 @@ int poll_active(agpc_ctx* ctx, const Launch& L, const int* active_dev, int nb, i
   return AGPC_OK;
 }
 
+// number of entries of a device flag array equal to `value` (one small D2H copy + stream synchronisation)
+int count_flags(agpc_ctx* ctx, const Launch& L, const int* flags_dev, int nb, int value, int* n_out) {
+  if (ctx->pinned_bytes < sizeof(int) * (size_t)nb) {
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr;
+    ctx->pinned_bytes = 0;
+    CK(cudaMallocHost(&ctx->pinned, sizeof(int) * (size_t)nb * 2));
+    ctx->pinned_bytes = sizeof(int) * (size_t)nb * 2;
+  }
+  CK(cudaMemcpyAsync(ctx->pinned, flags_dev, sizeof(int) * nb, cudaMemcpyDeviceToHost, L.stream));
+  CK(cudaStreamSynchronize(L.stream));
+  int cnt = 0;
+  const int* a = static_cast<const int*>(ctx->pinned);
+  for (int i = 0; i < nb; ++i) cnt += a[i] == value;
+  *n_out = cnt;
+  return AGPC_OK;
+}
+
 // EP for one lock-step chunk (K is already built): parallel-schedule sweeps until every item has converged, then the
 // posterior at the final sites, log Z_EP, alpha and (optionally) the gradient.  tau_src / nu_src: warm-start sites.
 int ep_chunk(agpc_ctx* ctx, Launch& L, Chunk& c, const agpc_ep_options* opt, int theta_stride, bool want_grad, int D,
@@ -186,6 +258,7 @@ int ep_chunk(agpc_ctx* ctx, Launch& L, Chunk& c, const agpc_ep_options* opt, int
   const int np = c.np, nb = c.nb;
   const int tb = 256;
   dim3 gvec((np + tb - 1) / tb, nb);
+  CK(cudaMemsetAsync(c.jit_used, 0, sizeof(int) * nb, L.stream));
   if (warm) {
     copy_strided_kernel<<<gvec, tb, 0, L.stream>>>(c.tau, np, tau_src, site_stride, c.n_of, np, 1);
     copy_strided_kernel<<<gvec, tb, 0, L.stream>>>(c.nu, np, nu_src, site_stride, c.n_of, np, 1);
@@ -201,7 +274,7 @@ int ep_chunk(agpc_ctx* ctx, Launch& L, Chunk& c, const agpc_ep_options* opt, int
     if (sweep == 1 && !warm) {
       CK(marginals_launch(L, c.tau, c.dB, c.w, c.kv, c.kdiag, c.sig, c.mu, c.n_of, np, nb, 1, c.active));
     } else {
-      CK(posterior(L, c, c.active));
+      CK(posterior(ctx, L, c, c.active));
     }
     // GPy measures convergence as the change between two sweeps (hence >= 2 from a cold start); the residual used here
     // is an absolute fixed-point error, so warm-started sites that are already converged may stop after one sweep
@@ -231,11 +304,13 @@ int ep_chunk(agpc_ctx* ctx, Launch& L, Chunk& c, const agpc_ep_options* opt, int
   }
   if (n_need > 0) {
     L.work_items = n_need;
-    CK(posterior(L, c, c.active));
+    CK(posterior(ctx, L, c, c.active));
     L.work_items = nb;
   }
   CK(ep_final_launch(L, c.tau, c.nu, c.sig, c.mu, c.yf, c.s, c.z, c.ms.A, c.ms.stride, c.n_of, np, nb, c.progs,
                      c.alpha, c.nlml, c.nlml_gauss, c.bic, c.status, c.info));
+  jitter_status_kernel<<<(nb + 255) / 256, 256, 0, L.stream>>>(c.jit_used, c.status, nb);
+  L.bump();
   if (want_grad) {
     CK(lauum_blocked(L, c.ms, c.ms.T, nullptr));
     GradArgs ga{};
@@ -652,7 +727,7 @@ static int predict_impl(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, cons
     copy_strided_kernel<<<gvec, tb, 0, L.stream>>>(c.nu, np, site_tmp, site_stride, c.n_of, np, 1);
     clamp_tau_kernel<<<gvec, tb, 0, L.stream>>>(c.tau, c.kdiag, c.n_of, np);
     L.bump(3);
-    CK(posterior(L, c, nullptr));
+    CK(posterior(ctx, L, c, nullptr));
     CK(ep_final_launch(L, c.tau, c.nu, c.sig, c.mu, c.yf, c.s, c.z, c.ms.A, c.ms.stride, c.n_of, np, nb, c.progs,
                        c.alpha, c.nlml, c.nlml_gauss, c.bic, c.status, c.info));
     // cross kernel, latent mean and variance

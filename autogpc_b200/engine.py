@@ -308,6 +308,13 @@ class Engine:
                                          C.c_void_p(stream) if stream else None))
 
 
+    def jitchol(self, A_dev_ptr: int, n: int, batch: int = 1, jitter_ptr: int = 0, info_ptr: int = 0, stream: int = 0):
+        """``agpc_jitchol``: in-place Cholesky with GPy's jitter ladder (``util.linalg.jitchol``)."""
+        self._check(self._L.agpc_jitchol(self._ctx, C.c_void_p(A_dev_ptr), n, batch,
+                                         C.c_void_p(jitter_ptr) if jitter_ptr else None,
+                                         C.c_void_p(info_ptr) if info_ptr else None,
+                                         C.c_void_p(stream) if stream else None))
+
     def gemm_nt_i8x(self, A_ptr: int, B_ptr: int, C_ptr: int, M: int, N: int, K: int, alpha=1.0, beta=0.0, batch=1,
                     n_slices: int = 7, stream: int = 0):
         """``agpc_gemm_nt_i8x``: the same product through int8 digit slices on tcgen05 (csrc/ozaki.cu)."""

@@ -273,8 +273,10 @@ def workload_config(args, world, n_items):
                         % (args.points, args.points - args.points // N_FOLDS),
             "candidates_per_gpu": args.cands, "folds": N_FOLDS, "items_total": n_items,
             "parallelism": ("one lock-step batch on 1 GPU" if world == 1 else
-                            "chunks of %d items claimed dynamically by %d GPUs from a shared counter; one all-gather of "
-                            "(score, theta) records per step" % (args.chunk, world)),
+                            ("items dealt longest-first over %d GPUs on the cost measured in the previous step (EP sweeps); "
+                             % world if args.deal == "lpt" else
+                             "chunks of %d items claimed dynamically by %d GPUs from a shared counter; " % (args.chunk, world))
+                            + "one all-gather of (score, theta) records per step"),
             "l2": "inputs larger than L2 (per-step working set >> 126 MB: %d x 5 n^2 FP64 matrices per rank)" % (args.cands * N_FOLDS)}
 
 
@@ -286,7 +288,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cands", type=int, default=8, help="candidate structures per GPU (x5 folds = items per step)")
     ap.add_argument("--points", type=int, default=N_POINTS)
-    ap.add_argument("--chunk", type=int, default=8, help="items per dynamically dealt chunk when N > 1")
+    ap.add_argument("--deal", default="lpt", choices=["lpt", "dynamic"],
+                    help="N > 1: cost-aware static dealing re-dealt from measured cost (lpt) or chunks claimed from a shared counter")
+    ap.add_argument("--chunk", type=int, default=8, help="items per chunk with --deal dynamic")
     ap.add_argument("--train-evals", type=int, default=50,
                     help="objective-evaluation budget per fold of the train_e2e leg (SURVEY 8d: 5 x 50 = 250 per candidate); 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -334,32 +338,25 @@ def main():
     rows = [folds[it[1]][0] for it in items]
     stride = max(p.n_theta for p in progs)
     n_max = max(len(r) for r in rows)
-    # Work distribution.  One GPU: the rank's 40 items are ONE lock-step batch.  Several GPUs: the global item list is cut
-    # into chunks of `--chunk` consecutive items which the ranks CLAIM from a shared counter as they go
-    # (sharding.WorkQueue) -- a rank whose items converge in fewer EP sweeps simply takes more chunks, so nobody idles at
-    # the all-gather; every rank keeps the (small) inputs of ALL items resident so that any chunk can run anywhere.
-    G = n_items if world == 1 else max(1, args.chunk)
-    chunks = [(lo, min(lo + G, n_items)) for lo in range(0, n_items, G)]
-    B = n_items   # rows of the device tables
-
-    # ---- device-resident inputs / outputs for `value` ----
+    # Work distribution (weak scaling: 40 items per GPU on average).  One GPU: the 40 items are ONE lock-step batch.
+    # Several GPUs, `--deal lpt` (default): every rank runs its share as one lock-step batch; the shares are dealt
+    # longest-processing-time-first (sharding.deal_items) on a cost estimate per item -- a-priori (structure type) for the
+    # first step, then the MEASURED cost of the previous step (EP sweeps taken, exchanged with the records anyway), so the
+    # ranks finish together and nobody idles at the all-gather.  `--deal dynamic`: chunks of `--chunk` consecutive items
+    # claimed from a shared counter (sharding.WorkQueue); measured slower here because 8-item batches run the
+    # factorisations ~20 % less efficiently than 40-item ones (profiles/r02_summary.md).
+    # Every rank keeps the (small) inputs of ALL items resident so that any item can run anywhere.
+    B = n_items
     th_h = np.zeros((B, stride))
     for b, t in enumerate(thetas):
         th_h[b, :len(t)] = t
-    row_off = np.zeros(B + 1, dtype=np.int64)
-    row_off[1:] = np.cumsum([len(r) for r in rows])
-    rows_cat = np.concatenate(rows).astype(np.int32)
-    th_d = torch.from_numpy(th_h).to(dev)
-    rows_d = torch.from_numpy(rows_cat).to(dev)
-    tau_d = torch.zeros((B, n_max), dtype=torch.float64, device=dev)
-    nu_d = torch.zeros_like(tau_d)
+    th_all = torch.from_numpy(th_h).to(dev)
+    # results of every item this rank has scored (device path), by global item id
     nlml_d = torch.zeros(B, dtype=torch.float64, device=dev)
     grad_d = torch.zeros((B, stride), dtype=torch.float64, device=dev)
     bic_d = torch.zeros_like(nlml_d)
-    gauss_d = torch.zeros_like(nlml_d)
     sweeps_d = torch.zeros(B, dtype=torch.int32, device=dev)
     status_d = torch.zeros(B, dtype=torch.int32, device=dev)
-    prog_arrs = [(Program * (hi - lo))(*progs[lo:hi]) for lo, hi in chunks]
     opt = EPOptions(1e-6, 0.0, 100, 0, 0, 0)   # damping 0 = the engine's automatic schedule (production default)
     did = eng.dataset(data.X, data.Y)
     # one explicit stream for torch, the timing events and the engine's launches (a NULL stream would make the engine use
@@ -367,44 +364,104 @@ def main():
     side = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(side)
     stream = side.cuda_stream
-    chunks_done_total = [0]
-    rank_busy_ms = []   # per step: this rank's time from the start of the step until its last chunk finished
+    rank_busy_ms = []   # per step: this rank's time from the start of the step until its last batch finished
+    units_run = [0]
 
-    def exchange(done, nlml_np, bic_np, status_np):
-        """All-gather of the (score, theta) records of the chunks this rank processed."""
-        if world == 1:
-            return
-        ids = [i for c in done for i in range(*chunks[c])]
-        local = np.zeros((len(ids), sharding.RECORD_WIDTH))
-        for j, i in enumerate(ids):
-            local[j] = sharding.pack_record(i, nlml_np[i], bic_np[i], 0.0, int(status_np[i]), thetas[i])
-        sharding.allgather_records(local, n_items, per_rank_max=n_items)
+    def item_prior(i):
+        p = progs[i]
+        types = [p.leaf_type[l] for l in range(p.n_leaves)]
+        return sharding.item_cost(len(rows[i]), p.n_leaves, sum(1 for t in types if t == 1))
 
-    def claim_loop(run_chunk):
+    costs = [item_prior(i) for i in range(n_items)]
+    state = {"mine": sharding.shard_indices(n_items, rank, world, costs) if world > 1 else list(range(n_items))}
+    chunks = [list(range(lo, min(lo + max(1, args.chunk), n_items))) for lo in range(0, n_items, max(1, args.chunk))]
+    preps = {}
+
+    def prepare(ids):
+        """Compact device-resident inputs / outputs of one lock-step batch (cached: assignments repeat)."""
+        key = tuple(ids)
+        if key not in preps:
+            nb = len(ids)
+            off = np.zeros(nb + 1, dtype=np.int64)
+            off[1:] = np.cumsum([len(rows[i]) for i in ids])
+            idx = torch.tensor(ids, dtype=torch.long, device=dev)
+            preps[key] = dict(
+                nb=nb, idx=idx, off=off, prog=(Program * nb)(*[progs[i] for i in ids]),
+                th=th_all.index_select(0, idx).contiguous(),
+                rows=torch.from_numpy(np.concatenate([rows[i] for i in ids]).astype(np.int32)).to(dev),
+                tau=torch.zeros((nb, n_max), dtype=torch.float64, device=dev),
+                nu=torch.zeros((nb, n_max), dtype=torch.float64, device=dev),
+                nlml=torch.zeros(nb, dtype=torch.float64, device=dev), bic=torch.zeros(nb, dtype=torch.float64, device=dev),
+                gauss=torch.zeros(nb, dtype=torch.float64, device=dev),
+                grad=torch.zeros((nb, stride), dtype=torch.float64, device=dev),
+                sweeps=torch.zeros(nb, dtype=torch.int32, device=dev), status=torch.zeros(nb, dtype=torch.int32, device=dev))
+            while len(preps) > 64:
+                preps.pop(next(iter(preps)))
+        return preps[key]
+
+    def run_unit_device(ids):
+        p = prepare(ids)
+        eng.score_batch_dev(did, p["prog"], p["nb"], p["th"].data_ptr(), stride, p["rows"].data_ptr(), p["off"], opt,
+                            p["tau"].data_ptr(), p["nu"].data_ptr(), n_max, p["nlml"].data_ptr(), p["grad"].data_ptr(),
+                            p["bic"].data_ptr(), p["gauss"].data_ptr(), p["sweeps"].data_ptr(), p["status"].data_ptr(), stream)
+        nlml_d.index_copy_(0, p["idx"], p["nlml"])
+        bic_d.index_copy_(0, p["idx"], p["bic"])
+        grad_d.index_copy_(0, p["idx"], p["grad"])
+        sweeps_d.index_copy_(0, p["idx"], p["sweeps"])
+        status_d.index_copy_(0, p["idx"], p["status"])
+
+    def my_units(run_unit):
+        """Runs this rank's work of one step; returns the item ids it scored."""
+        if world == 1 or args.deal == "lpt":
+            if state["mine"]:
+                run_unit(state["mine"])
+                units_run[0] += 1
+            return list(state["mine"])
         q = sharding.WorkQueue(len(chunks), tag="bench")
         done = []
         while True:
             c = q.claim()
             if c is None:
                 return done
-            run_chunk(c)
-            done.append(c)
+            run_unit(chunks[c])
+            units_run[0] += 1
+            done += chunks[c]
 
-    def run_chunk_device(c):
-        lo, hi = chunks[c]
-        eng.score_batch_dev(did, prog_arrs[c], hi - lo, th_d[lo].data_ptr(), stride, rows_d.data_ptr(), row_off[lo:hi + 1].copy(),
-                            opt, tau_d[lo].data_ptr(), nu_d[lo].data_ptr(), n_max, nlml_d[lo:].data_ptr(),
-                            grad_d[lo].data_ptr(), bic_d[lo:].data_ptr(), gauss_d[lo:].data_ptr(), sweeps_d[lo:].data_ptr(),
-                            status_d[lo:].data_ptr(), stream)
+    def exchange(ids, nlml_np, bic_np, status_np, sweeps_np):
+        """All-gather of the (score, theta) records of the items this rank scored; re-deals the next step's shares."""
+        if world == 1:
+            return
+        local = np.zeros((len(ids), sharding.RECORD_WIDTH))
+        for j, i in enumerate(ids):   # the cv-error slot carries the EP sweep count: the measured cost of the item
+            local[j] = sharding.pack_record(i, nlml_np[i], bic_np[i], float(sweeps_np[i]), int(status_np[i]), thetas[i])
+        table = sharding.allgather_records(local, n_items, per_rank_max=n_items)
+        if args.deal == "lpt":
+            # cost model of one item: S sweeps = S - 1 factorisations + inverses, the final one, lauum -> ~ 2 S + 1 units
+            # of n^3 / 3; then calibrated per rank: the items of a rank are scaled so that they add up to the time that
+            # rank actually took (the late sweeps of a batch run with few items left, which no per-item model sees)
+            model = np.array([(2.0 * table[i, 3] + 1.0) * float(len(rows[i])) ** 3 for i in range(n_items)])
+            busy = torch.zeros(world, dtype=torch.float64, device=dev)
+            busy[rank] = rank_busy_ms[-1] if rank_busy_ms else 0.0
+            dist.all_reduce(busy)
+            own = torch.full((n_items,), -1.0, dtype=torch.float64, device=dev)
+            own[torch.tensor(ids, dtype=torch.long, device=dev)] = float(rank)
+            dist.all_reduce(own, op=dist.ReduceOp.MAX)
+            owner = own.cpu().numpy().astype(int)
+            busy = busy.cpu().numpy()
+            if np.all(busy > 0) and np.all(owner >= 0):
+                for rr in range(world):
+                    sel = owner == rr
+                    if sel.any():
+                        model[sel] *= busy[rr] / model[sel].sum()
+            state["mine"] = sharding.shard_indices(n_items, rank, world, list(model))
 
     def step_device():
         t0 = time.perf_counter()
-        done = claim_loop(run_chunk_device)
-        chunks_done_total[0] += len(done)
+        ids = my_units(run_unit_device)
         if world > 1:
             torch.cuda.synchronize()
             rank_busy_ms.append(1e3 * (time.perf_counter() - t0))
-            exchange(done, nlml_d.cpu().numpy(), bic_d.cpu().numpy(), status_d.cpu().numpy())
+            exchange(ids, nlml_d.cpu().numpy(), bic_d.cpu().numpy(), status_d.cpu().numpy(), sweeps_d.cpu().numpy())
 
     def barrier():
         if world > 1:
@@ -446,8 +503,9 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    sweeps_mean = float(sweeps_d.float().mean().item())
-    status_ok = int((status_d == 0).sum().item())
+    scored = nlml_d != 0
+    sweeps_mean = float(sweeps_d[scored].float().mean().item())
+    status_ok = int(((status_d == 0) & scored).sum().item())
     n_cands_total = len(cands)
     value = n_cands_total * args.steps / (ms * 1e-3)
 
@@ -463,26 +521,26 @@ def main():
         t0 = time.perf_counter()
         d = eng.dataset(Xp, yp)
         t1 = time.perf_counter()
-        r = {"nlml": np.full(n_items, np.nan), "bic": np.full(n_items, np.nan), "status": np.zeros(n_items, dtype=np.int32)}
+        r = {"nlml": np.full(n_items, np.nan), "bic": np.full(n_items, np.nan), "status": np.zeros(n_items, dtype=np.int32),
+             "sweeps": np.zeros(n_items, dtype=np.int32)}
 
-        def run_chunk_host(c):
-            lo, hi = chunks[c]
-            rc = eng.score_batch(d, progs[lo:hi], thetas_p[lo:hi], rows_p[lo:hi], damping=0.0)
+        def run_unit_host(ids):
+            rc = eng.score_batch(d, [progs[i] for i in ids], [thetas_p[i] for i in ids], [rows_p[i] for i in ids], damping=0.0)
             for k in r:
-                r[k][lo:hi] = rc[k]
-        done = claim_loop(run_chunk_host)
+                r[k][ids] = rc[k]
+        ids = my_units(run_unit_host)
         t2 = time.perf_counter()
         eng.dataset_free(d)
         t3 = time.perf_counter()
-        exchange(done, r["nlml"], r["bic"], r["status"])
-        r["done"] = done
+        exchange(ids, r["nlml"], r["bic"], r["status"], r["sweeps"])
+        r["done"] = ids
         t4 = time.perf_counter()
         for k, v in zip(host_ms, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
             host_ms[k] += 1e3 * v
         return r
 
     Bm = n_items // world   # items per rank and step (on average, with dynamic dealing)
-    h2d = Xp.nbytes + yp.nbytes + Bm * stride * 8 + rows_cat.nbytes // world + Bm * 8 + Bm * 784
+    h2d = Xp.nbytes + yp.nbytes + Bm * stride * 8 + Bm * n_max * 4 + Bm * 8 + Bm * 784
     d2h = Bm * (8 * 3 + 4 * 2 + stride * 8) + 2 * Bm * n_max * 8
     e2e_steps = max(1, min(args.steps, 5))
     if args.kernels_only:
@@ -518,7 +576,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = n_cands_total * e2e_steps / e2e_s
-    mine_ids = [i for c in r["done"] for i in range(*chunks[c])]
+    mine_ids = list(r["done"])
     same = bool(np.allclose(r["nlml"][mine_ids], nlml_d.cpu().numpy()[mine_ids], rtol=1e-9, atol=0, equal_nan=True))
 
 
@@ -623,7 +681,8 @@ def main():
             "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
             "evals_per_s": len(items) * args.steps / (ms * 1e-3),
             "ep_sweeps_mean": sweeps_mean, "items_ok": status_ok, "items_per_gpu": n_items // world,
-            "chunks_this_rank_per_step": chunks_done_total[0] / float(args.warmup + args.steps),
+            "batches_this_rank_per_step": units_run[0] / float(args.warmup + args.steps + e2e_steps + 1),
+            "dealing": "one batch" if world == 1 else args.deal,
             "int8_slices": int(os.environ.get("AGPC_OZAKI", "7") or 0),
         }
         if busy is not None:

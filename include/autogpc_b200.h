@@ -180,6 +180,12 @@ int agpc_kernel_grad(agpc_ctx* ctx, const agpc_program* program, const double* t
  * Uinv_dev when those are non-NULL.  info_dev[b] = 0 or AGPC_ST_NOT_PD. */
 int agpc_potrf(agpc_ctx* ctx, double* A_dev, int32_t n, int32_t batch, double* Minv_dev, double* Uinv_dev,
                int32_t* info_dev, void* stream);
+/* util.linalg.jitchol(A, maxtries=5) as GPy defines it: agpc_potrf, and for every matrix whose plain factorisation
+ * fails a retry on A + jitter I with jitter = mean(diag A) * 1e-6, times 10 per further failure, at most 5 jittered
+ * attempts; a non-positive or non-finite diagonal fails at once.  jitter_dev[b] = the jitter that succeeded (0 = none
+ * needed), info_dev[b] = 0 or AGPC_ST_NOT_PD.  The same ladder runs inside agpc_score_batch on B = I + S^1/2 K S^1/2
+ * (status AGPC_ST_JITTER); AGPC_JITTER=0 in the environment switches that one off. */
+int agpc_jitchol(agpc_ctx* ctx, double* A_dev, int32_t n, int32_t batch, double* jitter_dev, int32_t* info_dev, void* stream);
 /* C = alpha * A * B^T + beta * C on the TMA + DMMA tile kernel (M, N % 128 == 0, K % 16 == 0, contiguous) */
 int agpc_gemm_nt(agpc_ctx* ctx, const double* A_dev, const double* B_dev, double* C_dev, int32_t M, int32_t N,
                  int32_t K, double alpha, double beta, int32_t batch, void* stream);

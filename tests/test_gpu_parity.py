@@ -802,3 +802,82 @@ def test_cumulate_additive_kernels_on_engine_matches_oracle_backed_run(engine):
             eng_mod.set_default_engine(None)
     assert out[0][0] == out[1][0] and out[0][1] == out[1][1]
     assert np.allclose(out[0][2], out[1][2]) and np.allclose(out[0][3], out[1][3], rtol=1e-8)
+
+
+@pytest.mark.gpu
+def test_jitchol_building_block_matches_gpy_ladder(engine):
+    """agpc_jitchol against the oracle's restatement of GPy util/linalg.py jitchol (reached from gpckernel.py:245-246):
+    a healthy matrix needs no jitter; a numerically rank-deficient one with a slightly negative spectrum is recovered
+    with exactly jitter = mean(diag) 1e-6 10^k for the same k; a non-positive diagonal fails at once."""
+    torch = _torch()
+    rng = np.random.default_rng(5)
+    n = 256
+    G = rng.standard_normal((n, n))
+    good = G @ G.T / n + np.eye(n)
+    W = rng.standard_normal((n, 8))
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    low = W @ W.T                                            # rank 8 ...
+    bad1 = low - 3e-6 * np.mean(np.diag(low)) * (Q[:, :4] @ Q[:, :4].T)     # ... minus a few 3e-6-relative directions
+    bad2 = low - 5e-4 * np.mean(np.diag(low)) * (Q[:, :4] @ Q[:, :4].T)     # needs three decades of jitter
+    neg = good.copy()
+    neg[7, 7] = -1.0
+    mats = [good, bad1, bad2, neg]
+    A = torch.from_numpy(np.stack(mats)).cuda()
+    jit = torch.zeros(len(mats), dtype=torch.float64, device="cuda")
+    info = torch.zeros(len(mats), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    engine.jitchol(A.data_ptr(), n, len(mats), jit.data_ptr(), info.data_ptr())
+    torch.cuda.synchronize()
+    jit, info, L = jit.cpu().numpy(), info.cpu().numpy(), np.tril(A.cpu().numpy())
+    for b, Mx in enumerate(mats[:3]):
+        Lo, jo = orc.jitchol(Mx)
+        assert info[b] == 0
+        assert jit[b] == pytest.approx(jo, rel=1e-12, abs=0.0) and (jo > 0) == (b > 0)
+        assert np.abs(L[b] @ L[b].T - (Mx + jo * np.eye(n))).max() <= 1e-12 * np.abs(Mx).max()
+    assert jit[2] > 50 * jit[1]
+    assert info[3] == orc.ST_NOT_PD
+    with pytest.raises(Exception):
+        orc.jitchol(neg)
+
+
+@pytest.mark.gpu
+def test_jitter_ladder_inside_score_batch():
+    """The same ladder inside score_batch (jitchol of B = I + S^1/2 K S^1/2, gpckernel.py:245-246; what the bare except
+    at :196-199 tolerates).  B is built from PSD kernels and bounded below by I, so it cannot be made to fail reliably
+    (an indefiniteness at rounding level passes LAPACK's dpotrf too); the failure is injected: AGPC_FAULT_NOT_PD=2 makes
+    the plain attempt and the first jittered attempt of item 0 report NOT_PD, so the ladder must succeed on its second
+    rung (jitter = mean(diag B) 1e-5), flag AGPC_ST_JITTER, move the NLML by a relative ~1e-5 and leave item 1 alone.
+    With the ladder switched off the same fault leaves the item NOT_PD."""
+    import subprocess
+    import sys
+    code = r'''
+import json, os, sys
+import numpy as np
+sys.path.insert(0, %r)
+from autogpc_b200.engine import Engine
+from oracle import gpc_oracle as orc
+from tests.util import TREES, synth, to_engine_program
+X, y = synth(300, 2, 17)
+prog = orc.KernelProgram.from_tree(TREES["se0xse1"])
+ep = to_engine_program(prog)
+th = [np.array([1.3, 0.9, 0.8, 1.2]), np.array([0.7, 1.1, 1.5, 0.6])]
+rows = [np.arange(300, dtype=np.int32)] * 2
+e = Engine(0)
+d = e.dataset(X, y)
+r = e.score_batch(d, [ep, ep], th, rows)
+print(json.dumps({"status": r["status"].tolist(), "nlml": r["nlml"].tolist(), "sweeps": r["sweeps"].tolist()}))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def run(env):
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    import json
+    clean = run({})
+    hit = run({"AGPC_FAULT_NOT_PD": "2"})
+    off = run({"AGPC_FAULT_NOT_PD": "2", "AGPC_JITTER": "0"})
+    assert clean["status"] == [0, 0]
+    assert hit["status"] == [orc.ST_JITTER, 0] and hit["nlml"][1] == clean["nlml"][1]
+    rel = abs(hit["nlml"][0] - clean["nlml"][0]) / abs(clean["nlml"][0])
+    assert 0 < rel < 1e-3
+    assert off["status"][0] == orc.ST_NOT_PD and off["status"][1] == 0 and off["nlml"][1] == clean["nlml"][1]
