@@ -19,6 +19,8 @@
 // HBM-write-bound for one-exp programs, FP64-ALU / issue-bound once a term carries sin/cos.
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace agpc {
@@ -373,9 +375,24 @@ build_K_kernel(const BuildArgs a) {
 // written transposed through shared memory, which halves the exp / sincos work per stored element -- that, not
 // HBM, is what bounds this kernel for anything beyond a single SE term.
 constexpr int KT = 64, KT_THREADS = 256, KT_LD = KT + 1;
+// A CTA walks a STRIP of up to KT_STRIP consecutive tiles of one tile row: the kernel program, theta, the leaf
+// constants and the row panel are loaded once per strip instead of once per tile, and the column panel of the next
+// tile arrives by cp.async while the current tile is evaluated.  (Per-tile prologue + its two barriers were 28 % + 14 %
+// of the warp-time samples of the one-tile-per-CTA form, profiles/r01_build_K_v2_ncu_source_regions.txt.)
+constexpr int KT_STRIP = 8;
 
-__global__ void __launch_bounds__(KT_THREADS, 3)
-build_K_tiled_kernel(const BuildArgs a, const int symmetric, const int tiles_n) {
+// xc[d][r] = Xb[col0 + r][d], r < 64, by all 256 threads
+__device__ __forceinline__ void load_xc_async(double* xc, const double* __restrict__ Xb, int col0, int nb_pad, int D) {
+  const int r = threadIdx.x & 63, d0 = threadIdx.x >> 6;
+  const int g = col0 + r;
+  const bool ok = g < nb_pad;
+  const double* src = Xb + (ok ? (long long)g * D : 0);
+  for (int d = d0; d < D; d += 4) cp_async8(xc + d * KT + r, src + d, ok);
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(KT_THREADS, MINB)
+build_K_tiled_kernel(const BuildArgs a, const int symmetric, const int tiles_n, const int strip) {
   const int b = blockIdx.z;
   if (a.active != nullptr && a.active[b] == 0) return;
   extern __shared__ double smem[];
@@ -385,22 +402,31 @@ build_K_tiled_kernel(const BuildArgs a, const int symmetric, const int tiles_n) 
   if (threadIdx.x < 32) exp_tab[threadIdx.x] = EXP_T[threadIdx.x];
   const int D = a.D;
   double* xr = smem;                // [D][KT]
-  double* xc = smem + D * KT;       // [D][KT]
-  double* st = xc + D * KT;         // [KT][KT_LD] transposition buffer (symmetric mode)
-  int ti, tj;
-  if (symmetric) {
-    const int t = blockIdx.x;
-    ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);  // estimate; the loops below make it exact
-    while (ti * (ti + 1) / 2 > t) --ti;
-    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-    tj = t - ti * (ti + 1) / 2;
-  } else {
-    ti = blockIdx.x / tiles_n;
-    tj = blockIdx.x % tiles_n;
+  double* xc0 = smem + D * KT;      // [2][D][KT]: column panel, double-buffered across the strip
+  double* st = xc0 + 2 * D * KT;    // [KT][KT_LD] transposition buffer (symmetric mode)
+  // strip index -> (tile row, first tile column): row ti holds ti + 1 (symmetric) or tiles_n tiles
+  int ti = 0, tj0;
+  {
+    int t = blockIdx.x;
+    if (symmetric) {
+      for (;;) {
+        const int strips = (ti + 1 + strip - 1) / strip;
+        if (t < strips) break;
+        t -= strips;
+        ++ti;
+      }
+    } else {
+      const int strips = (tiles_n + strip - 1) / strip;
+      ti = t / strips;
+      t %= strips;
+    }
+    tj0 = t * strip;
   }
-  const int row0 = ti * KT, col0 = tj * KT;
-  load_x_tiles_async<KT>(xr, xc, a.Xa + (long long)b * a.xa_batch, a.Xb + (long long)b * a.xb_batch, row0, col0,
-                         a.na_pad, a.nb_pad, D);
+  const int row_tiles = symmetric ? ti + 1 : tiles_n;
+  const int n_tiles = min(strip, row_tiles - tj0);
+  const int row0 = ti * KT;
+  const double* Xb = a.Xb + (long long)b * a.xb_batch;
+  load_x_tiles_async<KT>(xr, xc0, a.Xa + (long long)b * a.xa_batch, Xb, row0, tj0 * KT, a.na_pad, a.nb_pad, D);
   load_program_raw(P, th_s, a.progs[b], a.theta + (long long)b * a.theta_stride, a.theta_stride);
   const int na = a.na_of ? a.na_of[b] : a.na_fixed, nb = a.nb_of ? a.nb_of[b] : a.nb_fixed;
   cp_async_wait_all();
@@ -408,6 +434,11 @@ build_K_tiled_kernel(const BuildArgs a, const int symmetric, const int tiles_n) 
   derive_leaf_consts(P, th_s);
   __syncthreads();
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  for (int kt = 0; kt < n_tiles; ++kt) {
+  const int tj = tj0 + kt;
+  const int col0 = tj * KT;
+  const double* xc = xc0 + (kt & 1) * D * KT;
+  if (kt + 1 < n_tiles) load_xc_async(xc0 + ((kt + 1) & 1) * D * KT, Xb, (tj + 1) * KT, a.nb_pad, D);
 
   // two passes of 2 x 4 pairs (rows ty + 16r, r = 2h, 2h + 1): keeps the live set under 80 registers -> 3 CTAs per SM,
   // which is what hides the load -> compute -> store latency chain of a tile (the kernel is latency-, not ALU-bound)
@@ -535,6 +566,10 @@ build_K_tiled_kernel(const BuildArgs a, const int symmetric, const int tiles_n) 
         }
       }
     }
+  }
+  // the next tile's column panel has landed; the transposition buffer and the panel just used are free again
+  cp_async_wait_all();
+  __syncthreads();
   }
 }
 
@@ -774,9 +809,12 @@ cudaError_t build_K_launch(const Launch& L, const BuildArgs& a, int batch, bool 
     return cudaGetLastError();
   }
   bool& configured = func_attr_done(__LINE__);
-  const size_t smem = sizeof(double) * (2 * (size_t)a.D * KT + KT * KT_LD);
+  const size_t smem = sizeof(double) * (3 * (size_t)a.D * KT + KT * KT_LD);
+  static const int occ = getenv("AGPC_KB_OCC") ? atoi(getenv("AGPC_KB_OCC")) : 2;   // resident CTAs per SM the kernel is built for
   if (!configured || smem > 48 * 1024) {
-    AGPC_CUDA_TRY(cudaFuncSetAttribute(build_K_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    AGPC_CUDA_TRY(cudaFuncSetAttribute(build_K_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(smem > 100 * 1024 ? smem : 100 * 1024)));
+    AGPC_CUDA_TRY(cudaFuncSetAttribute(build_K_tiled_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(smem > 100 * 1024 ? smem : 100 * 1024)));
     configured = true;
   }
@@ -786,8 +824,20 @@ cudaError_t build_K_launch(const Launch& L, const BuildArgs& a, int batch, bool 
   const int tiles_m = (a.na_pad + KT - 1) / KT;
   const int cols = symmetric ? a.na_pad : (int)a.ld;
   const int tiles_n = (cols + KT - 1) / KT;
-  dim3 grid(symmetric ? (unsigned)(tiles_m * (tiles_m + 1) / 2) : (unsigned)(tiles_m * tiles_n), 1, batch);
-  build_K_tiled_kernel<<<grid, KT_THREADS, smem, L.stream>>>(a, symmetric ? 1 : 0, tiles_n);
+  // strip length: as long as possible (KT_STRIP) while the launch still has ~4 CTAs per resident slot
+  const long long tiles_total = (symmetric ? (long long)tiles_m * (tiles_m + 1) / 2 : (long long)tiles_m * tiles_n) * batch;
+  int strip = (int)(tiles_total / (148LL * occ * 4));
+  strip = strip < 1 ? 1 : (strip > KT_STRIP ? KT_STRIP : strip);
+  unsigned strips = 0;
+  if (symmetric)
+    for (int ti = 0; ti < tiles_m; ++ti) strips += (unsigned)((ti + 1 + strip - 1) / strip);
+  else
+    strips = (unsigned)(tiles_m * ((tiles_n + strip - 1) / strip));
+  dim3 grid(strips, 1, batch);
+  if (occ == 2)
+    build_K_tiled_kernel<2><<<grid, KT_THREADS, smem, L.stream>>>(a, symmetric ? 1 : 0, tiles_n, strip);
+  else
+    build_K_tiled_kernel<3><<<grid, KT_THREADS, smem, L.stream>>>(a, symmetric ? 1 : 0, tiles_n, strip);
   L.bump();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;

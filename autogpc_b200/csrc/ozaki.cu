@@ -426,6 +426,11 @@ static cudaError_t oz_gemm_launch_t(const Launch& L, const OzGemmArgs& a, int ti
     AGPC_CUDA_TRY(cudaFuncSetAttribute(ozaki_gemm_kernel<S, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz_smem_bytes<S>()));
     configured = true;
   }
+  if (!PAIR) {
+    dim3 grid(2 * tiles128, groups, batch);
+    ozaki_gemm_kernel<S, false><<<grid, OZ_THREADS, oz_smem_bytes<S>(), L.stream>>>(a);
+    return cudaGetLastError();
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * tiles128, groups, batch);
   cfg.blockDim = dim3(OZ_THREADS);
@@ -478,8 +483,10 @@ cudaError_t oz_gemm_launch(const Launch& L, const OzGemmArgs& a, int tiles128, i
   if (L.prof && L.prof->enabled)
     L.add_work(oz_cls, 2.0 * oz_executed_macs(a, tiles128, groups, S) * (a.active ? (double)(L.work_items < batch ? L.work_items : batch) : (double)batch));
   L.bump();
-  // pairs need both halves of a tile to run the same K range (KRULE_END_AT_COL clips per half); AGPC_OZ_PAIR=0: single CTAs
-  static const bool pair_env = !(getenv("AGPC_OZ_PAIR") && atoi(getenv("AGPC_OZ_PAIR")) == 0);
+  // AGPC_OZ_PAIR=1: 2-CTA multicast pairs.  Measured no faster (profiles/r02_summary.md: the kernel is bound by operand
+  // delivery into the tensor core, not by L2 -> SM traffic), so single CTAs are the default.  Pairs need both halves of a
+  // tile to run the same K range (KRULE_END_AT_COL clips per half).
+  static const bool pair_env = getenv("AGPC_OZ_PAIR") && atoi(getenv("AGPC_OZ_PAIR")) != 0;
   const bool pair = pair_env && a.k_rule != KRULE_END_AT_COL;
   if (S == 6) return pair ? oz_gemm_launch_t<6, true>(L, a, tiles128, groups, batch) : oz_gemm_launch_t<6, false>(L, a, tiles128, groups, batch);
   return pair ? oz_gemm_launch_t<7, true>(L, a, tiles128, groups, batch) : oz_gemm_launch_t<7, false>(L, a, tiles128, groups, batch);

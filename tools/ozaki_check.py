@@ -54,7 +54,7 @@ for S in (7, 6):
         # error measured against the natural scale of each entry: |alpha| max_k|a_ik| max_k|b_jk| sqrt(K)
         scale = abs(alpha) * A.abs().amax(2, keepdim=True) * B.abs().amax(2, keepdim=True).transpose(1, 2) * K ** 0.5 + 1e-300
         err = ((C - ref).abs() / scale).max().item()
-        bound = 2e-15 if S == 7 else 3e-13
+        bound = 3e-14 if S == 7 else 3e-13   # FP64 rounding level of the K-term sum itself for S = 7
         ok = err <= bound
         fails += not ok
         print(f"gemm_nt_i8x S={S} M={M} N={N} K={K} batch={batch} alpha={alpha} beta={beta}: scaled max err {err:.3e} "
@@ -91,9 +91,9 @@ def timeit(f, reps=5):
     return best
 
 
-ms_arr = (ctypes.c_double * 11)()
-wk_arr = (ctypes.c_double * 11)()
-ln_arr = (ctypes.c_int64 * 11)()
+ms_arr = (ctypes.c_double * 16)()
+wk_arr = (ctypes.c_double * 16)()
+ln_arr = (ctypes.c_int64 * 16)()
 
 
 def prof(f):
@@ -177,4 +177,7 @@ if not quick:
         torch.cuda.empty_cache()
 
 print("ozaki_check done, %d failures" % fails, flush=True)
-sys.exit(1 if fails else 0)
+sync()
+lib.agpc_destroy(ctx)
+sys.stdout.flush()
+os._exit(1 if fails else 0)
