@@ -239,14 +239,14 @@ cudaError_t dmu_dx_launch(const Launch& L, const agpc_program* prog, const doubl
 // ep.cu
 cudaError_t rowdot_launch(const Launch& L, int range, bool sq, const double* A, const double* x, double* y,
                           double* y2, int nrows, int ncols, long long a_batch, long long x_batch, long long y_batch,
-                          int batch, const int* active);
+                          int batch, const int* active, bool strict_sq = false);
 cudaError_t sqrt_scale_launch(const Launch& L, const double* tau, const double* w, double* s, double* u, int np,
                               int batch, const int* active);
 cudaError_t mul_launch(const Launch& L, const double* a, const double* b, double* out, int np, int batch,
                        const int* active);
-cudaError_t marginals_launch(const Launch& L, const double* tau, const double* dB, const double* w, const double* kv,
-                             const double* kdiag, double* sig, double* mu, const int* n_of, int np, int batch, int cold,
-                             const int* active);
+cudaError_t marginals_launch(const Launch& L, const double* tau, const double* usq, const double* lsq, const double* Lmat,
+                             long long l_stride, const double* w, const double* kv, const double* kdiag, double* sig,
+                             double* mu, const int* n_of, int np, int batch, int cold, const int* active);
 cudaError_t ep_update_launch(const Launch& L, double* tau, double* nu, const double* sig, const double* mu,
                              const double* yf, const double* kdiag, const int* n_of, int np, int batch, double eps,
                              double damping, int min_sweeps, int* active, int* sweeps, int* status, int* converged,

@@ -15,8 +15,8 @@ namespace agpc {
 
 // ---- row-oriented matrix-vector kernels: one warp per row, coalesced along the row ---------------------------
 // y_i = sum_{k in range(i)} A[i,k] x_k ;  optionally y2_i = sum_{k in range(i)} A[i,k]^2
-// range: 0 = all k < np, 1 = k <= i (lower), 2 = k >= i (upper)
-template <int RANGE, bool SQ>
+// range: 0 = all k < np, 1 = k <= i (lower), 2 = k >= i (upper); STRICT: the sum of squares leaves the diagonal out
+template <int RANGE, bool SQ, bool STRICT = false>
 __global__ void __launch_bounds__(256)
 rowdot_kernel(const double* __restrict__ A, const double* __restrict__ x, double* __restrict__ y,
               double* __restrict__ y2, int nrows, int ncols, long long a_batch, long long x_batch, long long y_batch,
@@ -39,11 +39,11 @@ rowdot_kernel(const double* __restrict__ A, const double* __restrict__ x, double
     const double2 x2 = *reinterpret_cast<const double2*>(xb + k);
     if (k >= k0) {
       s += a2.x * x2.x;
-      if (SQ) q += a2.x * a2.x;
+      if (SQ && !(STRICT && k == i)) q += a2.x * a2.x;
     }
     if (k + 1 < k1) {
       s += a2.y * x2.y;
-      if (SQ) q += a2.y * a2.y;
+      if (SQ && !(STRICT && k + 1 == i)) q += a2.y * a2.y;
     }
   }
 #pragma unroll
@@ -60,16 +60,20 @@ rowdot_kernel(const double* __restrict__ A, const double* __restrict__ x, double
 // range: 0 full row, 1 lower (k <= i), 2 upper (k >= i); sq: also y2_i = sum A[i,k]^2 over the same range
 cudaError_t rowdot_launch(const Launch& L, int range, bool sq, const double* A, const double* x, double* y,
                           double* y2, int nrows, int ncols, long long a_batch, long long x_batch, long long y_batch,
-                          int batch, const int* active) {
+                          int batch, const int* active, bool strict_sq) {
   ProfScope prof_scope(L, CLS_MATVEC);
   dim3 grid((nrows + 7) / 8, batch);
 #define RD(R, S) rowdot_kernel<R, S><<<grid, 256, 0, L.stream>>>(A, x, y, y2, nrows, ncols, a_batch, x_batch, y_batch, active)
-  if (range == 0 && !sq) RD(0, false);
+#define RDS(R) rowdot_kernel<R, true, true><<<grid, 256, 0, L.stream>>>(A, x, y, y2, nrows, ncols, a_batch, x_batch, y_batch, active)
+  if (strict_sq && range == 1) RDS(1);
+  else if (strict_sq && range == 2) RDS(2);
+  else if (range == 0 && !sq) RD(0, false);
   else if (range == 0) RD(0, true);
   else if (range == 1) RD(1, false);
   else if (sq) RD(2, true);
   else RD(2, false);
 #undef RD
+#undef RDS
   L.bump();
   return cudaGetLastError();
 }
@@ -107,8 +111,15 @@ __global__ void mul_kernel(const double* __restrict__ a, const double* __restric
   const long long o = (long long)b * np + i;
   out[o] = a[o] * bvec[o];
 }
-// sig = (1 - dB) / tau (or kdiag when tau == 0 everywhere: cold start), mu = w - kv
-__global__ void marginals_kernel(const double* __restrict__ tau, const double* __restrict__ dB,
+// Posterior marginals.  mu = w - kv.  Variance (kdiag when tau == 0 everywhere: cold start):
+//   Sigma_ii = (1 - (B^-1)_ii) / tau_i  with  (B^-1)_ii = sum_k M_ki^2 = 1 / L_ii^2 + usq_i,  usq_i = sum_{k>i} U_ik^2.
+// Evaluated literally that identity cancels against 1 and loses everything once tau_i Sigma_ii < 1e-16 -- sites at
+// the tau floor of a kernel with K_ii ~ 1e6 (two of the 4096 models of configs[4] ended non-finite that way).  With
+// L_ii^2 - 1 = tau_i K_ii - lsq_i,  lsq_i = sum_{k<i} L_ik^2, everything is O(tau_i) BEFORE the subtraction:
+//   Sigma_ii = ((tau_i K_ii - lsq_i) / L_ii^2 - usq_i) / tau_i
+// whose only cancellation is K_ii against the explained variance, as in GPy's  diag(K) - sum(V^2, 0).
+__global__ void marginals_kernel(const double* __restrict__ tau, const double* __restrict__ usq,
+                                 const double* __restrict__ lsq, const double* __restrict__ Lmat, long long l_stride,
                                  const double* __restrict__ w, const double* __restrict__ kv,
                                  const double* __restrict__ kdiag, double* __restrict__ sig, double* __restrict__ mu,
                                  const int* __restrict__ n_of, int np, int cold, const int* __restrict__ active) {
@@ -126,7 +137,9 @@ __global__ void marginals_kernel(const double* __restrict__ tau, const double* _
     sig[o] = kdiag[o];
     mu[o] = 0.0;
   } else {
-    sig[o] = (1.0 - dB[o]) / tau[o];
+    const double lii = Lmat[(long long)b * l_stride + (long long)i * np + i];
+    const double t = tau[o];
+    sig[o] = (fma(t, kdiag[o], -lsq[o]) / (lii * lii) - usq[o]) / t;
     mu[o] = w[o] - kv[o];
   }
 }
@@ -147,12 +160,12 @@ cudaError_t mul_launch(const Launch& L, const double* a, const double* b, double
   L.bump();
   return cudaGetLastError();
 }
-cudaError_t marginals_launch(const Launch& L, const double* tau, const double* dB, const double* w, const double* kv,
-                             const double* kdiag, double* sig, double* mu, const int* n_of, int np, int batch, int cold,
-                             const int* active) {
+cudaError_t marginals_launch(const Launch& L, const double* tau, const double* usq, const double* lsq, const double* Lmat,
+                             long long l_stride, const double* w, const double* kv, const double* kdiag, double* sig,
+                             double* mu, const int* n_of, int np, int batch, int cold, const int* active) {
   ProfScope prof_scope(L, CLS_EP);
   dim3 grid((np + 255) / 256, batch);
-  marginals_kernel<<<grid, 256, 0, L.stream>>>(tau, dB, w, kv, kdiag, sig, mu, n_of, np, cold, active);
+  marginals_kernel<<<grid, 256, 0, L.stream>>>(tau, usq, lsq, Lmat, l_stride, w, kv, kdiag, sig, mu, n_of, np, cold, active);
   L.bump();
   return cudaGetLastError();
 }

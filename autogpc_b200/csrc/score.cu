@@ -50,7 +50,7 @@ struct Carver {
 struct Chunk {
   int nb = 0, np = 0, D = 0, theta_stride = 0;
   MatSet ms;
-  double *tau, *nu, *s, *sig, *mu, *w, *u, *t, *z, *kv, *dB, *alpha, *kdiag, *yf, *tmp;
+  double *tau, *nu, *s, *sig, *mu, *w, *u, *t, *z, *kv, *dB, *alpha, *kdiag, *yf, *tmp, *lsq, *lsq_dummy;
   double* Xf;
   int *n_of, *active, *sweeps, *status, *converged, *info, *ones;
   int *jit_tries, *jit_retry, *jit_used;  // jitchol ladder state per item
@@ -77,6 +77,7 @@ struct Chunk {
     mu = c.take<double>(vec); w = c.take<double>(vec); u = c.take<double>(vec); t = c.take<double>(vec);
     z = c.take<double>(vec); kv = c.take<double>(vec); dB = c.take<double>(vec); alpha = c.take<double>(vec);
     kdiag = c.take<double>(vec); yf = c.take<double>(vec); tmp = c.take<double>(vec);
+    lsq = c.take<double>(vec); lsq_dummy = c.take<double>(vec);
     Xf = c.take<double>(vec * D);
     n_of = c.take<int>(nb); active = c.take<int>(nb); sweeps = c.take<int>(nb); status = c.take<int>(nb);
     converged = c.take<int>(nb); info = c.take<int>(nb); ones = c.take<int>(nb);
@@ -190,7 +191,7 @@ cudaError_t posterior(agpc_ctx* ctx, const Launch& L, Chunk& c, const int* activ
   {
     const double wn = L.work_n > 0.0 ? L.work_n : (double)np, n2 = 8.0 * wn * wn * L.work_items;
     L.add_work(CLS_FORMB, n2);          // read lower K, write lower B
-    L.add_work(CLS_MATVEC, 3.0 * n2);   // two full K passes, two triangular passes over M and U
+    L.add_work(CLS_MATVEC, 3.5 * n2);   // two full K passes, three triangular passes over M, U and L
   }
   AGPC_CUDA_TRY(sqrt_scale_launch(L, c.tau, nullptr, c.s, nullptr, np, nb, active));
   AGPC_CUDA_TRY(form_B_launch(L, c.ms.K, c.s, c.ms.A, np, st, nb, active));
@@ -202,10 +203,12 @@ cudaError_t posterior(agpc_ctx* ctx, const Launch& L, Chunk& c, const int* activ
   AGPC_CUDA_TRY(rowdot_launch(L, 0, false, c.ms.K, c.nu, c.w, nullptr, np, np, st, np, np, nb, active));
   AGPC_CUDA_TRY(mul_launch(L, c.s, c.w, c.u, np, nb, active));
   AGPC_CUDA_TRY(rowdot_launch(L, 1, false, c.ms.M, c.u, c.t, nullptr, np, np, st, np, np, nb, active));
-  AGPC_CUDA_TRY(rowdot_launch(L, 2, true, c.ms.U, c.t, c.z, c.dB, np, np, st, np, np, nb, active));
+  // z = U t and usq_i = sum_{k>i} U_ik^2; lsq_i = sum_{k<i} L_ik^2 (one more triangular pass, over L): see marginals_kernel
+  AGPC_CUDA_TRY(rowdot_launch(L, 2, true, c.ms.U, c.t, c.z, c.dB, np, np, st, np, np, nb, active, true));
+  AGPC_CUDA_TRY(rowdot_launch(L, 1, true, c.ms.A, c.t, c.lsq_dummy, c.lsq, np, np, st, np, np, nb, active, true));
   AGPC_CUDA_TRY(mul_launch(L, c.s, c.z, c.tmp, np, nb, active));
   AGPC_CUDA_TRY(rowdot_launch(L, 0, false, c.ms.K, c.tmp, c.kv, nullptr, np, np, st, np, np, nb, active));
-  AGPC_CUDA_TRY(marginals_launch(L, c.tau, c.dB, c.w, c.kv, c.kdiag, c.sig, c.mu, c.n_of, np, nb, 0, active));
+  AGPC_CUDA_TRY(marginals_launch(L, c.tau, c.dB, c.lsq, c.ms.A, st, c.w, c.kv, c.kdiag, c.sig, c.mu, c.n_of, np, nb, 0, active));
   return cudaSuccess;
 }
 
@@ -272,7 +275,7 @@ int ep_chunk(agpc_ctx* ctx, Launch& L, Chunk& c, const agpc_ep_options* opt, int
   // ---- EP sweeps (parallel schedule) ----
   for (int sweep = 1; sweep <= opt->max_sweeps; ++sweep) {
     if (sweep == 1 && !warm) {
-      CK(marginals_launch(L, c.tau, c.dB, c.w, c.kv, c.kdiag, c.sig, c.mu, c.n_of, np, nb, 1, c.active));
+      CK(marginals_launch(L, c.tau, c.dB, c.lsq, c.ms.A, c.ms.stride, c.w, c.kv, c.kdiag, c.sig, c.mu, c.n_of, np, nb, 1, c.active));
     } else {
       CK(posterior(ctx, L, c, c.active));
     }

@@ -60,11 +60,57 @@ elif mode == "large":
     dt = time.time() - t0
     prof = eng.profile_read()
     g = prof["gemm"]
-    print(json.dumps({"config": "configs[3] single composite SE0xSE1+Per2+SE3, n=%d, one cold evaluation" % n, "seconds": dt,
-                      "ep_sweeps": int(r["sweeps"][0]), "status": int(r["status"][0]), "nlml": float(r["nlml"][0]),
-                      "grad_norm": float(np.linalg.norm(r["grad"][0])),
-                      "gemm_tflops": g["work"] / (g["ms"] * 1e-3) / 1e12, "kernel_ms": {k: v["ms"] for k, v in prof.items()},
-                      "kbuild_gbs": prof["kbuild"]["work"] / (prof["kbuild"]["ms"] * 1e-3) / 1e9}))
+    out = {"config": "configs[3] single composite SE0xSE1+Per2+SE3, n=%d, one cold evaluation" % n, "seconds": dt,
+           "ep_sweeps": int(r["sweeps"][0]), "status": int(r["status"][0]), "nlml": float(r["nlml"][0]),
+           "grad_norm": float(np.linalg.norm(r["grad"][0])),
+           "gemm_tflops": g["work"] / (g["ms"] * 1e-3) / 1e12, "kernel_ms": {k: v["ms"] for k, v in prof.items()},
+           "kbuild_gbs": prof["kbuild"]["work"] / (prof["kbuild"]["ms"] * 1e-3) / 1e9}
+    eng.profile_enable(False)
+    # ---- correctness at size (no CPU oracle finishes here): (1) the gradient against a directional central difference
+    #      of the NLML through re-converged EP; (2) the factorisation residuals of B = I + S^1/2 K S^1/2 at the final sites
+    rng = np.random.default_rng(0)
+    d = rng.standard_normal(len(th))
+    d /= np.linalg.norm(d)
+    h = 1e-4
+    tight = dict(epsilon=1e-12, max_sweeps=200)
+    rp = eng.score_batch(did, [p], [th * np.exp(h * d)], rows, **tight)
+    rm = eng.score_batch(did, [p], [th * np.exp(-h * d)], rows, **tight)
+    r0 = eng.score_batch(did, [p], [th], rows, **tight)
+    fd = (rp["nlml"][0] - rm["nlml"][0]) / (2 * h)
+    an = float(np.dot(r0["grad"][0, :len(th)] * th, d))   # d/dh NLML(theta exp(h d)) = sum_j g_j theta_j d_j
+    out["directional_derivative"] = {"finite_difference": float(fd), "analytic": an, "rel_diff": float(abs(fd - an) / abs(an)),
+                                     "h": h, "nlml_tight_vs_default_rel": float(abs(r0["nlml"][0] - r["nlml"][0]) / abs(r["nlml"][0]))}
+    import torch
+    from autogpc_b200.engine import Program as _P
+    st = torch.cuda.Stream()
+    torch.cuda.set_stream(st)
+    Xd = torch.from_numpy(X).cuda()
+    K = torch.empty(n, n, dtype=torch.float64, device="cuda")
+    eng.build_K(p, th, Xd.data_ptr(), n, 4, K.data_ptr(), n, 0, st.cuda_stream)
+    sroot = torch.from_numpy(np.sqrt(r0["tau"][0][:n])).cuda()
+    K.mul_(sroot[:, None]).mul_(sroot[None, :])
+    K.diagonal().add_(1.0)                                   # K now holds B
+    A = K.clone()
+    Mi = torch.empty_like(K)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    eng.potrf(A.data_ptr(), n, 1, Mi.data_ptr(), 0, 0, st.cuda_stream)
+    torch.cuda.synchronize()
+    t_f = time.time() - t0
+    L = torch.tril(A)
+    del A
+    R = L @ L.T
+    R.sub_(K)
+    res1 = float(R.abs().max().item() / K.abs().max().item())
+    del R, K
+    Ml = torch.tril(Mi)
+    del Mi
+    R = Ml @ L
+    R.diagonal().sub_(1.0)
+    res2 = float(R.abs().max().item())
+    out["factorisation_residuals"] = {"LLt_minus_B_over_B": res1, "ML_minus_I": res2, "potrf_trtri_seconds": t_f,
+                                      "potrf_trtri_tflops": 2 * n ** 3 / 3.0 / t_f / 1e12}
+    print(json.dumps(out))
 
 elif mode == "small":
     n, n_struct, n_restart = 1024, 64, 64
@@ -97,4 +143,7 @@ elif mode == "small":
                                 % (len(progs), len(pool), n_restart, n),
                       "seconds": dt, "models_per_s": len(progs) / dt, "ep_sweeps_mean": float(np.mean(r["sweeps"])),
                       "status_ok": int(np.sum(r["status"] == 0)),
+                      "not_ok": [{"item": int(i), "structure": pool[i // n_restart].kernel.structure(), "status": int(r["status"][i]),
+                                  "sweeps": int(r["sweeps"][i]), "nlml": float(r["nlml"][i]),
+                                  "theta": [float(v) for v in thetas[i]]} for i in np.nonzero(r["status"] != 0)[0][:8]],
                       "gemm_tflops": g["work"] / (g["ms"] * 1e-3) / 1e12, "kernel_ms": {k: v["ms"] for k, v in prof.items()}}))
