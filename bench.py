@@ -7,9 +7,9 @@
 
 Workload (weak scaling, synthetic): N = 8000 points, D = 8, 5 folds (n = 6400 training points per model).  The
 candidate pool is what gpcsearch generates with SE/LIN/PER bases (depth-1 and depth-2 expansions): one block of 8
-candidates, one per structure shape, and per additional GPU the same block with the input dimensions shifted -- distinct
-candidates, identical composition, fixed per-GPU work; every rank owns `--cands` candidates x 5 folds = 40 items by default (round-robin by global item id,
-autogpc_b200/sharding.py).  One STEP = every item of the rank taken through one full cold-start
+candidates, one per structure shape, and per additional GPU the same block with fresh random restarts (distinct models,
+the same expected work per GPU); `--cands` candidates x 5 folds = 40 items per GPU, dealt over the ranks longest-first
+on their measured cost (autogpc_b200/sharding.py).  One STEP = every item of the rank taken through one full cold-start
 evaluation -- K build, parallel EP to epsilon = 1e-6, blocked FP64 Cholesky / triangular inverse per sweep, log Z_EP,
 gradient, BIC -- followed (N > 1) by the NCCL all-gather of the (score, theta) records.  A candidate counts as scored
 when its 5 fold models have been evaluated: value = candidates / s over all ranks.
@@ -68,12 +68,7 @@ def build_workload(world: int, cands_per_gpu: int, n_points: int = N_POINTS):
     depth2 = [k for k in depth1[0].expand(base_kernels="SE,Lin,Per") if len(k.getActiveDims()) > 1]
     # One BLOCK of `cands_per_gpu` candidates is a stratified sample of what a search to depth 3 scores (24 / 42 / 72
     # candidates per level, i.e. mostly composite ones): 3 depth-1 and 5 depth-2 structures per 8, both strata shuffled
-    # with a fixed seed (the expansions come grouped by base kernel: SE.., Lin.., Per..).  The candidates of world rank
-    # block j > 0 are the SAME structures with every input dimension shifted by j (mod D): distinct candidates, identical
-    # structure-type composition, so the per-GPU work stays fixed as the world grows -- weak scaling.  (Earlier versions
-    # took "the next 8 candidates of the pool" per added GPU: the cost of a candidate depends on its structure type --
-    # EP sweeps 3 to 9 -- so one GPU happened to score a lighter sample than two or eight, which read as a 15-20 %
-    # scaling loss although no rank ever waits on another.)
+    # with a fixed seed (the expansions come grouped by base kernel: SE.., Lin.., Per..).
     prng = np.random.default_rng(0)
     d1 = [depth1[i] for i in prng.permutation(len(depth1))]
     d2 = [depth2[i] for i in prng.permutation(len(depth2))]
@@ -103,20 +98,14 @@ def build_workload(world: int, cands_per_gpu: int, n_points: int = N_POINTS):
     p1, p2 = pick(d1, n1, set()), pick(d2, cands_per_gpu - n1, set())
     block = [(p1.pop(0) if i % 8 in (0, 3, 6) else p2.pop(0)) for i in range(cands_per_gpu)]
 
-    def shifted(gk_kernel, j):
-        k = gk_kernel.kernel.copy()
-        stack = [k]
-        while stack:
-            node = stack.pop()
-            if getattr(node, "is_operator", False):
-                stack.extend(node.operands)
-            elif getattr(node, "dimension", None) is not None:
-                node.dimension = (node.dimension + j) % N_DIM
-        return gk.GPCKernel(k.canonical(), data, depth=gk_kernel.depth)
-
+    # Every further GPU adds the SAME block of structures with its own random restarts (BASELINE configs[2]: "candidates
+    # and restarts sharded across 1/2/4/8 B200"): resetGpssParams below draws a fresh theta_0 for every (candidate, fold,
+    # block) from the one seeded stream, so the items are distinct models while the expected work per GPU is fixed --
+    # weak scaling.  (Round 1 shifted the input dimensions per block instead: those blocks need systematically more EP
+    # sweeps -- 4.1-4.6 against 3.9 -- because the signal sits in dimensions 0-5, i.e. the per-GPU work GREW with N.)
     cands = []
     for j in range(world):
-        cands += block if j % N_DIM == 0 and j == 0 else [shifted(c, j % N_DIM) for c in block]
+        cands += block if j == 0 else [gk.GPCKernel(c.kernel.copy(), data, depth=c.depth) for c in block]
     folds = data.kFoldIndices(N_FOLDS)
     items = []
     for ci, c in enumerate(cands):
