@@ -310,6 +310,255 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzGemmA
   }
 }
 
+// ---- 128 x 128 tile, accumulators split over a CTA pair ------------------------------------------------------------------
+// The 128 x 64 kernel above is bound by operand delivery: a 128 x 64 x 32 instruction takes 48-55 cycles, a 128 x 128 x
+// 32 one 64 (profiles/r02_summary.md), but S accumulators of 128 columns do not fit the 512 TMEM columns of one SM.
+// Here the two CTAs of a cluster own the SAME 128 x 128 tile and split the weight groups d = p + q between them (S = 7:
+// CTA 0 takes d in {0, 1, 2, 6} = 13 products, CTA 1 d in {3, 4, 5} = 15): each issues N = 128 instructions into 4 / 3
+// accumulators of 128 columns.  Both need (nearly) all operand slices, so CTA 0 loads the A stage and CTA 1 the B stage
+// and each copy is multicast into both shared memories.  Epilogue: every CTA forms its partial FP64 sum for all 128
+// columns, keeps the 64 columns it finalises (CTA r: columns 64 r ..) and writes the other 64 into the peer's shared
+// memory (DSMEM); after a cluster barrier each adds the two partials, scales and updates its half of C.
+constexpr int OZ2_STAGES = 3;
+template <int S>
+constexpr int oz2_stage_bytes() {
+  return S * 2 * TILE * OZ_KB;
+}
+template <int S>
+constexpr int oz2_smem_bytes() {
+  return OZ2_STAGES * oz2_stage_bytes<S>() + 1024 + 256;
+}
+constexpr int OZ2_EPI_LD = OZ_BN + 1;
+static_assert(2 * TILE * OZ2_EPI_LD * 8 <= OZ2_STAGES * oz2_stage_bytes<6>(), "the two epilogue buffers must fit the ring");
+
+// weight groups of CTA `rank`, as a bit mask over d = 0 .. S-1 (product counts 13 | 15 for S = 7, 12 | 9 for S = 6)
+template <int S>
+__host__ __device__ constexpr uint32_t oz2_groups(int rank) {
+  return S == 7 ? (rank == 0 ? 0x47u : 0x38u) : (rank == 0 ? 0x27u : 0x18u);
+}
+
+template <int S>
+__global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm128_kernel(const OzGemmArgs args) {
+  using namespace oz;
+  constexpr int CPB = TILE / OZ_KB;
+  const int b = blockIdx.z;
+  if (args.active != nullptr && args.active[b] == 0) return;
+  const int g = blockIdx.y;
+  int h2 = 0;
+  if (args.grp_blocks > 0) {
+    h2 = args.nblk - g * args.grp_blocks - args.half_blocks;
+    h2 = h2 < 0 ? 0 : (h2 > args.half_blocks ? args.half_blocks : h2);
+  }
+  const int shift = g * args.grp_blocks * TILE;
+  const int mt = args.m_kind == EXT_H2 ? h2 : args.m_tiles;
+  const int nt = args.n_kind == EXT_H2 ? h2 : args.n_tiles;
+  const int kt = args.k_kind == EXT_H2 ? h2 * CPB : args.k_chunks;
+  if (mt <= 0 || nt <= 0) return;
+  const int rank = blockIdx.x & 1;  // position in the CTA pair (cluster of 2 along x)
+  const int t = blockIdx.x >> 1;
+  int ti, tj;
+  if (args.lower_only) {
+    if (t >= mt * (mt + 1) / 2) return;
+    ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while (ti * (ti + 1) / 2 > t) --ti;
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    tj = t - ti * (ti + 1) / 2;
+  } else {
+    ti = t / nt;
+    tj = t % nt;
+    if (ti >= mt) return;
+    if (args.skip_upper && tj > ti) return;
+  }
+  int k_begin = 0, k_end = kt;
+  if (args.k_rule == KRULE_BEGIN_AT_ROW) k_begin = ti * CPB;
+  if (args.k_rule == KRULE_END_AT_ROW) k_end = min(kt, (ti + 1) * CPB);
+  if (args.k_rule == KRULE_END_AT_COL) k_end = min(kt, (tj + 1) * CPB);
+  const int n_iter = k_end - k_begin;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  constexpr uint32_t SLICE = TILE * OZ_KB;          // 4 KB: one digit slice of 128 rows x 32 k
+  constexpr uint32_t STAGE = oz2_stage_bytes<S>();  // A slices 0..S-1, then B slices 0..S-1
+  const uint32_t bars = smem_base + OZ2_STAGES * STAGE;  // full[0..ST), empty[0..ST), accf
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + OZ2_STAGES * STAGE + 8 * (2 * OZ2_STAGES + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2 * OZ2_STAGES + 1; ++s) mbar_init(bars + 8 * s, (s >= OZ2_STAGES && s < 2 * OZ2_STAGES) ? 2 : 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  const int a_row = args.a_row0 + shift + ti * TILE;
+  const int b_row = args.b_row0 + shift + tj * TILE;
+  constexpr uint32_t GROUPS0 = oz2_groups<S>(0), GROUPS1 = oz2_groups<S>(1);
+  const uint32_t my_groups = rank ? GROUPS1 : GROUPS0;
+
+  if (warp == 0) {
+    // ---------------- producer: CTA 0 brings the A stage, CTA 1 the B stage, each into BOTH shared memories ------------
+    if (lane == 0) {
+      const OzOperand& op = rank ? args.B : args.A;
+      const int row = rank ? b_row : a_row;
+      const int col0 = (rank ? args.b_col0 : args.a_col0) + shift;
+      const long long tile = (long long)(row >> 7) * op.nkc + (col0 / OZ_KB) + k_begin;
+      const int8_t* src = op.S + (long long)b * op.s_batch + tile * (S * (long long)SLICE);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % OZ2_STAGES;
+        const uint32_t ph = (uint32_t)(it / OZ2_STAGES) & 1u;
+        mbar_wait(bars + 8 * (OZ2_STAGES + s), ph ^ 1u);
+        const uint32_t full = bars + 8 * s;
+        mbar_expect_tx(full, STAGE);
+        bulk_g2s_mc(smem_base + s * STAGE + rank * (S * SLICE), src + (long long)it * (S * (long long)SLICE), S * SLICE, full, (uint16_t)3);
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer: this CTA's weight groups, N = 128 ----------------
+    if (lane == 0) {
+      constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+      constexpr uint64_t DESC_HI = (1ull << 16) | ((uint64_t)((8 * OZ_KB) >> 4) << 32) | (1ull << 46) | (6ull << 61);
+      // accumulator column of weight group d in this CTA: its rank among the CTA's groups, times 128
+      uint32_t col_of[S];
+      {
+        uint32_t c = 0;
+#pragma unroll
+        for (int d = 0; d < S; ++d) {
+          col_of[d] = c * TILE;
+          if ((my_groups >> d) & 1u) ++c;
+        }
+      }
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % OZ2_STAGES;
+        const uint32_t ph = (uint32_t)(it / OZ2_STAGES) & 1u;
+        mbar_wait(bars + 8 * s, ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_base + s * STAGE, sb = sa + S * SLICE;
+        uint32_t touched = 0;
+#pragma unroll
+        for (int p = 0; p < S; ++p) {
+          const uint64_t da = DESC_HI | (uint64_t)(((sa + p * SLICE) >> 4) & 0x3FFF);
+#pragma unroll
+          for (int q = 0; q < S - p; ++q) {
+            const int d = p + q;
+            if (!((my_groups >> d) & 1u)) continue;
+            const uint64_t db = DESC_HI | (uint64_t)(((sb + q * SLICE) >> 4) & 0x3FFF);
+            // an accumulator is overwritten by its first product of the tile and accumulated into afterwards
+            const uint32_t acc = (it == 0 && !((touched >> d) & 1u)) ? 0u : 1u;
+            touched |= 1u << d;
+            umma_i8(tmem + col_of[d], da, db, IDESC, acc, 0);
+          }
+        }
+        umma_commit_mc(bars + 8 * (OZ2_STAGES + s), (uint16_t)3);  // the stage is free once BOTH CTAs have read it
+      }
+      if (n_iter > 0) umma_commit(bars + 8 * (2 * OZ2_STAGES));
+    }
+  }
+  // ---------------- epilogue ----------------
+  double* mine = reinterpret_cast<double*>(smem_gen);          // [128][65]: my partial sums of the 64 columns I finalise
+  double* inbox = mine + TILE * OZ2_EPI_LD;                    // [128][65]: the peer's partial sums of the same columns
+  if (warp >= 2 && n_iter > 0) {
+    mbar_wait(bars + 8 * (2 * OZ2_STAGES), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  __syncwarp();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs are past their main loops: the rings (and the peer's) are free to become epilogue buffers
+  if (warp >= 2) {
+    const int ew = warp - 2, q4 = warp & 3, ch = ew >> 2;  // TMEM lane quarter, 64-column half
+    const int row = q4 * 32 + lane;
+    // the half this warp handles stays here when it is mine (ch == rank), else it goes to the peer's inbox
+    uint32_t dst_local = smem_u32(ch == rank ? mine : inbox) + (uint32_t)(row * OZ2_EPI_LD) * 8u;
+    uint32_t dst = dst_local;
+    if (ch != rank) asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(dst_local), "r"((uint32_t)(rank ^ 1)));
+    const uint32_t taddr = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(ch * 64);
+#pragma unroll 1
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      double sum[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) sum[j] = 0.0;
+      if (n_iter > 0) {
+        // Horner over this CTA's groups from the smallest weight up; the step between consecutive owned groups d' > d
+        // is 256^-(d' - d), and the lowest owned group carries 256^-d_min at the end
+        int prev = -1;
+        uint32_t c = 0;
+#pragma unroll
+        for (int d = 0; d < S; ++d)
+          if ((my_groups >> d) & 1u) ++c;
+#pragma unroll
+        for (int d = S - 1; d >= 0; --d) {
+          if (!((my_groups >> d) & 1u)) continue;
+          --c;
+          uint32_t v[16];
+          tmem_ld16(taddr + c * TILE + (uint32_t)c0, v);
+          tmem_ld_wait();
+          const double w = prev < 0 ? 0.0 : scalbn(1.0, -8 * (prev - d));
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sum[j] = fma(sum[j], w, (double)(int)v[j]);
+          prev = d;
+        }
+        const double w0 = scalbn(1.0, -8 * prev);  // prev = lowest owned group
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sum[j] *= w0;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(dst + (uint32_t)(c0 + j) * 8u), "d"(sum[j]) : "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();  // partial sums exchanged
+  if (warp >= 2) {
+    const int ew = warp - 2;
+    const long long c_row = (long long)args.c_row0 + shift + ti * TILE;
+    const long long c_col = (long long)args.c_col0 + shift + tj * TILE + rank * OZ_BN;
+    const int bcol = b_row + rank * OZ_BN;  // B-operand rows = C columns of my half
+    const double2 sb2 = *reinterpret_cast<const double2*>(args.B.scale + (long long)b * args.B.sc_batch + bcol + 2 * lane);
+    const double* sA = args.A.scale + (long long)b * args.A.sc_batch + a_row;
+    double* Cb = args.C + (long long)b * args.c_batch;
+    const double alpha = args.alpha, beta = args.beta;
+    for (int rr = ew; rr < TILE; rr += 8) {
+      const double sa = sA[rr] * alpha;
+      double2 v;
+      v.x = (mine[rr * OZ2_EPI_LD + 2 * lane] + inbox[rr * OZ2_EPI_LD + 2 * lane]) * sa * sb2.x;
+      v.y = (mine[rr * OZ2_EPI_LD + 2 * lane + 1] + inbox[rr * OZ2_EPI_LD + 2 * lane + 1]) * sa * sb2.y;
+      double2* dstp = reinterpret_cast<double2*>(Cb + (c_row + rr) * args.ldc + c_col + 2 * lane);
+      if (beta != 0.0) {
+        const double2 old = *dstp;
+        v.x = fma(beta, old.x, v.x);
+        v.y = fma(beta, old.y, v.y);
+      }
+      *dstp = v;
+    }
+    if (args.Ct != nullptr) {
+      const long long t_row = (long long)args.ct_row0 + shift + tj * TILE + rank * OZ_BN;
+      const long long t_col = (long long)args.ct_col0 + shift + ti * TILE;
+      double* Tb = args.Ct + (long long)b * args.c_batch;
+      for (int cc = ew; cc < OZ_BN; cc += 8) {
+        const double sbc = args.B.scale[(long long)b * args.B.sc_batch + bcol + cc] * alpha;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = lane + 32 * i;
+          Tb[(t_row + cc) * args.ldc + t_col + r] = (mine[r * OZ2_EPI_LD + cc] + inbox[r * OZ2_EPI_LD + cc]) * sA[r] * sbc;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+  }
+}
+
 // ---- slicing: FP64 region -> S int8 digit tiles (shared-memory image) + one scale per row --------------------------
 // One CTA per 128-row block of the region.  Pass 1: row maxima over the K range (8 warps x 16 rows, coalesced row reads)
 // -> e_i, 2^(8S - e_i) kept in shared memory, 2^(e_i - 8) written out for the GEMM epilogue.  Pass 2: per K chunk every
@@ -475,6 +724,28 @@ static double oz_executed_macs(const OzGemmArgs& a, int tiles128, int groups, in
   return chunks * (S * (S + 1) / 2) * (double)TILE * OZ_BN * OZ_KB;
 }
 
+template <int S>
+static cudaError_t oz_gemm128_launch_t(const Launch& L, const OzGemmArgs& a, int tiles128, int groups, int batch) {
+  bool& configured = func_attr_done(__LINE__ + S);
+  if (!configured) {
+    AGPC_CUDA_TRY(cudaFuncSetAttribute(ozaki_gemm128_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz2_smem_bytes<S>()));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * tiles128, groups, batch);
+  cfg.blockDim = dim3(OZ_THREADS);
+  cfg.dynamicSmemBytes = oz2_smem_bytes<S>();
+  cfg.stream = L.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, ozaki_gemm128_kernel<S>, a);
+}
+
 cudaError_t oz_gemm_launch(const Launch& L, const OzGemmArgs& a, int tiles128, int groups, int batch, int S) {
   ProfScope prof_scope(L, L.gemm_cls);
   const int oz_cls = L.gemm_cls == CLS_GEMM_TRTRI ? CLS_OZ_TRTRI : L.gemm_cls == CLS_GEMM_LAUUM ? CLS_OZ_LAUUM : CLS_OZ_POTRF;
@@ -486,6 +757,9 @@ cudaError_t oz_gemm_launch(const Launch& L, const OzGemmArgs& a, int tiles128, i
   // AGPC_OZ_PAIR=1: 2-CTA multicast pairs.  Measured no faster (profiles/r02_summary.md: the kernel is bound by operand
   // delivery into the tensor core, not by L2 -> SM traffic), so single CTAs are the default.  Pairs need both halves of a
   // tile to run the same K range (KRULE_END_AT_COL clips per half).
+  // AGPC_OZ_TILE=128: the 128 x 128 tile with its accumulators split over a CTA pair (ozaki_gemm128_kernel)
+  static const int tile_env = getenv("AGPC_OZ_TILE") ? atoi(getenv("AGPC_OZ_TILE")) : 64;
+  if (tile_env == 128) return S == 6 ? oz_gemm128_launch_t<6>(L, a, tiles128, groups, batch) : oz_gemm128_launch_t<7>(L, a, tiles128, groups, batch);
   static const bool pair_env = getenv("AGPC_OZ_PAIR") && atoi(getenv("AGPC_OZ_PAIR")) != 0;
   const bool pair = pair_env && a.k_rule != KRULE_END_AT_COL;
   if (S == 6) return pair ? oz_gemm_launch_t<6, true>(L, a, tiles128, groups, batch) : oz_gemm_launch_t<6, false>(L, a, tiles128, groups, batch);

@@ -129,12 +129,13 @@ ts_kernel(const int8_t* __restrict__ A, const int8_t* __restrict__ B, int32_t* _
 }
 
 template <int S, int NT, int DB, int KS>
-int run(int reps_rate) {
+int run(int reps_rate, int data_mode = 0) {
   const int Ktot = KS * KB;
   std::vector<int8_t> hA((size_t)S * 128 * Ktot), hB((size_t)S * N * Ktot);
   srand(99 + S + NT);
-  for (auto& x : hA) x = (int8_t)(rand() % 256 - 128);
-  for (auto& x : hB) x = (int8_t)(rand() % 256 - 128);
+  // data_mode: 0 = random full-range digits, 1 = small digits 0..3, 2 = all zero (the MMA timing depends on the data)
+  for (auto& x : hA) x = data_mode == 2 ? 0 : data_mode == 1 ? (int8_t)(rand() % 4) : (int8_t)(rand() % 256 - 128);
+  for (auto& x : hB) x = data_mode == 2 ? 0 : data_mode == 1 ? (int8_t)(rand() % 4) : (int8_t)(rand() % 256 - 128);
   std::vector<int32_t> ref((size_t)S * 128 * N, 0), got((size_t)S * 128 * N, -1);
   for (int p = 0; p < S; ++p)
     for (int q = 0; p + q < S; ++q)
@@ -172,9 +173,9 @@ int run(int reps_rate) {
   long long cyc[148];
   CK(cudaMemcpy(cyc, dC, sizeof cyc, cudaMemcpyDeviceToHost));
   const double ksteps = (double)reps_rate * KS;
-  printf("S=%d A-slices in TMEM=%d double-buffered=%d k-steps=%d : %s (%zu / %zu mismatches) | %.0f cycles per k-step "
+  printf("data=%s S=%d A-slices in TMEM=%d double-buffered=%d k-steps=%d : %s (%zu / %zu mismatches) | %.0f cycles per k-step "
          "(%d MMAs + %d cp), %.1f TF-equivalent chip (FP64 flops of the 128x64x32 tile-step / time)\n",
-         S, NT, DB, KS, bad ? "FAIL" : "ok", bad, got.size(), cyc[0] / ksteps, S * (S + 1) / 2, NT,
+         data_mode == 2 ? "zero" : data_mode == 1 ? "small" : "random", S, NT, DB, KS, bad ? "FAIL" : "ok", bad, got.size(), cyc[0] / ksteps, S * (S + 1) / 2, NT,
          2.0 * 128 * N * 32 * ksteps * 148 / (ms * 1e-3) / 1e12);
   cudaFree(dA); cudaFree(dB); cudaFree(dO); cudaFree(dC);
   return bad ? 1 : 0;
@@ -183,6 +184,10 @@ int run(int reps_rate) {
 int main() {
   int bad = 0;
   bad += run<7, 0, 0, 4>(200);   // all SS: baseline (1344 cycles per k-step expected)
+  bad += run<7, 0, 0, 4>(200, 1);
+  bad += run<7, 0, 0, 4>(200, 2);
+  bad += run<7, 0, 0, 4>(2000, 0);   // 10 x longer: set-up amortised, wall-clock rate ~ cycle rate if the clock holds
+  bad += run<7, 0, 0, 4>(2000, 2);
   bad += run<7, 7, 0, 4>(200);   // all A slices in TMEM, single buffer: relies on mma -> cp ordering
   bad += run<7, 4, 1, 4>(200);   // A_0..A_3 in TMEM, double-buffered (64 spare columns)
   bad += run<7, 4, 0, 4>(200);
