@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzGemmA
 // and each copy is multicast into both shared memories.  Epilogue: every CTA forms its partial FP64 sum for all 128
 // columns, keeps the 64 columns it finalises (CTA r: columns 64 r ..) and writes the other 64 into the peer's shared
 // memory (DSMEM); after a cluster barrier each adds the two partials, scales and updates its half of C.
-constexpr int OZ2_STAGES = 3;
+constexpr int OZ2_STAGES = 4;
 template <int S>
 constexpr int oz2_stage_bytes() {
   return S * 2 * TILE * OZ_KB;

@@ -4,7 +4,9 @@ This file is the *checker* for the CUDA engine in ``autogpc_b200/csrc``.  Only `
 ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it.
 The product path never does: ``autogpc_b200`` fails loudly when its CUDA library is missing.
 
-PARITY UNPINNED.  The reference (``/root/reference``, charles92/autogpc) contains none of this arithmetic: it
+PARITY UNPINNED for the EP recursion; the kernel functions (kern_K, kern_dK) and the Gaussian log-marginal are pinned
+against scikit-learn (independent code) in ``tests/test_oracle_pinned.py``.  The reference (``/root/reference``,
+charles92/autogpc) contains none of this arithmetic: it
 delegates to GPy (SheffieldML/GPy, un-vendored and un-pinned: ``README.md:14-19``; era ~GPy 0.8-1.0, Python 2.7),
 paramz and SciPy, none of which exist in the build image, and none of the reference's own tests asserts a numerical
 value (``gpckerneltest.py:88-107,121`` are structural).  What follows is therefore a NumPy/SciPy FP64 restatement of
