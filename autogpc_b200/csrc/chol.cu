@@ -11,6 +11,8 @@
 //   trtri  : level-synchronous recursive doubling, M21 = -M22 L21 M11, two batched triangular-aware GEMMs per level;
 //            both M = L^-1 and U = M^T are kept so every product is in K-contiguous ("NT") form.
 //   lauum  : B^-1 = U U^T, lower tiles only, K range clipped at the tile row.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace agpc {
@@ -325,8 +327,85 @@ static cudaError_t potrf_slice_panel(const Launch& L, const MatSet& ms, const in
   if (nblk - r0 <= 0) return cudaSuccess;
   OzSliceArgs a = oz_slice_args(ms, ms.A, false, active);
   a.row0 = r0 * TILE; a.col0 = k0 * TILE; a.row_blocks = nblk - r0; a.col_chunks = kb * OZ_CPB;
+  a.fixed_scale = ms.scA;  // row scales from |L_ik| <= sqrt(B_ii) (oz_row_bound_launch): every panel of L shares them
   L.add_work(CLS_SLICE, 8.0 * (double)(nblk - r0) * TILE * kb * TILE * L.work_items);
   return oz_slice_launch(L, a, nblk - r0, 1, ms.batch, ms.oz_S);
+}
+
+static cudaError_t potrf_panels(const Launch& L, const MatSet& ms, const int* active, int* info, int k0, int kb,
+                                bool first_staged);
+
+// Left-looking update of one outer block column from the persistent digit slices of the panels factored so far:
+//   C[k0:, k0 : k0 + kb] -= L[k0:, kc0 : kc0 + kcb] L[k0 : k0 + kb, kc0 : kc0 + kcb]^T     (tiles on or below the diagonal)
+// One call with a long K range replaces kc / 4 right-looking K = 512 passes over the same tiles: the per-tile prologue and
+// epilogue of the int8 kernel (a third of a K = 512 launch) are paid once per tile instead of once per outer block.
+static cudaError_t potrf_update_oz(const Launch& L, const MatSet& ms, const int* active, int k0, int kb, int kc0, int kcb,
+                                   bool stage_first_col) {
+  const int nblk = ms.np / TILE;
+  const int rows = nblk - k0;
+  if (rows <= 0 || kcb <= 0) return cudaSuccess;
+  OzGemmArgs z{};
+  z.A = oz_operand(ms, false); z.B = z.A;
+  z.C = ms.A; z.Ct = nullptr; z.ldc = ms.np; z.c_batch = ms.stride;
+  z.a_row0 = k0 * TILE; z.a_col0 = kc0 * TILE; z.b_row0 = k0 * TILE; z.b_col0 = kc0 * TILE;
+  z.c_row0 = k0 * TILE; z.c_col0 = k0 * TILE;
+  z.k_chunks = kcb * OZ_CPB; z.k_rule = KRULE_FULL; z.alpha = -1.0; z.beta = 1.0; z.active = active;
+  const int nc = kb < rows ? kb : rows;
+  z.m_tiles = rows; z.n_tiles = nc; z.lower_only = 0; z.skip_upper = 1;
+  AGPC_CUDA_TRY(oz_gemm_launch(L, z, rows * nc, 1, ms.batch, ms.oz_S));
+  if (stage_first_col && rows > 1)  // the thin panel solve reads its panel from the M scratch
+    AGPC_CUDA_TRY(copy_panel_launch(L, ms.A, ms.M, ms.np, ms.stride, (k0 + 1) * TILE, k0 * TILE, (rows - 1) * TILE, ms.batch, active));
+  return cudaSuccess;
+}
+
+// potrf on the int8 tensor-core path: LEFT-looking over outer blocks.  Block column j is brought up to date from all
+// earlier panels right before it is factored -- part 1 (every panel but the last outer block's: long K) on the caller's
+// stream while the previous block's panel chain still runs on the high-priority stream, part 2 (the last outer block,
+// K = 512) on the chain itself.
+//   hi:  part2(j) [after part1(j)] | panels(j) | slice(j) | part2(j+1) ...
+//   lo:  part1(j+1) [after slice(j-1)]                     | part1(j+2) ...
+static cudaError_t potrf_blocked_oz(const Launch& L, const MatSet& ms, const int* active, int* info) {
+  const int nblk = ms.np / TILE;
+  AGPC_CUDA_TRY(oz_row_bound_launch(L, ms.A, ms.np, ms.stride, ms.np, ms.batch, ms.scA, ms.np, active));
+  const bool lookahead = L.side != nullptr && nblk > 2 * POTRF_OUTER;
+  if (!lookahead) {
+    for (int k0 = 0; k0 < nblk; k0 += POTRF_OUTER) {
+      const int kb = nblk - k0 < POTRF_OUTER ? nblk - k0 : POTRF_OUTER;
+      const bool thin = (nblk - k0 - 1) * ms.batch <= THIN_CTA_LIMIT;
+      if (k0 > 0) AGPC_CUDA_TRY(potrf_update_oz(L, ms, active, k0, kb, 0, k0, thin));
+      AGPC_CUDA_TRY(potrf_panels(L, ms, active, info, k0, kb, k0 > 0 && thin));
+      if (k0 + kb < nblk) AGPC_CUDA_TRY(potrf_slice_panel(L, ms, active, k0, kb, k0 + kb));
+    }
+    return cudaSuccess;
+  }
+  Launch H = L;
+  H.stream = L.side;
+  AGPC_CUDA_TRY(cudaEventRecord(L.ev_rest, L.stream));  // everything queued so far (form_B, the row bounds) precedes the chain
+  AGPC_CUDA_TRY(cudaStreamWaitEvent(H.stream, L.ev_rest, 0));
+  for (int k0 = 0; k0 < nblk; k0 += POTRF_OUTER) {
+    const int kb = nblk - k0 < POTRF_OUTER ? nblk - k0 : POTRF_OUTER;
+    const int r0 = k0 + kb;
+    const bool thin = (nblk - k0 - 1) * ms.batch <= THIN_CTA_LIMIT;
+    // (a) the chain needs part 1 of THIS block column (queued on the caller's stream one iteration ago)
+    if (k0 > POTRF_OUTER) AGPC_CUDA_TRY(cudaStreamWaitEvent(H.stream, L.ev_rest, 0));
+    // (b) part 1 of the NEXT block column: all panels before this block; their slices were completed with ev_panel
+    if (k0 > 0 && r0 < nblk) {
+      const int kbn = nblk - r0 < POTRF_OUTER ? nblk - r0 : POTRF_OUTER;
+      AGPC_CUDA_TRY(cudaStreamWaitEvent(L.stream, L.ev_panel, 0));
+      AGPC_CUDA_TRY(potrf_update_oz(L, ms, active, r0, kbn, 0, k0, false));
+      AGPC_CUDA_TRY(cudaEventRecord(L.ev_rest, L.stream));
+    }
+    // (c) part 2 of this block column: the previous outer block (sliced at the end of the last iteration)
+    if (k0 > 0) AGPC_CUDA_TRY(potrf_update_oz(H, ms, active, k0, kb, k0 - POTRF_OUTER, POTRF_OUTER, thin));
+    // (d) factor it, slice it
+    AGPC_CUDA_TRY(potrf_panels(H, ms, active, info, k0, kb, k0 > 0 && thin));
+    if (r0 >= nblk) break;
+    AGPC_CUDA_TRY(potrf_slice_panel(H, ms, active, k0, kb, r0));
+    AGPC_CUDA_TRY(cudaEventRecord(L.ev_panel, H.stream));
+  }
+  AGPC_CUDA_TRY(cudaEventRecord(L.ev_panel, H.stream));  // join: the caller's stream continues after the chain
+  AGPC_CUDA_TRY(cudaStreamWaitEvent(L.stream, L.ev_panel, 0));
+  return cudaSuccess;
 }
 
 // panels k0 .. k0 + kb of one outer block: in-block left-looking update, diagonal block, panel solve
@@ -436,6 +515,8 @@ cudaError_t potrf_blocked(const Launch& L, const MatSet& ms, const int* active, 
   const int nblk = ms.np / TILE;
   const double wn = L.work_n > 0.0 ? L.work_n : (double)ms.np;
   L.add_work(CLS_GEMM, (double)L.work_items * wn * wn * wn / 3.0);  // LAPACK dpotrf count
+  static const bool right_looking = getenv("AGPC_OZ_RIGHT") && atoi(getenv("AGPC_OZ_RIGHT")) != 0;  // round-2 first form
+  if (oz_on(ms) && !right_looking) return potrf_blocked_oz(L, ms, active, info);
   const bool lookahead = L.side != nullptr && nblk > 2 * POTRF_OUTER;
   if (!lookahead) {
     for (int k0 = 0; k0 < nblk; k0 += POTRF_OUTER) {

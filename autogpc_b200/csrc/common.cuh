@@ -135,6 +135,8 @@ struct OzGemmArgs {  // same tile / group / K-range semantics as GemmArgs; n_til
   int k_rule, lower_only, skip_upper;
   double alpha, beta;
   const int* active;
+  int dbg;  // measurement aid (AGPC_OZ_DBG): 1 = main loop without MMAs (data movement only), 2 = without loads (MMAs on
+            // whatever the ring holds); results are garbage in both
 };
 struct OzSliceArgs {
   const double* X;  // source region: rows row0 .. , columns col0 .. (group g adds g * grp_blocks * 128 to both)
@@ -148,6 +150,8 @@ struct OzSliceArgs {
   int rows_kind, cols_kind;    // EXT_H2: right-half size of trtri group g
   int grp_blocks, half_blocks, nblk;
   int need_h2;  // grouped launches: skip groups without a right half (their left half may lie outside the matrix)
+  const double* fixed_scale;  // non-null: the row scales are GIVEN (scale[] already holds 2^(e - 8) from a bound on the row):
+                              // no row-maximum pass, slices made with different calls share their scales
   int tri;  // 0: whole rectangle; 1: chunks up to the end of the row block's own diagonal block (lower triangular
             // region); 2: chunks from the start of it (upper triangular).  The row scale covers exactly that range.
   const int* active;
@@ -155,6 +159,9 @@ struct OzSliceArgs {
 struct Launch;
 cudaError_t oz_gemm_launch(const Launch& L, const OzGemmArgs& a, int tiles128, int groups, int batch, int S);
 cudaError_t oz_slice_launch(const Launch& L, const OzSliceArgs& a, int row_blocks, int groups, int batch, int S);
+// scale[b][i] = 2^(e_i - 8) with 2^e_i > 4 sqrt(A_ii): |L_ik| <= sqrt(A_ii) for every entry of row i of the Cholesky factor
+cudaError_t oz_row_bound_launch(const Launch& L, const double* A, long long ld, long long a_batch, int n, int batch,
+                                double* scale, long long sc_batch, const int* active);
 
 // One lock-step batch of padded np x np matrices (np % 128 == 0, ld == np, matrix b at base + b*stride) and the
 // tensor maps the GEMM kernel reads them through.

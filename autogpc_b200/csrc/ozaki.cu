@@ -94,6 +94,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
                : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// exact int32 -> double without the conversion pipe: 2^52 + 2^31 + v has v in its low mantissa bits
+__device__ __forceinline__ double i32_to_f64(uint32_t v) {
+  return __hiloint2double(0x43300000, (int)(v ^ 0x80000000u)) - 4503601774854144.0;
+}
 
 }  // namespace oz
 
@@ -191,7 +195,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzGemmA
       const long long tileB = (long long)(b_row >> 7) * args.B.nkc + ((args.b_col0 + shift) / OZ_KB) + k_begin;
       const int8_t* srcA = args.A.S + (long long)b * args.A.s_batch + tileA * (S * (long long)A_SLICE);
       const int8_t* srcB = args.B.S + (long long)b * args.B.s_batch + tileB * (S * (long long)A_SLICE) + ((b_row >> 6) & 1) * B_SLICE;
-      for (int it = 0; it < n_iter; ++it) {
+      for (int it = 0; it < n_iter && args.dbg != 2; ++it) {
         const int s = it % OZ_STAGES;
         const uint32_t ph = (uint32_t)(it / OZ_STAGES) & 1u;
         mbar_wait(bars + 8 * (OZ_STAGES + s), ph ^ 1u);
@@ -220,9 +224,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzGemmA
       for (int it = 0; it < n_iter; ++it) {
         const int s = it % OZ_STAGES;
         const uint32_t ph = (uint32_t)(it / OZ_STAGES) & 1u;
-        mbar_wait(bars + 8 * s, ph);
+        if (args.dbg != 2) mbar_wait(bars + 8 * s, ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = smem_base + s * STAGE, sb = sa + S * A_SLICE;
+        if (args.dbg != 1)
 #pragma unroll
         for (int p = 0; p < S; ++p) {
           const uint64_t da = DESC_HI | (uint64_t)(((sa + p * A_SLICE) >> 4) & 0x3FFF);
@@ -265,7 +270,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzGemmA
           tmem_ld16(taddr + (uint32_t)(d * OZ_BN + c0), v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) sum[j] = fma(sum[j], 0.00390625, (double)(int)v[j]);
+          for (int j = 0; j < 16; ++j) sum[j] = fma(sum[j], 0.00390625, i32_to_f64(v[j]));
         }
       }
 #pragma unroll
@@ -501,7 +506,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm128_kernel(const OzGe
           tmem_ld_wait();
           const double w = prev < 0 ? 0.0 : scalbn(1.0, -8 * (prev - d));
 #pragma unroll
-          for (int j = 0; j < 16; ++j) sum[j] = fma(sum[j], w, (double)(int)v[j]);
+          for (int j = 0; j < 16; ++j) sum[j] = fma(sum[j], w, i32_to_f64(v[j]));
           prev = d;
         }
         const double w0 = scalbn(1.0, -8 * prev);  // prev = lowest owned group
@@ -586,6 +591,10 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const OzSliceArgs a) {
   const double* Xb = a.X + (long long)b * a.x_batch;
   __shared__ double s_mult[TILE];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (a.fixed_scale != nullptr) {
+    // given scales 2^(e - 8): multiplier 2^(8S - e) = 2^(8S - 8) / scale, exact
+    if (tid < TILE) s_mult[tid] = scalbn(1.0, 8 * S - 8) / a.fixed_scale[(long long)b * a.sc_batch + row_base + tid];
+  } else
   for (int rr = 0; rr < 16; ++rr) {
     const int r = warp * 16 + rr;
     const double* p = Xb + (long long)(row_base + r) * a.ld + col_base;
@@ -648,6 +657,22 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const OzSliceArgs a) {
       const double mult = s_mult[r];
       const double x[4] = {v[i][0].x, v[i][0].y, v[i][1].x, v[i][1].y};
       uint32_t lo[4], hi[4];
+      if (a.fixed_scale != nullptr) {
+        // no row-maximum pass looked at the data: a non-finite entry poisons the row's scale here, and an entry
+        // above the bound saturates instead of wrapping around
+        constexpr double LIM = (double)(1ull << (8 * S - 2)) * 1.9;
+        bool bad = false;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) bad |= !(fabs(x[e]) <= 1.7976931348623157e308);
+        if (bad) a.scale[(long long)b * a.sc_batch + row_base + r] = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const double t = fmin(fmax(x[e] * mult, -LIM), LIM);
+          const unsigned long long z = ((unsigned long long)__double2ll_rn(bad ? 0.0 : t) + BIAS) ^ BIAS;
+          lo[e] = (uint32_t)z;
+          hi[e] = (uint32_t)(z >> 32);
+        }
+      } else
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const unsigned long long z = ((unsigned long long)__double2ll_rn(x[e] * mult) + BIAS) ^ BIAS;
@@ -665,6 +690,27 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const OzSliceArgs a) {
       }
     }
   }
+}
+
+// scale[i] = 2^(e_i - 8), 2^e_i > 4 sqrt(A_ii) (A before factorisation): a bound on every entry of row i of its Cholesky factor
+__global__ void oz_row_bound_kernel(const double* __restrict__ A, long long ld, long long a_batch, int n,
+                                    double* __restrict__ scale, long long sc_batch, const int* __restrict__ active) {
+  const int b = blockIdx.y;
+  if (active != nullptr && active[b] == 0) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double d = A[(long long)b * a_batch + (long long)i * ld + i];
+  double sc = scalbn(1.0, -8);
+  if (d > 0.0 && d <= 1.7976931348623157e308) sc = scalbn(1.0, ilogb(sqrt(d)) + 3 - 8);
+  scale[(long long)b * sc_batch + i] = sc;  // (a non-positive or non-finite diagonal fails in potf2_inv anyway)
+}
+cudaError_t oz_row_bound_launch(const Launch& L, const double* A, long long ld, long long a_batch, int n, int batch,
+                                double* scale, long long sc_batch, const int* active) {
+  ProfScope prof_scope(L, CLS_SLICE);
+  dim3 grid((n + 255) / 256, batch);
+  oz_row_bound_kernel<<<grid, 256, 0, L.stream>>>(A, ld, a_batch, n, scale, sc_batch, active);
+  L.bump();
+  return cudaGetLastError();
 }
 
 // ---- launchers ---------------------------------------------------------------------------------------------------
@@ -758,6 +804,12 @@ cudaError_t oz_gemm_launch(const Launch& L, const OzGemmArgs& a, int tiles128, i
   // delivery into the tensor core, not by L2 -> SM traffic), so single CTAs are the default.  Pairs need both halves of a
   // tile to run the same K range (KRULE_END_AT_COL clips per half).
   // AGPC_OZ_TILE=128: the 128 x 128 tile with its accumulators split over a CTA pair (ozaki_gemm128_kernel)
+  static const int dbg_env = getenv("AGPC_OZ_DBG") ? atoi(getenv("AGPC_OZ_DBG")) : 0;
+  if (dbg_env) {
+    OzGemmArgs d = a;
+    d.dbg = dbg_env;
+    return S == 6 ? oz_gemm_launch_t<6, false>(L, d, tiles128, groups, batch) : oz_gemm_launch_t<7, false>(L, d, tiles128, groups, batch);
+  }
   static const int tile_env = getenv("AGPC_OZ_TILE") ? atoi(getenv("AGPC_OZ_TILE")) : 64;
   if (tile_env == 128) return S == 6 ? oz_gemm128_launch_t<6>(L, a, tiles128, groups, batch) : oz_gemm128_launch_t<7>(L, a, tiles128, groups, batch);
   static const bool pair_env = getenv("AGPC_OZ_PAIR") && atoi(getenv("AGPC_OZ_PAIR")) != 0;
