@@ -439,7 +439,9 @@ def _merge_sum_constants(k: Kernel) -> Kernel:
         consts = [o for o in k.operands if isinstance(o, ConstKernel)]
         if len(consts) > 1:
             sfs = [c.sf for c in consts]
-            sf = None if any(s is None for s in sfs) else 0.5 * math.log(sum(math.exp(2 * s) for s in sfs))
+            # log-sum-exp: a trained (linear-scale) sf above ~355 must not overflow -- the reference's np.exp gives inf
+            # with a warning and the merged value is re-drawn by GPCKernel.__init__ anyway
+            sf = None if any(s is None for s in sfs) else 0.5 * float(np.logaddexp.reduce([2.0 * s for s in sfs]))
             k.operands = [o for o in k.operands if not isinstance(o, ConstKernel)] + [ConstKernel(sf=sf)]
     return k.canonical()
 

@@ -142,6 +142,7 @@ def optimize_models(models, max_evals: int = 1000, warm_start: bool = True):
     engine = models[0].engine
     fails = [0] * len(models)
     evals = [0] * len(models)
+    last_grad = [None] * len(models)   # transformed gradient of the last successful evaluation (what paramz reports on a failure)
     # L-BFGS-B returns an iterate it has already evaluated: the last few successful evaluations of every model are kept
     # (keyed by the bytes of x) so that leaving the model "at its optimum" does not cost one more engine evaluation
     recent = [dict() for _ in models]
@@ -178,11 +179,15 @@ def optimize_models(models, max_evals: int = 1000, warm_start: bool = True):
                         res[i] = np.linalg.LinAlgError("too many failed evaluations")
                         continue
                     mdl.status = st
-                    res[i] = (FAIL_VALUE, np.zeros_like(x))
+                    # paramz: objective = a huge value, gradient = the model's CURRENT gradient, i.e. the one left by
+                    # the last successful parameters_changed() -- not zero, which L-BFGS-B would read as convergence
+                    res[i] = (FAIL_VALUE, np.zeros_like(x) if last_grad[i] is None else last_grad[i].copy())
                     continue
+                fails[i] = 0   # paramz counts CONSECUTIVE failures: _fail_count is reset by every successful evaluation
                 mdl._absorb(r, b)
                 gf = np.array([p.gradfactor() for p in params[b]])
-                res[i] = (mdl._nlml, mdl._grad * gf)
+                last_grad[i] = np.clip(mdl._grad * gf, -1e10, 1e10)           # paramz clips the transformed gradient
+                res[i] = (mdl._nlml, last_grad[i])
                 rec = recent[i]
                 rec[np.asarray(x, dtype=np.float64).tobytes()] = (mdl._nlml, mdl._grad, mdl.bic, mdl.status,
                                                                   mdl.ep_sweeps, mdl._tau, mdl._nu)

@@ -210,3 +210,32 @@ def test_optimum_is_taken_from_the_evaluation_cache(fake):
         assert -m.log_likelihood() == pytest.approx(o["nlml"], rel=5e-6)
         assert m.bic == pytest.approx(o["bic"], rel=5e-6)
         assert m._tau.shape == (80,) and np.all(np.isfinite(m._grad))
+
+
+def test_failed_evaluations_are_tolerated_like_paramz(fake):
+    """A failed evaluation (not-PD / non-finite) is reported to L-BFGS-B as a huge objective with the gradient of the last
+    successful evaluation (paramz: the model's current gradient), it is counted per model, the count is reset by the next
+    success (paramz gives up after more than 10 CONSECUTIVE failures), and the model is left at its best evaluated point."""
+    class Flaky(OracleEngine):
+        n_fail = 0
+
+        def score_batch(self, *a, **kw):
+            r = super().score_batch(*a, **kw)
+            if self.calls > 1 and self.calls % 3 == 0:
+                r["status"][:] = orc.ST_NOT_PD
+                r["nlml"][:] = np.inf
+                self.n_fail += 1
+            return r
+    e = Flaky()
+    eng_mod.set_default_engine(e)
+    try:
+        X, y = synth(60, 2, 5)
+        d = GPCData(X, y.reshape(-1, 1))
+        k = ff.ProductKernel([ff.SqExpKernel(0, 1.0, 1.0), ff.SqExpKernel(1, 1.5, 0.8)])
+        m = GPy.models.GPClassification(X, y.reshape(-1, 1), kernel=gpckernel.gpss2gpy(k, data=d))
+        f0 = m._nlml
+        optim.optimize_models([m], max_evals=40)
+        assert e.n_fail >= 1 and getattr(m, "optimization_error", None) is None
+        assert np.isfinite(m._nlml) and m._nlml <= f0 and m.status == 0
+    finally:
+        eng_mod.set_default_engine(None)
