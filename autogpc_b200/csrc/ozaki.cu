@@ -342,7 +342,9 @@ __host__ __device__ constexpr uint32_t oz2_groups(int rank) {
   return S == 7 ? (rank == 0 ? 0x47u : 0x38u) : (rank == 0 ? 0x27u : 0x18u);
 }
 
-template <int S>
+// MC = true: each CTA loads one operand stage and multicasts it (half the L2 traffic, but every stage then waits for
+// both CTAs' producers and both CTAs' MMAs); MC = false: each CTA loads both operand stages for itself.
+template <int S, bool MC>
 __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm128_kernel(const OzGemmArgs args) {
   using namespace oz;
   constexpr int CPB = TILE / OZ_KB;
@@ -390,7 +392,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm128_kernel(const OzGe
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2 * OZ2_STAGES + 1; ++s) mbar_init(bars + 8 * s, (s >= OZ2_STAGES && s < 2 * OZ2_STAGES) ? 2 : 1);
+    for (int s = 0; s < 2 * OZ2_STAGES + 1; ++s) mbar_init(bars + 8 * s, (MC && s >= OZ2_STAGES && s < 2 * OZ2_STAGES) ? 2 : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -411,18 +413,23 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm128_kernel(const OzGe
   if (warp == 0) {
     // ---------------- producer: CTA 0 brings the A stage, CTA 1 the B stage, each into BOTH shared memories ------------
     if (lane == 0) {
-      const OzOperand& op = rank ? args.B : args.A;
-      const int row = rank ? b_row : a_row;
-      const int col0 = (rank ? args.b_col0 : args.a_col0) + shift;
-      const long long tile = (long long)(row >> 7) * op.nkc + (col0 / OZ_KB) + k_begin;
-      const int8_t* src = op.S + (long long)b * op.s_batch + tile * (S * (long long)SLICE);
+      const long long tileA = (long long)(a_row >> 7) * args.A.nkc + ((args.a_col0 + shift) / OZ_KB) + k_begin;
+      const long long tileB = (long long)(b_row >> 7) * args.B.nkc + ((args.b_col0 + shift) / OZ_KB) + k_begin;
+      const int8_t* srcA = args.A.S + (long long)b * args.A.s_batch + tileA * (S * (long long)SLICE);
+      const int8_t* srcB = args.B.S + (long long)b * args.B.s_batch + tileB * (S * (long long)SLICE);
       for (int it = 0; it < n_iter; ++it) {
         const int s = it % OZ2_STAGES;
         const uint32_t ph = (uint32_t)(it / OZ2_STAGES) & 1u;
         mbar_wait(bars + 8 * (OZ2_STAGES + s), ph ^ 1u);
         const uint32_t full = bars + 8 * s;
         mbar_expect_tx(full, STAGE);
-        bulk_g2s_mc(smem_base + s * STAGE + rank * (S * SLICE), src + (long long)it * (S * (long long)SLICE), S * SLICE, full, (uint16_t)3);
+        const long long off = (long long)it * (S * (long long)SLICE);
+        if (MC) {
+          bulk_g2s_mc(smem_base + s * STAGE + rank * (S * SLICE), (rank ? srcB : srcA) + off, S * SLICE, full, (uint16_t)3);
+        } else {
+          bulk_g2s(smem_base + s * STAGE, srcA + off, S * SLICE, full);
+          bulk_g2s(smem_base + s * STAGE + S * SLICE, srcB + off, S * SLICE, full);
+        }
       }
     }
   } else if (warp == 1) {
@@ -461,7 +468,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm128_kernel(const OzGe
             umma_i8(tmem + col_of[d], da, db, IDESC, acc, 0);
           }
         }
-        umma_commit_mc(bars + 8 * (OZ2_STAGES + s), (uint16_t)3);  // the stage is free once BOTH CTAs have read it
+        if (MC) umma_commit_mc(bars + 8 * (OZ2_STAGES + s), (uint16_t)3);  // the stage is free once BOTH CTAs have read it
+        else umma_commit(bars + 8 * (OZ2_STAGES + s));
       }
       if (n_iter > 0) umma_commit(bars + 8 * (2 * OZ2_STAGES));
     }
@@ -770,11 +778,11 @@ static double oz_executed_macs(const OzGemmArgs& a, int tiles128, int groups, in
   return chunks * (S * (S + 1) / 2) * (double)TILE * OZ_BN * OZ_KB;
 }
 
-template <int S>
+template <int S, bool MC>
 static cudaError_t oz_gemm128_launch_t(const Launch& L, const OzGemmArgs& a, int tiles128, int groups, int batch) {
-  bool& configured = func_attr_done(__LINE__ + S);
+  bool& configured = func_attr_done(__LINE__ + 2 * S + (MC ? 1 : 0));
   if (!configured) {
-    AGPC_CUDA_TRY(cudaFuncSetAttribute(ozaki_gemm128_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz2_smem_bytes<S>()));
+    AGPC_CUDA_TRY(cudaFuncSetAttribute(ozaki_gemm128_kernel<S, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz2_smem_bytes<S>()));
     configured = true;
   }
   cudaLaunchConfig_t cfg{};
@@ -789,7 +797,7 @@ static cudaError_t oz_gemm128_launch_t(const Launch& L, const OzGemmArgs& a, int
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, ozaki_gemm128_kernel<S>, a);
+  return cudaLaunchKernelEx(&cfg, ozaki_gemm128_kernel<S, MC>, a);
 }
 
 cudaError_t oz_gemm_launch(const Launch& L, const OzGemmArgs& a, int tiles128, int groups, int batch, int S) {
@@ -811,7 +819,8 @@ cudaError_t oz_gemm_launch(const Launch& L, const OzGemmArgs& a, int tiles128, i
     return S == 6 ? oz_gemm_launch_t<6, false>(L, d, tiles128, groups, batch) : oz_gemm_launch_t<7, false>(L, d, tiles128, groups, batch);
   }
   static const int tile_env = getenv("AGPC_OZ_TILE") ? atoi(getenv("AGPC_OZ_TILE")) : 64;
-  if (tile_env == 128) return S == 6 ? oz_gemm128_launch_t<6>(L, a, tiles128, groups, batch) : oz_gemm128_launch_t<7>(L, a, tiles128, groups, batch);
+  if (tile_env == 128) return S == 6 ? oz_gemm128_launch_t<6, true>(L, a, tiles128, groups, batch) : oz_gemm128_launch_t<7, true>(L, a, tiles128, groups, batch);
+  if (tile_env == 129) return S == 6 ? oz_gemm128_launch_t<6, false>(L, a, tiles128, groups, batch) : oz_gemm128_launch_t<7, false>(L, a, tiles128, groups, batch);
   static const bool pair_env = getenv("AGPC_OZ_PAIR") && atoi(getenv("AGPC_OZ_PAIR")) != 0;
   const bool pair = pair_env && a.k_rule != KRULE_END_AT_COL;
   if (S == 6) return pair ? oz_gemm_launch_t<6, true>(L, a, tiles128, groups, batch) : oz_gemm_launch_t<6, false>(L, a, tiles128, groups, batch);
