@@ -392,7 +392,14 @@ static cudaError_t potrf_blocked_oz(const Launch& L, const MatSet& ms, const int
     if (k0 > 0 && r0 < nblk) {
       const int kbn = nblk - r0 < POTRF_OUTER ? nblk - r0 : POTRF_OUTER;
       AGPC_CUDA_TRY(cudaStreamWaitEvent(L.stream, L.ev_panel, 0));
-      AGPC_CUDA_TRY(potrf_update_oz(L, ms, active, r0, kbn, 0, k0, false));
+      // (AGPC_OZ_KCAP = c > 0 cuts the K range into segments of c panels: shorter tiles free SMs for the chain sooner,
+      //  at the price of one more epilogue pass per segment)
+      static const int kcap = getenv("AGPC_OZ_KCAP") ? atoi(getenv("AGPC_OZ_KCAP")) : 0;
+      if (kcap > 0) {
+        for (int kc = 0; kc < k0; kc += kcap) AGPC_CUDA_TRY(potrf_update_oz(L, ms, active, r0, kbn, kc, k0 - kc < kcap ? k0 - kc : kcap, false));
+      } else {
+        AGPC_CUDA_TRY(potrf_update_oz(L, ms, active, r0, kbn, 0, k0, false));
+      }
       AGPC_CUDA_TRY(cudaEventRecord(L.ev_rest, L.stream));
     }
     // (c) part 2 of this block column: the previous outer block (sliced at the end of the last iteration)

@@ -881,3 +881,83 @@ print(json.dumps({"status": r["status"].tolist(), "nlml": r["nlml"].tolist(), "s
     rel = abs(hit["nlml"][0] - clean["nlml"][0]) / abs(clean["nlml"][0])
     assert 0 < rel < 1e-3
     assert off["status"][0] == orc.ST_NOT_PD and off["status"][1] == 0 and off["nlml"][1] == clean["nlml"][1]
+
+
+@pytest.mark.gpu
+def test_gemm_nt_i8x_building_block(engine):
+    """The sliced-integer tensor-core product (csrc/ozaki.cu, tcgen05 kind::i8) against torch FP64: with S = 7 digit slices
+    it must pass the FP64 DMMA kernel's own bound (test_gemm_nt_building_block) with two orders of magnitude to spare --
+    also when the rows differ by e^(+-9) in magnitude and some are exactly zero -- and S = 6 stays below 1e-12.  A
+    non-finite operand entry poisons its row of C, as it would in FP64."""
+    torch = _torch()
+    torch.manual_seed(3)
+    for S, tol in ((7, 1e-15), (6, 1e-12)):
+        for (M, N, K, batch, alpha, beta) in [(128, 128, 32, 1, 1.0, 0.0), (256, 384, 160, 2, -1.0, 1.0), (512, 256, 1024, 3, 0.5, 0.25)]:
+            A = torch.randn(batch, M, K, dtype=torch.float64, device="cuda")
+            Bm = torch.randn(batch, N, K, dtype=torch.float64, device="cuda")
+            C = torch.randn(batch, M, N, dtype=torch.float64, device="cuda")
+            ref = alpha * A @ Bm.transpose(1, 2) + beta * C
+            torch.cuda.synchronize()
+            engine.gemm_nt_i8x(A.data_ptr(), Bm.data_ptr(), C.data_ptr(), M, N, K, alpha, beta, batch, S)
+            torch.cuda.synchronize()
+            assert (C - ref).abs().max().item() <= tol * ref.abs().max().item() * K ** 0.5, (S, M, N, K)
+    # rows of very different magnitude, exact zero rows: error against the natural scale of each entry
+    A = torch.randn(2, 256, 512, dtype=torch.float64, device="cuda") * torch.exp(3.0 * torch.randn(2, 256, 1, dtype=torch.float64, device="cuda"))
+    Bm = torch.randn(2, 128, 512, dtype=torch.float64, device="cuda")
+    Bm[:, 5, :] = 0.0
+    C = torch.zeros(2, 256, 128, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    engine.gemm_nt_i8x(A.data_ptr(), Bm.data_ptr(), C.data_ptr(), 256, 128, 512, 1.0, 0.0, 2, 7)
+    torch.cuda.synchronize()
+    ref = A @ Bm.transpose(1, 2)
+    scale = A.abs().amax(2, keepdim=True) * Bm.abs().amax(2, keepdim=True).transpose(1, 2) * 512 ** 0.5 + 1e-300
+    assert ((C - ref).abs() / scale).max().item() <= 3e-14
+    assert (C[:, :, 5] == 0).all()
+    A[0, 7, 100] = float("nan")
+    engine.gemm_nt_i8x(A.data_ptr(), Bm.data_ptr(), C.data_ptr(), 256, 128, 512, 1.0, 0.0, 2, 7)
+    torch.cuda.synchronize()
+    assert torch.isnan(C[0, 7]).all() and torch.isfinite(C[0, 8]).all() and torch.isfinite(C[1]).all()
+
+
+@pytest.mark.gpu
+def test_int8_and_fp64_factorisation_paths_agree():
+    """potrf + trtri through the int8 tensor-core path (left-looking, statically scaled slices; the default) and through
+    the FP64 DMMA path (AGPC_OZAKI=0) on the same matrices: both within 1e-12 of LAPACK, and of each other."""
+    import json
+    import subprocess
+    import sys
+    code = r'''
+import json, os, sys
+import numpy as np, torch
+sys.path.insert(0, %r)
+from autogpc_b200.engine import Engine
+e = Engine(0)
+rng = np.random.default_rng(2)
+out = {}
+for n, batch in ((640, 2), (2304, 1)):
+    G = rng.standard_normal((batch, n, n))
+    S = G @ G.transpose(0, 2, 1) / n + np.eye(n) * (1.0 + 50.0 * rng.random((batch, n, 1)))
+    S = 0.5 * (S + S.transpose(0, 2, 1))
+    A = torch.from_numpy(S.copy()).cuda()
+    Mi = torch.zeros_like(A)
+    Ui = torch.zeros_like(A)
+    torch.cuda.synchronize()
+    e.potrf(A.data_ptr(), n, batch, Mi.data_ptr(), Ui.data_ptr(), 0)
+    torch.cuda.synchronize()
+    L = np.tril(A.cpu().numpy())
+    Lref = np.linalg.cholesky(S)
+    Minv = np.linalg.inv(Lref)
+    out[str(n)] = [float(np.abs(L - Lref).max() / np.abs(Lref).max()), float(np.abs(np.tril(Mi.cpu().numpy()) - Minv).max()),
+                   float(np.abs(np.triu(Ui.cpu().numpy()) - Minv.transpose(0, 2, 1)).max()), float(L.sum()), float(np.tril(Mi.cpu().numpy()).sum())]
+print(json.dumps(out))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for oz in ("7", "0"):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, AGPC_OZAKI=oz), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[oz] = json.loads(r.stdout.strip().splitlines()[-1])
+    for n in ("640", "2304"):
+        for oz in ("7", "0"):
+            assert res[oz][n][0] <= 1e-12 and res[oz][n][1] <= 1e-12 and res[oz][n][2] <= 1e-12, (oz, n, res[oz][n])
+        assert abs(res["7"][n][3] - res["0"][n][3]) <= 1e-10 * abs(res["0"][n][3])
+        assert abs(res["7"][n][4] - res["0"][n][4]) <= 1e-10 * abs(res["0"][n][4])
