@@ -340,7 +340,7 @@ static cudaError_t potrf_panels(const Launch& L, const MatSet& ms, const int* ac
 // One call with a long K range replaces kc / 4 right-looking K = 512 passes over the same tiles: the per-tile prologue and
 // epilogue of the int8 kernel (a third of a K = 512 launch) are paid once per tile instead of once per outer block.
 static cudaError_t potrf_update_oz(const Launch& L, const MatSet& ms, const int* active, int k0, int kb, int kc0, int kcb,
-                                   bool stage_first_col) {
+                                   bool stage_first_col, bool concurrent = false) {
   const int nblk = ms.np / TILE;
   const int rows = nblk - k0;
   if (rows <= 0 || kcb <= 0) return cudaSuccess;
@@ -350,6 +350,7 @@ static cudaError_t potrf_update_oz(const Launch& L, const MatSet& ms, const int*
   z.a_row0 = k0 * TILE; z.a_col0 = kc0 * TILE; z.b_row0 = k0 * TILE; z.b_col0 = kc0 * TILE;
   z.c_row0 = k0 * TILE; z.c_col0 = k0 * TILE;
   z.k_chunks = kcb * OZ_CPB; z.k_rule = KRULE_FULL; z.alpha = -1.0; z.beta = 1.0; z.active = active;
+  z.concurrent = concurrent ? 1 : 0;
   const int nc = kb < rows ? kb : rows;
   z.m_tiles = rows; z.n_tiles = nc; z.lower_only = 0; z.skip_upper = 1;
   AGPC_CUDA_TRY(oz_gemm_launch(L, z, rows * nc, 1, ms.batch, ms.oz_S));
@@ -366,11 +367,18 @@ static cudaError_t potrf_update_oz(const Launch& L, const MatSet& ms, const int*
 //   lo:  part1(j+1) [after slice(j-1)]                     | part1(j+2) ...
 static cudaError_t potrf_blocked_oz(const Launch& L, const MatSet& ms, const int* active, int* info) {
   const int nblk = ms.np / TILE;
+  static const int ob_env = getenv("AGPC_POTRF_OUTER") ? atoi(getenv("AGPC_POTRF_OUTER")) : 0;
+  // panels per outer block of the left-looking form: 2 up to n = 12 k (the persistent int8 kernel makes K = 256 passes cheap
+  // and fewer in-block updates stay on the FP64 pipe: -3 % at n = 6400 x 40, -4 % x 8), 4 above (one big matrix: fewer, larger
+  // launches beside the panel chain: n = 16384 28.1 ms against 30.2).  A function of n ONLY: the blocking fixes the
+  // summation order, and results must not depend on how many other matrices share the batch
+  // (tests/test_gpu_parity.py::test_chunked_batches_equal_one_chunk).  profiles/r02_summary.md section 7
+  const int OB = ob_env > 0 ? ob_env : (nblk < 96 ? 2 : POTRF_OUTER);
   AGPC_CUDA_TRY(oz_row_bound_launch(L, ms.A, ms.np, ms.stride, ms.np, ms.batch, ms.scA, ms.np, active));
-  const bool lookahead = L.side != nullptr && nblk > 2 * POTRF_OUTER;
+  const bool lookahead = L.side != nullptr && nblk > 2 * OB;
   if (!lookahead) {
-    for (int k0 = 0; k0 < nblk; k0 += POTRF_OUTER) {
-      const int kb = nblk - k0 < POTRF_OUTER ? nblk - k0 : POTRF_OUTER;
+    for (int k0 = 0; k0 < nblk; k0 += OB) {
+      const int kb = nblk - k0 < OB ? nblk - k0 : OB;
       const bool thin = (nblk - k0 - 1) * ms.batch <= THIN_CTA_LIMIT;
       if (k0 > 0) AGPC_CUDA_TRY(potrf_update_oz(L, ms, active, k0, kb, 0, k0, thin));
       AGPC_CUDA_TRY(potrf_panels(L, ms, active, info, k0, kb, k0 > 0 && thin));
@@ -382,15 +390,15 @@ static cudaError_t potrf_blocked_oz(const Launch& L, const MatSet& ms, const int
   H.stream = L.side;
   AGPC_CUDA_TRY(cudaEventRecord(L.ev_rest, L.stream));  // everything queued so far (form_B, the row bounds) precedes the chain
   AGPC_CUDA_TRY(cudaStreamWaitEvent(H.stream, L.ev_rest, 0));
-  for (int k0 = 0; k0 < nblk; k0 += POTRF_OUTER) {
-    const int kb = nblk - k0 < POTRF_OUTER ? nblk - k0 : POTRF_OUTER;
+  for (int k0 = 0; k0 < nblk; k0 += OB) {
+    const int kb = nblk - k0 < OB ? nblk - k0 : OB;
     const int r0 = k0 + kb;
     const bool thin = (nblk - k0 - 1) * ms.batch <= THIN_CTA_LIMIT;
     // (a) the chain needs part 1 of THIS block column (queued on the caller's stream one iteration ago)
-    if (k0 > POTRF_OUTER) AGPC_CUDA_TRY(cudaStreamWaitEvent(H.stream, L.ev_rest, 0));
+    if (k0 > OB) AGPC_CUDA_TRY(cudaStreamWaitEvent(H.stream, L.ev_rest, 0));
     // (b) part 1 of the NEXT block column: all panels before this block; their slices were completed with ev_panel
     if (k0 > 0 && r0 < nblk) {
-      const int kbn = nblk - r0 < POTRF_OUTER ? nblk - r0 : POTRF_OUTER;
+      const int kbn = nblk - r0 < OB ? nblk - r0 : OB;
       AGPC_CUDA_TRY(cudaStreamWaitEvent(L.stream, L.ev_panel, 0));
       // (AGPC_OZ_KCAP = c > 0 cuts the K range into segments of c panels: shorter tiles free SMs for the chain sooner,
       //  at the price of one more epilogue pass per segment)
@@ -398,12 +406,12 @@ static cudaError_t potrf_blocked_oz(const Launch& L, const MatSet& ms, const int
       if (kcap > 0) {
         for (int kc = 0; kc < k0; kc += kcap) AGPC_CUDA_TRY(potrf_update_oz(L, ms, active, r0, kbn, kc, k0 - kc < kcap ? k0 - kc : kcap, false));
       } else {
-        AGPC_CUDA_TRY(potrf_update_oz(L, ms, active, r0, kbn, 0, k0, false));
+        AGPC_CUDA_TRY(potrf_update_oz(L, ms, active, r0, kbn, 0, k0, false, true));
       }
       AGPC_CUDA_TRY(cudaEventRecord(L.ev_rest, L.stream));
     }
     // (c) part 2 of this block column: the previous outer block (sliced at the end of the last iteration)
-    if (k0 > 0) AGPC_CUDA_TRY(potrf_update_oz(H, ms, active, k0, kb, k0 - POTRF_OUTER, POTRF_OUTER, thin));
+    if (k0 > 0) AGPC_CUDA_TRY(potrf_update_oz(H, ms, active, k0, kb, k0 - OB, OB, thin));
     // (d) factor it, slice it
     AGPC_CUDA_TRY(potrf_panels(H, ms, active, info, k0, kb, k0 > 0 && thin));
     if (r0 >= nblk) break;

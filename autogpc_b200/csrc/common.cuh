@@ -135,6 +135,7 @@ struct OzGemmArgs {  // same tile / group / K-range semantics as GemmArgs; n_til
   int k_rule, lower_only, skip_upper;
   double alpha, beta;
   const int* active;
+  int concurrent;  // host hint: this launch shares the GPU with a latency-bound chain on another stream (look-ahead)
   int dbg;  // measurement aid (AGPC_OZ_DBG): 1 = main loop without MMAs (data movement only), 2 = without loads (MMAs on
             // whatever the ring holds); results are garbage in both
 };

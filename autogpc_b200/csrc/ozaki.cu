@@ -26,6 +26,7 @@
 // thread, 8 epilogue warps that read TMEM (tcgen05.ld), run the FP64 Horner recombination, and go through a padded
 // shared-memory transposition so that every global access of C is a full-line row access.
 #include <cstdlib>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -309,6 +310,327 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzGemmA
   __syncwarp();
   __syncthreads();
   if (PAIR) cluster_sync_all();  // the peer may still arrive on our barriers / multicast until it is done as well
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+  }
+}
+
+// ---- persistent form: tiles streamed through a resident CTA ---------------------------------------------------------
+// One CTA per SM stays resident and pulls 128 x 64 tiles from a per-stream atomic counter.  What the one-tile-per-CTA form
+// pays per tile -- CTA launch, barrier init, TMEM allocation, the first stage's load latency and the whole epilogue with
+// the tensor core idle, about a third of a K = 512 tile -- is overlapped here:
+//   * the producer keeps loading across the tile boundary (the stage ring belongs to the main loop alone: the epilogue
+//     goes from TMEM through registers straight to global memory, 32 B per thread per store, full sectors);
+//   * TMEM holds 8 accumulator slots of 64 columns for the S <= 7 accumulators of a tile, and the slot of accumulator d
+//     rotates by one per tile: tile j keeps weight d in slot (d + j) mod 8, i.e. where tile j-1 kept weight d + 1.  The
+//     epilogue drains weights S-1, S-2, ... 0 (its Horner order anyway) and signals each slot as it is read; the first
+//     K step of the next tile issues its products weight-major in the same order, so its MMAs chase the drain one slot
+//     behind and the tensor pipe never waits for an epilogue.
+constexpr int OZP_RING = 4;      // tile records in flight between producer, MMA issuer and epilogue
+constexpr int OZP_MAX_BATCH = 1024;
+struct OzTileRec {
+  int b, a_row, b_row, a_kc, b_kc, n_iter;  // a_kc / b_kc: first K chunk in each operand's own columns; n_iter < 0: no more tiles
+  int c_row, c_col, t_row, t_col;
+  int pad[6];
+};
+static_assert(sizeof(OzTileRec) == 64, "one record per 64-byte slot");
+constexpr int OZP_EXTRA = 256 /*barriers*/ + 256 /*tmem slot, counts*/ + OZP_RING * 64 + 2 * OZP_MAX_BATCH;
+template <int S>
+constexpr int ozp_smem_bytes() {
+  return OZ_STAGES * oz_stage_bytes<S>() + 1024 /*align slack*/ + OZP_EXTRA;
+}
+static_assert(ozp_smem_bytes<7>() <= 227 * 1024, "persistent kernel: shared memory");
+
+namespace oz {
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void st_global_v4(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void ld_global_v4(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
+}
+}  // namespace oz
+
+// (x, group, item) -> tile record; false when the index names no work (ozaki_gemm_kernel's early returns)
+__device__ __forceinline__ bool oz_decode_tile(const OzGemmArgs& args, int x, int g, int b, OzTileRec& T) {
+  constexpr int CPB = TILE / OZ_KB;
+  int h2 = 0;
+  if (args.grp_blocks > 0) {
+    h2 = args.nblk - g * args.grp_blocks - args.half_blocks;
+    h2 = h2 < 0 ? 0 : (h2 > args.half_blocks ? args.half_blocks : h2);
+  }
+  const int shift = g * args.grp_blocks * TILE;
+  const int mt = args.m_kind == EXT_H2 ? h2 : args.m_tiles;
+  const int nt = args.n_kind == EXT_H2 ? h2 : args.n_tiles;
+  const int kt = args.k_kind == EXT_H2 ? h2 * CPB : args.k_chunks;
+  if (mt <= 0 || nt <= 0) return false;
+  const int half = x & 1, t = x >> 1;
+  int ti, tj;
+  if (args.lower_only) {
+    if (t >= mt * (mt + 1) / 2) return false;
+    ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while (ti * (ti + 1) / 2 > t) --ti;
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    tj = t - ti * (ti + 1) / 2;
+  } else {
+    ti = t / nt;
+    tj = t % nt;
+    if (ti >= mt) return false;
+    if (args.skip_upper && tj > ti) return false;
+  }
+  int k_begin = 0, k_end = kt;
+  if (args.k_rule == KRULE_BEGIN_AT_ROW) k_begin = ti * CPB;
+  if (args.k_rule == KRULE_END_AT_ROW) k_end = min(kt, (ti + 1) * CPB);
+  if (args.k_rule == KRULE_END_AT_COL) k_end = min(kt, (2 * tj + half + 1) * (OZ_BN / OZ_KB));
+  T.b = b;
+  T.a_row = args.a_row0 + shift + ti * TILE;
+  T.b_row = args.b_row0 + shift + tj * TILE + half * OZ_BN;
+  T.a_kc = (args.a_col0 + shift) / OZ_KB + k_begin;
+  T.b_kc = (args.b_col0 + shift) / OZ_KB + k_begin;
+  T.n_iter = max(k_end - k_begin, 0);
+  T.c_row = args.c_row0 + shift + ti * TILE;
+  T.c_col = args.c_col0 + shift + tj * TILE + half * OZ_BN;
+  T.t_row = args.ct_row0 + shift + tj * TILE + half * OZ_BN;
+  T.t_col = args.ct_col0 + shift + ti * TILE;
+  return true;
+}
+
+template <int S>
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+ozaki_gemm_stream_kernel(const OzGemmArgs args, const int gx, const int gy, const int batch, int* __restrict__ counter) {
+  using namespace oz;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  constexpr uint32_t STAGE = oz_stage_bytes<S>();
+  constexpr uint32_t A_SLICE = TILE * OZ_KB, B_SLICE = OZ_BN * OZ_KB;
+  constexpr int ST = OZ_STAGES, R = OZP_RING;
+  // barriers: full[ST], empty[ST], accf, drained[S] (weight d of the current tile has been read out of TMEM),
+  //           tfull[R] / tempty[R] (tile record ring)
+  const uint32_t bars = smem_base + ST * STAGE;
+  const uint32_t bar_accf = bars + 8 * (2 * ST), bar_drained = bar_accf + 8, bar_tfull = bar_drained + 8 * S,
+                 bar_tempty = bar_tfull + 8 * R;
+  static_assert(8 * (2 * ST + 1 + S + 2 * R) <= 256, "barrier block");
+  uint8_t* extra = smem_gen + ST * STAGE + 256;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(extra);
+  int* n_act_s = reinterpret_cast<int*>(extra + 8);
+  volatile int* ring = reinterpret_cast<volatile int*>(extra + 256);  // R records of 16 ints
+  uint16_t* act = reinterpret_cast<uint16_t*>(extra + 256 + R * 64);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2 * ST + 1; ++s) mbar_init(bars + 8 * s, 1);
+    for (int d = 0; d < S; ++d) mbar_init(bar_drained + 8 * d, 8);  // one arrival per epilogue warp
+    for (int r = 0; r < R; ++r) {
+      mbar_init(bar_tfull + 8 * r, 1);
+      mbar_init(bar_tempty + 8 * r, 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (warp == 2) {  // compact list of the batch items that still take part
+    int cnt = 0;
+    for (int base = 0; base < batch; base += 32) {
+      const int i = base + lane;
+      const bool on = i < batch && (args.active == nullptr || args.active[i] != 0);
+      const unsigned m = __ballot_sync(0xffffffffu, on);
+      if (on) act[cnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+      cnt += __popc(m);
+    }
+    if (lane == 0) *n_act_s = cnt;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------- producer: tile fetch, then S + 1 bulk copies per stage ----------------
+    if (lane == 0) {
+      const int per_item = gx * gy;
+      const long long total = (long long)per_item * *n_act_s;
+      const bool longest_last = args.k_rule == KRULE_END_AT_ROW || args.k_rule == KRULE_END_AT_COL;
+      int gs = 0, pub = 0;
+      long long w = atomicAdd(counter, 1);
+      for (;;) {
+        OzTileRec T = {};
+        bool have = false;
+        while (w < total) {
+          const int bi = (int)(w / per_item);
+          int rem = (int)(w % per_item);
+          if (longest_last) rem = per_item - 1 - rem;  // hand out an item's long tiles first: short ones fill the tail
+          if (oz_decode_tile(args, rem % gx, rem / gx, (int)act[bi], T)) {
+            have = true;
+            break;
+          }
+          w = atomicAdd(counter, 1);
+        }
+        const int r = pub % R;
+        if (pub >= R) mbar_wait(bar_tempty + 8 * r, (uint32_t)((pub / R) - 1) & 1u);
+        if (!have) T.n_iter = -1;
+        volatile int* rec = ring + 16 * r;
+        rec[0] = T.b; rec[1] = T.a_row; rec[2] = T.b_row; rec[3] = T.n_iter;
+        rec[4] = T.c_row; rec[5] = T.c_col; rec[6] = T.t_row; rec[7] = T.t_col;
+        mbar_arrive(bar_tfull + 8 * r);
+        ++pub;
+        if (!have) break;
+        const long long w_next = atomicAdd(counter, 1);  // its latency hides behind this tile's copies
+        const int8_t* srcA = args.A.S + (long long)T.b * args.A.s_batch +
+                             ((long long)(T.a_row >> 7) * args.A.nkc + T.a_kc) * (S * (long long)A_SLICE);
+        const int8_t* srcB = args.B.S + (long long)T.b * args.B.s_batch +
+                             ((long long)(T.b_row >> 7) * args.B.nkc + T.b_kc) * (S * (long long)A_SLICE) + ((T.b_row >> 6) & 1) * B_SLICE;
+        for (int it = 0; it < T.n_iter; ++it, ++gs) {
+          const int s = gs % ST;
+          const uint32_t ph = (uint32_t)(gs / ST) & 1u;
+          mbar_wait(bars + 8 * (ST + s), ph ^ 1u);
+          const uint32_t full = bars + 8 * s;
+          mbar_expect_tx(full, STAGE);
+          const uint32_t dst = smem_base + s * STAGE;
+          bulk_g2s(dst, srcA + (long long)it * (S * (long long)A_SLICE), S * A_SLICE, full);
+#pragma unroll
+          for (int q = 0; q < S; ++q)
+            bulk_g2s(dst + S * A_SLICE + q * B_SLICE, srcB + (long long)it * (S * (long long)A_SLICE) + q * (long long)A_SLICE, B_SLICE, full);
+        }
+        w = w_next;
+      }
+      if (atomicAdd(counter + 1, 1) == (int)gridDim.x - 1) {  // last CTA out re-arms the counter for the stream's next launch
+        counter[0] = 0;
+        counter[1] = 0;
+        __threadfence();
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+      constexpr uint64_t DESC_HI = (1ull << 16) | ((uint64_t)((8 * OZ_KB) >> 4) << 32) | (1ull << 46) | (6ull << 61);
+      int gs = 0;
+      for (int j = 0;; ++j) {
+        const int r = j % R;
+        mbar_wait(bar_tfull + 8 * r, (uint32_t)(j / R) & 1u);
+        const int n_iter = ring[16 * r + 3];
+        if (n_iter < 0) break;
+        const uint32_t rot = (uint32_t)j & 7u;
+        const uint32_t prev = (uint32_t)(j - 1) & 1u;
+        if (j >= 1 && n_iter == 0)  // nothing to issue: still keep in step with the drain of the previous tile
+          for (int d = 1; d < S; ++d) mbar_wait(bar_drained + 8 * d, prev);
+        for (int it = 0; it < n_iter; ++it, ++gs) {
+          const int s = gs % ST;
+          const uint32_t ph = (uint32_t)(gs / ST) & 1u;
+          mbar_wait(bars + 8 * s, ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_base + s * STAGE, sb = sa + S * A_SLICE;
+          if (it == 0) {
+            // weight-major, lightest weight first: accumulator d takes over the slot weight d + 1 of the previous tile had
+#pragma unroll
+            for (int d = S - 1; d >= 0; --d) {
+              if (j >= 1 && d <= S - 2) {
+                mbar_wait(bar_drained + 8 * (d + 1), prev);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              }
+              const uint32_t acc = tmem + (((uint32_t)d + rot) & 7u) * OZ_BN;
+#pragma unroll
+              for (int p = 0; p <= d; ++p) {
+                const uint64_t da = DESC_HI | (uint64_t)(((sa + p * A_SLICE) >> 4) & 0x3FFF);
+                const uint64_t db = DESC_HI | (uint64_t)(((sb + (d - p) * B_SLICE) >> 4) & 0x3FFF);
+                umma_i8(acc, da, db, IDESC, p == 0 ? 0u : 1u, 0);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int p = 0; p < S; ++p) {
+              const uint64_t da = DESC_HI | (uint64_t)(((sa + p * A_SLICE) >> 4) & 0x3FFF);
+#pragma unroll
+              for (int q = 0; q < S - p; ++q) {
+                const uint64_t db = DESC_HI | (uint64_t)(((sb + q * B_SLICE) >> 4) & 0x3FFF);
+                umma_i8(tmem + (((uint32_t)(p + q) + rot) & 7u) * OZ_BN, da, db, IDESC, 1u, 0);
+              }
+            }
+          }
+          umma_commit(bars + 8 * (ST + s));
+        }
+        // the slot the NEXT tile writes first (its weight S-1) was weight 0 of the previous tile: make sure that drain is
+        // over before this tile is handed to the epilogue (which also keeps every drained[] barrier within one phase)
+        if (j >= 1) mbar_wait(bar_drained, prev);
+        umma_commit(bar_accf);
+      }
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> FP64 Horner in registers -> global ----------------
+    const int ew = warp - 2;  // 0..7
+    const int q4 = warp & 3;  // TMEM lane quarter this warp may read
+    const int ch = ew >> 2;   // column half (32 columns) of the 64-wide tile
+    const int row = q4 * 32 + lane;
+    const double beta = args.beta;
+    for (int j = 0;; ++j) {
+      const int r = j % R;
+      mbar_wait(bar_tfull + 8 * r, (uint32_t)(j / R) & 1u);
+      volatile int* rec = ring + 16 * r;
+      const int b = rec[0], a_row = rec[1], b_row = rec[2], n_iter = rec[3];
+      const int c_row = rec[4], c_col = rec[5], t_row = rec[6], t_col = rec[7];
+      if (n_iter < 0) break;
+      const uint32_t rot = (uint32_t)j & 7u;
+      mbar_wait(bar_accf, (uint32_t)j & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      double sum[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sum[i] = 0.0;
+      const uint32_t tbase = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(ch * 32);
+#pragma unroll
+      for (int d = S - 1; d >= 0; --d) {
+        uint32_t v0[16], v1[16];
+        if (n_iter > 0) {
+          const uint32_t ta = tbase + (((uint32_t)d + rot) & 7u) * OZ_BN;
+          tmem_ld16(ta, v0);
+          tmem_ld16(ta + 16, v1);
+          tmem_ld_wait();
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_drained + 8 * d);
+        if (n_iter > 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            sum[i] = fma(sum[i], 0.00390625, i32_to_f64(v0[i]));
+            sum[16 + i] = fma(sum[16 + i], 0.00390625, i32_to_f64(v1[i]));
+          }
+        }
+      }
+      const double sa = args.A.scale[(long long)b * args.A.sc_batch + a_row + row] * args.alpha;
+      const double* sbp = args.B.scale + (long long)b * args.B.sc_batch + b_row + ch * 32;
+      double* Cb = args.C + (long long)b * args.c_batch;
+      double* crow = Cb + (long long)(c_row + row) * args.ldc + c_col + ch * 32;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sum[i] = (sum[i] * sa) * __ldg(sbp + i);
+      if (beta != 0.0) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          double o0, o1, o2, o3;
+          ld_global_v4(crow + i, o0, o1, o2, o3);
+          st_global_v4(crow + i, fma(beta, o0, sum[i]), fma(beta, o1, sum[i + 1]), fma(beta, o2, sum[i + 2]), fma(beta, o3, sum[i + 3]));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) st_global_v4(crow + i, sum[i], sum[i + 1], sum[i + 2], sum[i + 3]);
+      }
+      if (args.Ct != nullptr) {  // transposed copy (alpha A B^T only, as in the one-tile kernel): lanes = consecutive columns of Ct
+        double* Tb = args.Ct + (long long)b * args.c_batch + (long long)(t_row + ch * 32) * args.ldc + t_col + row;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) Tb[(long long)i * args.ldc] = sum[i];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * r);
+    }
+  }
+  __syncwarp();
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
@@ -800,6 +1122,57 @@ static cudaError_t oz_gemm128_launch_t(const Launch& L, const OzGemmArgs& a, int
   return cudaLaunchKernelEx(&cfg, ozaki_gemm128_kernel<S, MC>, a);
 }
 
+// Tile counters of the persistent kernel: {next tile, CTAs finished} per stream.  Launches on one stream run one after the
+// other and the last CTA of each re-arms its pair, so one pair per (device, stream) is enough.
+constexpr int OZP_STREAM_SLOTS = 64;
+__device__ int oz_tile_counters[OZP_STREAM_SLOTS][2];
+
+static int* ozp_counter_for(cudaStream_t st) {
+  struct Slot {
+    int dev;
+    cudaStream_t st;
+  };
+  static Slot slots[OZP_STREAM_SLOTS];
+  static int used = 0;
+  static int* base[64] = {};
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (base[dev & 63] == nullptr) {
+    void* p = nullptr;
+    if (cudaGetSymbolAddress(&p, oz_tile_counters) != cudaSuccess) return nullptr;
+    if (cudaMemset(p, 0, sizeof(int) * 2 * OZP_STREAM_SLOTS) != cudaSuccess) return nullptr;
+    base[dev & 63] = static_cast<int*>(p);
+  }
+  int per_dev = 0;
+  for (int i = 0; i < used; ++i) {
+    if (slots[i].dev != dev) continue;
+    if (slots[i].st == st) return base[dev & 63] + 2 * per_dev;
+    ++per_dev;
+  }
+  if (used == OZP_STREAM_SLOTS || per_dev == OZP_STREAM_SLOTS) return nullptr;
+  slots[used++] = Slot{dev, st};
+  return base[dev & 63] + 2 * per_dev;
+}
+
+template <int S>
+static cudaError_t oz_gemm_stream_launch_t(const Launch& L, const OzGemmArgs& a, int tiles128, int groups, int batch, int* counter) {
+  bool& configured = func_attr_done(__LINE__ + S);
+  if (!configured) {
+    AGPC_CUDA_TRY(cudaFuncSetAttribute(ozaki_gemm_stream_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, ozp_smem_bytes<S>()));
+    configured = true;
+  }
+  static int sms[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (sms[dev & 63] == 0) AGPC_CUDA_TRY(cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+  const long long tiles = 2LL * tiles128 * groups * batch;
+  const int grid = (int)(tiles < sms[dev & 63] ? tiles : sms[dev & 63]);
+  ozaki_gemm_stream_kernel<S><<<grid, OZ_THREADS, ozp_smem_bytes<S>(), L.stream>>>(a, 2 * tiles128, groups, batch, counter);
+  return cudaGetLastError();
+}
+
 cudaError_t oz_gemm_launch(const Launch& L, const OzGemmArgs& a, int tiles128, int groups, int batch, int S) {
   ProfScope prof_scope(L, L.gemm_cls);
   const int oz_cls = L.gemm_cls == CLS_GEMM_TRTRI ? CLS_OZ_TRTRI : L.gemm_cls == CLS_GEMM_LAUUM ? CLS_OZ_LAUUM : CLS_OZ_POTRF;
@@ -817,6 +1190,17 @@ cudaError_t oz_gemm_launch(const Launch& L, const OzGemmArgs& a, int tiles128, i
     OzGemmArgs d = a;
     d.dbg = dbg_env;
     return S == 6 ? oz_gemm_launch_t<6, false>(L, d, tiles128, groups, batch) : oz_gemm_launch_t<7, false>(L, d, tiles128, groups, batch);
+  }
+  // AGPC_OZ_PERSIST: 1 = persistent tile-streaming kernel (ozaki_gemm_stream_kernel) for every launch, 0 = one CTA per
+  // tile, 2 = persistent except launches that run beside a look-ahead chain; unset: 1 for batches of >= 16 matrices (every
+  // kernel of the chain fills the GPU by itself, resident CTAs cost the chain nothing), 2 below (the chain's small
+  // kernels need the SMs that one-tile CTAs hand back as they finish).  profiles/r02_summary.md section 7.
+  static const int persist_set = getenv("AGPC_OZ_PERSIST") ? atoi(getenv("AGPC_OZ_PERSIST")) : -1;
+  const int persist_env = persist_set >= 0 ? persist_set : (batch >= 16 ? 1 : 2);
+  if (persist_env && batch <= OZP_MAX_BATCH && !(persist_env == 2 && a.concurrent)) {
+    int* counter = ozp_counter_for(L.stream);
+    if (counter != nullptr)
+      return S == 6 ? oz_gemm_stream_launch_t<6>(L, a, tiles128, groups, batch, counter) : oz_gemm_stream_launch_t<7>(L, a, tiles128, groups, batch, counter);
   }
   static const int tile_env = getenv("AGPC_OZ_TILE") ? atoi(getenv("AGPC_OZ_TILE")) : 64;
   if (tile_env == 128) return S == 6 ? oz_gemm128_launch_t<6, true>(L, a, tiles128, groups, batch) : oz_gemm128_launch_t<7, true>(L, a, tiles128, groups, batch);
