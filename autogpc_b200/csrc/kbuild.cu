@@ -380,6 +380,13 @@ constexpr int KT = 64, KT_THREADS = 256, KT_LD = KT + 1;
 // tile arrives by cp.async while the current tile is evaluated.  (Per-tile prologue + its two barriers were 28 % + 14 %
 // of the warp-time samples of the one-tile-per-CTA form, profiles/r01_build_K_v2_ncu_source_regions.txt.)
 constexpr int KT_STRIP = 8;
+// PER leaves are evaluated through the angle-difference identity: sin(pi (x_i - x_j) / T) = s_i c_j - c_i s_j with
+// (s, c) = sincospi(x / T) tabulated ONCE per tile row / tile column (64 sincos calls per leaf and tile side instead of
+// 4096 sin calls per leaf and tile): the per-pair cost of a PER leaf drops from ~60 instructions to 3 FP64 ones, the
+// same as an SE leaf.  Both forms round the phase pi x / T to ~1e-16 |x / T|, so they agree to that level (the oracle
+// parity tests hold unchanged).  Up to KT_PER leaves get a table; further ones (never produced by the search grammar
+// within AGPC_MAX_LEAVES in practice) fall back to the direct form.
+constexpr int KT_PER = 8;
 
 // xc[d][r] = Xb[col0 + r][d], r < 64, by all 256 threads
 __device__ __forceinline__ void load_xc_async(double* xc, const double* __restrict__ Xb, int col0, int nb_pad, int D) {
@@ -399,11 +406,16 @@ build_K_tiled_kernel(const BuildArgs a, const int symmetric, const int tiles_n, 
   __shared__ ProgShared P;
   __shared__ double exp_tab[32];
   __shared__ double th_s[AGPC_MAX_THETA];
+  __shared__ int per_slot[AGPC_MAX_LEAVES];   // leaf -> trig table (or -1)
+  __shared__ int per_leaf[KT_PER];            // table -> leaf
+  __shared__ int n_per_s;
   if (threadIdx.x < 32) exp_tab[threadIdx.x] = EXP_T[threadIdx.x];
   const int D = a.D;
   double* xr = smem;                // [D][KT]
   double* xc0 = smem + D * KT;      // [2][D][KT]: column panel, double-buffered across the strip
   double* st = xc0 + 2 * D * KT;    // [KT][KT_LD] transposition buffer (symmetric mode)
+  double* trg_r = st + KT * KT_LD;  // [KT_PER][2][KT]: (1/2l^2)^(1/4) * (sin, cos)(pi x_i / T) of the tile rows
+  double* trg_c = trg_r + KT_PER * 2 * KT;  // [KT_PER][2][KT]: the same of the tile columns
   // strip index -> (tile row, first tile column): row ti holds ti + 1 (symmetric) or tiles_n tiles
   int ti = 0, tj0;
   {
@@ -432,13 +444,45 @@ build_K_tiled_kernel(const BuildArgs a, const int symmetric, const int tiles_n, 
   cp_async_wait_all();
   __syncthreads();
   derive_leaf_consts(P, th_s);
+  if (threadIdx.x == KT_THREADS - 1) {
+    int np = 0;
+    for (int l = 0; l < P.n_leaves; ++l) {
+      const bool tab = P.leaf[l].type == AGPC_LEAF_PER && np < KT_PER;
+      per_slot[l] = tab ? np : -1;
+      if (tab) per_leaf[np++] = l;
+    }
+    n_per_s = np;
+  }
   __syncthreads();
+  const int n_per = n_per_s;
+  // row tables, once per strip; both sides carry (1 / 2 l^2)^(1/4), so a pair costs  t = sr cc - cr sc; arg -= t t
+  for (int idx = threadIdx.x; idx < n_per * KT; idx += KT_THREADS) {
+    const int sl = idx >> 6, r = idx & (KT - 1);
+    const LeafConst& lc = P.leaf[per_leaf[sl]];
+    double sn, cs;
+    sincospi(xr[lc.dim * KT + r] * lc.a, &sn, &cs);
+    const double w = sqrt(sqrt(0.5 * lc.b));
+    trg_r[(sl * 2 + 0) * KT + r] = w * sn;
+    trg_r[(sl * 2 + 1) * KT + r] = w * cs;
+  }
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   for (int kt = 0; kt < n_tiles; ++kt) {
   const int tj = tj0 + kt;
   const int col0 = tj * KT;
   const double* xc = xc0 + (kt & 1) * D * KT;
   if (kt + 1 < n_tiles) load_xc_async(xc0 + ((kt + 1) & 1) * D * KT, Xb, (tj + 1) * KT, a.nb_pad, D);
+  if (n_per > 0) {  // column tables of this tile (the previous tile's readers passed the barrier that ended it)
+    for (int idx = threadIdx.x; idx < n_per * KT; idx += KT_THREADS) {
+      const int sl = idx >> 6, r = idx & (KT - 1);
+      const LeafConst& lc = P.leaf[per_leaf[sl]];
+      double sn, cs;
+      sincospi(xc[lc.dim * KT + r] * lc.a, &sn, &cs);
+      const double w = sqrt(sqrt(0.5 * lc.b));
+      trg_c[(sl * 2 + 0) * KT + r] = w * sn;
+      trg_c[(sl * 2 + 1) * KT + r] = w * cs;
+    }
+    __syncthreads();
+  }
 
   // two passes of 2 x 4 pairs (rows ty + 16r, r = 2h, 2h + 1): keeps the live set under 80 registers -> 3 CTAs per SM,
   // which is what hides the load -> compute -> store latency chain of a tile (the kernel is latency-, not ALU-bound)
@@ -466,9 +510,36 @@ build_K_tiled_kernel(const BuildArgs a, const int symmetric, const int tiles_n, 
       double scale = 1.0;
       bool has_exp = false, has_mult = false;
       for (int p = 0; p < len; ++p) {
-        const LeafConst& lc = P.leaf[P.term_leaf[t][p]];
+        const int leaf_id = P.term_leaf[t][p];
+        const LeafConst& lc = P.leaf[leaf_id];
         scale *= lc.var;
         if (lc.type == AGPC_LEAF_CONST) continue;
+        if (lc.type == AGPC_LEAF_PER && per_slot[leaf_id] >= 0) {
+          has_exp = true;
+          const double* tr = trg_r + per_slot[leaf_id] * 2 * KT;
+          const double* tc = trg_c + per_slot[leaf_id] * 2 * KT;
+          double sr[2], cr[2], sc[4], cc[4];
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            sr[r] = tr[ty + 16 * (2 * h + r)];
+            cr[r] = tr[KT + ty + 16 * (2 * h + r)];
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            sc[c] = tc[tx + 16 * c];
+            cc[c] = tc[KT + tx + 16 * c];
+          }
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              // sqrt(1/2l^2) sin(pi (x_i - x_j) / T); two rounded products and a difference (no fma), so that swapping
+              // i and j negates it EXACTLY: the diagonal tiles evaluate both (i, j) and (j, i), and K must be symmetric
+              const double sn = __dsub_rn(__dmul_rn(sr[r], cc[c]), __dmul_rn(cr[r], sc[c]));
+              arg[r][c] = fma(-sn, sn, arg[r][c]);
+            }
+          continue;
+        }
         double xi[2], xj[4];
 #pragma unroll
         for (int r = 0; r < 2; ++r) xi[r] = xr[lc.dim * KT + ty + 16 * (2 * h + r)];
@@ -809,7 +880,7 @@ cudaError_t build_K_launch(const Launch& L, const BuildArgs& a, int batch, bool 
     return cudaGetLastError();
   }
   bool& configured = func_attr_done(__LINE__);
-  const size_t smem = sizeof(double) * (3 * (size_t)a.D * KT + KT * KT_LD);
+  const size_t smem = sizeof(double) * (3 * (size_t)a.D * KT + KT * KT_LD + 2 * KT_PER * 2 * KT);
   static const int occ = getenv("AGPC_KB_OCC") ? atoi(getenv("AGPC_KB_OCC")) : 2;   // resident CTAs per SM the kernel is built for
   if (!configured || smem > 48 * 1024) {
     AGPC_CUDA_TRY(cudaFuncSetAttribute(build_K_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -53,6 +53,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (!done && ++spins > (1u << 26)) __trap();
   } while (!done);
 }
+// the same for waits that are long by design (epilogue warps waiting out a whole main loop): sleep between polls, so that
+// sixteen polling warps do not compete with the MMA operand reads for shared-memory cycles
+__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity, unsigned ns) {
+  uint32_t done;
+  uint32_t spins = 0;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done) {
+      if (++spins > (1u << 24)) __trap();
+      __nanosleep(ns);
+    }
+  } while (!done);
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
@@ -328,6 +345,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzGemmA
 //     K step of the next tile issues its products weight-major in the same order, so its MMAs chase the drain one slot
 //     behind and the tensor pipe never waits for an epilogue.
 constexpr int OZP_RING = 4;      // tile records in flight between producer, MMA issuer and epilogue
+constexpr int OZS_EPI_WARPS = 16;
+constexpr int OZS_THREADS = 64 + 32 * OZS_EPI_WARPS;  // warp 0: producer, warp 1: TMEM owner + MMA issuer, warps 2-17: epilogue
 constexpr int OZP_MAX_BATCH = 1024;
 struct OzTileRec {
   int b, a_row, b_row, a_kc, b_kc, n_iter;  // a_kc / b_kc: first K chunk in each operand's own columns; n_iter < 0: no more tiles
@@ -399,7 +418,7 @@ __device__ __forceinline__ bool oz_decode_tile(const OzGemmArgs& args, int x, in
 }
 
 template <int S>
-__global__ void __launch_bounds__(OZ_THREADS, 1)
+__global__ void __launch_bounds__(OZS_THREADS, 1)
 ozaki_gemm_stream_kernel(const OzGemmArgs args, const int gx, const int gy, const int batch, int* __restrict__ counter) {
   using namespace oz;
   extern __shared__ uint8_t smem_raw[];
@@ -423,10 +442,10 @@ ozaki_gemm_stream_kernel(const OzGemmArgs args, const int gx, const int gy, cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2 * ST + 1; ++s) mbar_init(bars + 8 * s, 1);
-    for (int d = 0; d < S; ++d) mbar_init(bar_drained + 8 * d, 8);  // one arrival per epilogue warp
+    for (int d = 0; d < S; ++d) mbar_init(bar_drained + 8 * d, OZS_EPI_WARPS);  // one arrival per epilogue warp
     for (int r = 0; r < R; ++r) {
       mbar_init(bar_tfull + 8 * r, 1);
-      mbar_init(bar_tempty + 8 * r, 8);
+      mbar_init(bar_tempty + 8 * r, OZS_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -518,8 +537,11 @@ ozaki_gemm_stream_kernel(const OzGemmArgs args, const int gx, const int gy, cons
         if (n_iter < 0) break;
         const uint32_t rot = (uint32_t)j & 7u;
         const uint32_t prev = (uint32_t)(j - 1) & 1u;
-        if (j >= 1 && n_iter == 0)  // nothing to issue: still keep in step with the drain of the previous tile
+        const bool no_chase = args.dbg == 3;  // measurement aid: drain the previous tile completely before the first MMA
+        if (j >= 1 && (n_iter == 0 || no_chase)) {  // (n_iter == 0: nothing to issue, still keep in step with the drain)
           for (int d = 1; d < S; ++d) mbar_wait(bar_drained + 8 * d, prev);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
         for (int it = 0; it < n_iter; ++it, ++gs) {
           const int s = gs % ST;
           const uint32_t ph = (uint32_t)(gs / ST) & 1u;
@@ -530,7 +552,7 @@ ozaki_gemm_stream_kernel(const OzGemmArgs args, const int gx, const int gy, cons
             // weight-major, lightest weight first: accumulator d takes over the slot weight d + 1 of the previous tile had
 #pragma unroll
             for (int d = S - 1; d >= 0; --d) {
-              if (j >= 1 && d <= S - 2) {
+              if (j >= 1 && d <= S - 2 && !no_chase) {
                 mbar_wait(bar_drained + 8 * (d + 1), prev);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               }
@@ -549,7 +571,9 @@ ozaki_gemm_stream_kernel(const OzGemmArgs args, const int gx, const int gy, cons
 #pragma unroll
               for (int q = 0; q < S - p; ++q) {
                 const uint64_t db = DESC_HI | (uint64_t)(((sb + q * B_SLICE) >> 4) & 0x3FFF);
-                umma_i8(tmem + (((uint32_t)(p + q) + rot) & 7u) * OZ_BN, da, db, IDESC, 1u, 0);
+                const int nq = S - p;
+                const int mode = nq == 1 ? 0 : q == 0 ? 1 : q == nq - 1 ? 3 : 2;  // A slice p stays in the operand collector
+                umma_i8(tmem + (((uint32_t)(p + q) + rot) & 7u) * OZ_BN, da, db, IDESC, 1u, mode);
               }
             }
           }
@@ -563,32 +587,44 @@ ozaki_gemm_stream_kernel(const OzGemmArgs args, const int gx, const int gy, cons
     }
   } else {
     // ---------------- epilogue: TMEM -> FP64 Horner in registers -> global ----------------
-    const int ew = warp - 2;  // 0..7
-    const int q4 = warp & 3;  // TMEM lane quarter this warp may read
-    const int ch = ew >> 2;   // column half (32 columns) of the 64-wide tile
+    // 16 warps: lane quarter q4 (the TMEM lanes a warp may read) x 16-column group.  Everything that does not depend on
+    // the accumulators -- the tile's old C values when beta != 0, the row and column scales -- is requested BEFORE the
+    // wait for the MMAs, so its latency runs under the main loop.
+    const int ew = warp - 2;  // 0..15
+    const int q4 = warp & 3;
+    const int cgp = ew >> 2;  // columns 16 cgp .. 16 cgp + 15 of the 64-wide tile
     const int row = q4 * 32 + lane;
     const double beta = args.beta;
+    const unsigned idle_ns = args.dbg >= 100 ? (unsigned)(args.dbg - 100) : 0u;  // measurement aid: AGPC_OZ_DBG = 100 + ns
     for (int j = 0;; ++j) {
       const int r = j % R;
-      mbar_wait(bar_tfull + 8 * r, (uint32_t)(j / R) & 1u);
+      if (idle_ns) mbar_wait_idle(bar_tfull + 8 * r, (uint32_t)(j / R) & 1u, idle_ns);
+      else mbar_wait(bar_tfull + 8 * r, (uint32_t)(j / R) & 1u);
       volatile int* rec = ring + 16 * r;
       const int b = rec[0], a_row = rec[1], b_row = rec[2], n_iter = rec[3];
       const int c_row = rec[4], c_col = rec[5], t_row = rec[6], t_col = rec[7];
       if (n_iter < 0) break;
       const uint32_t rot = (uint32_t)j & 7u;
-      mbar_wait(bar_accf, (uint32_t)j & 1u);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      double sum[32];
+      double* crow = args.C + (long long)b * args.c_batch + (long long)(c_row + row) * args.ldc + c_col + cgp * 16;
+      double old[16];
+      if (beta != 0.0) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) sum[i] = 0.0;
-      const uint32_t tbase = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(ch * 32);
+        for (int i = 0; i < 16; i += 4) ld_global_v4(crow + i, old[i], old[i + 1], old[i + 2], old[i + 3]);
+      }
+      const double sa = args.A.scale[(long long)b * args.A.sc_batch + a_row + row] * args.alpha;
+      const double* sbp = args.B.scale + (long long)b * args.B.sc_batch + b_row + cgp * 16;
+      if (idle_ns) mbar_wait_idle(bar_accf, (uint32_t)j & 1u, idle_ns);
+      else mbar_wait(bar_accf, (uint32_t)j & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      double sum[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) sum[i] = 0.0;
+      const uint32_t tbase = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(cgp * 16);
 #pragma unroll
       for (int d = S - 1; d >= 0; --d) {
-        uint32_t v0[16], v1[16];
+        uint32_t v[16];
         if (n_iter > 0) {
-          const uint32_t ta = tbase + (((uint32_t)d + rot) & 7u) * OZ_BN;
-          tmem_ld16(ta, v0);
-          tmem_ld16(ta + 16, v1);
+          tmem_ld16(tbase + (((uint32_t)d + rot) & 7u) * OZ_BN, v);
           tmem_ld_wait();
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -596,33 +632,24 @@ ozaki_gemm_stream_kernel(const OzGemmArgs args, const int gx, const int gy, cons
         if (lane == 0) mbar_arrive(bar_drained + 8 * d);
         if (n_iter > 0) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            sum[i] = fma(sum[i], 0.00390625, i32_to_f64(v0[i]));
-            sum[16 + i] = fma(sum[16 + i], 0.00390625, i32_to_f64(v1[i]));
-          }
+          for (int i = 0; i < 16; ++i) sum[i] = fma(sum[i], 0.00390625, i32_to_f64(v[i]));
         }
       }
-      const double sa = args.A.scale[(long long)b * args.A.sc_batch + a_row + row] * args.alpha;
-      const double* sbp = args.B.scale + (long long)b * args.B.sc_batch + b_row + ch * 32;
-      double* Cb = args.C + (long long)b * args.c_batch;
-      double* crow = Cb + (long long)(c_row + row) * args.ldc + c_col + ch * 32;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) sum[i] = (sum[i] * sa) * __ldg(sbp + i);
+      for (int i = 0; i < 16; ++i) sum[i] = (sum[i] * sa) * __ldg(sbp + i);
       if (beta != 0.0) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          double o0, o1, o2, o3;
-          ld_global_v4(crow + i, o0, o1, o2, o3);
-          st_global_v4(crow + i, fma(beta, o0, sum[i]), fma(beta, o1, sum[i + 1]), fma(beta, o2, sum[i + 2]), fma(beta, o3, sum[i + 3]));
-        }
+        for (int i = 0; i < 16; i += 4)
+          st_global_v4(crow + i, fma(beta, old[i], sum[i]), fma(beta, old[i + 1], sum[i + 1]), fma(beta, old[i + 2], sum[i + 2]),
+                       fma(beta, old[i + 3], sum[i + 3]));
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) st_global_v4(crow + i, sum[i], sum[i + 1], sum[i + 2], sum[i + 3]);
+        for (int i = 0; i < 16; i += 4) st_global_v4(crow + i, sum[i], sum[i + 1], sum[i + 2], sum[i + 3]);
       }
-      if (args.Ct != nullptr) {  // transposed copy (alpha A B^T only, as in the one-tile kernel): lanes = consecutive columns of Ct
-        double* Tb = args.Ct + (long long)b * args.c_batch + (long long)(t_row + ch * 32) * args.ldc + t_col + row;
+      if (args.Ct != nullptr) {  // transposed copy (alpha A B^T alone, as in the one-tile kernel): lanes = consecutive columns of Ct
+        double* Tb = args.Ct + (long long)b * args.c_batch + (long long)(t_row + cgp * 16) * args.ldc + t_col + row;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) Tb[(long long)i * args.ldc] = sum[i];
+        for (int i = 0; i < 16; ++i) Tb[(long long)i * args.ldc] = sum[i];
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * r);
@@ -1169,7 +1196,7 @@ static cudaError_t oz_gemm_stream_launch_t(const Launch& L, const OzGemmArgs& a,
   if (sms[dev & 63] == 0) AGPC_CUDA_TRY(cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
   const long long tiles = 2LL * tiles128 * groups * batch;
   const int grid = (int)(tiles < sms[dev & 63] ? tiles : sms[dev & 63]);
-  ozaki_gemm_stream_kernel<S><<<grid, OZ_THREADS, ozp_smem_bytes<S>(), L.stream>>>(a, 2 * tiles128, groups, batch, counter);
+  ozaki_gemm_stream_kernel<S><<<grid, OZS_THREADS, ozp_smem_bytes<S>(), L.stream>>>(a, 2 * tiles128, groups, batch, counter);
   return cudaGetLastError();
 }
 
@@ -1186,6 +1213,13 @@ cudaError_t oz_gemm_launch(const Launch& L, const OzGemmArgs& a, int tiles128, i
   // tile to run the same K range (KRULE_END_AT_COL clips per half).
   // AGPC_OZ_TILE=128: the 128 x 128 tile with its accumulators split over a CTA pair (ozaki_gemm128_kernel)
   static const int dbg_env = getenv("AGPC_OZ_DBG") ? atoi(getenv("AGPC_OZ_DBG")) : 0;
+  if ((dbg_env == 3 || dbg_env >= 100) && batch <= OZP_MAX_BATCH) {
+    OzGemmArgs d = a;
+    d.dbg = dbg_env;
+    int* counter = ozp_counter_for(L.stream);
+    if (counter != nullptr)
+      return S == 6 ? oz_gemm_stream_launch_t<6>(L, d, tiles128, groups, batch, counter) : oz_gemm_stream_launch_t<7>(L, d, tiles128, groups, batch, counter);
+  }
   if (dbg_env) {
     OzGemmArgs d = a;
     d.dbg = dbg_env;

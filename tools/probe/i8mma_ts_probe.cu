@@ -61,7 +61,7 @@ __host__ __device__ inline uint32_t make_idesc() {
 
 // whole problem resident in shared memory: KS k-steps x (S A-tiles of 4 KB + S B-tiles of 2 KB); every MMA / cp is issued
 // back to back by one thread with no wait in between (REPS > 1 repeats the whole sequence for the rate measurement)
-template <int S, int NT, int DB, int KS>
+template <int S, int NT, int DB, int KS, int MODE = 0>
 __global__ void __launch_bounds__(128, 1)
 ts_kernel(const int8_t* __restrict__ A, const int8_t* __restrict__ B, int32_t* __restrict__ out, int reps, long long* cycles) {
   extern __shared__ uint8_t raw[];
@@ -96,12 +96,16 @@ ts_kernel(const int8_t* __restrict__ A, const int8_t* __restrict__ B, int32_t* _
   const uint32_t idesc = make_idesc();
   const uint32_t ta_base = tmem + S * N;  // A buffers right after the S accumulators
   if (tid == 0) {
+    if (MODE == 1)
+      for (int p = 0; p < NT; ++p) tmem_cp(ta_base + p * 8, make_desc(base + p * A_T));
     const long long t0 = clock64();
     for (int rep = 0; rep < reps; ++rep)
       for (int ks = 0; ks < KS; ++ks) {
         const uint32_t sa = base + ks * STEP, sb = sa + S * A_T;
         const uint32_t ta = ta_base + (DB ? (uint32_t)(ks & 1) * NT * 8 : 0u);
-        for (int p = 0; p < NT; ++p) tmem_cp(ta + p * 8, make_desc(sa + p * A_T));
+        if (MODE != 1)
+          for (int p = 0; p < NT; ++p) tmem_cp(ta + p * 8, make_desc(sa + p * A_T));
+        if (MODE != 2)
         for (int p = 0; p < S; ++p)
           for (int q = 0; p + q < S; ++q) {
             const uint64_t db = make_desc(sb + q * B_T);
@@ -128,7 +132,7 @@ ts_kernel(const int8_t* __restrict__ A, const int8_t* __restrict__ B, int32_t* _
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
 }
 
-template <int S, int NT, int DB, int KS>
+template <int S, int NT, int DB, int KS, int MODE = 0>
 int run(int reps_rate, int data_mode = 0) {
   const int Ktot = KS * KB;
   std::vector<int8_t> hA((size_t)S * 128 * Ktot), hB((size_t)S * N * Ktot);
@@ -156,8 +160,8 @@ int run(int reps_rate, int data_mode = 0) {
   CK(cudaMemcpy(dB, hB.data(), hB.size(), cudaMemcpyHostToDevice));
   CK(cudaMemset(dO, 0xff, got.size() * 4));
   const int smem = KS * S * (128 + N) * KB + 1024;
-  CK(cudaFuncSetAttribute(ts_kernel<S, NT, DB, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  ts_kernel<S, NT, DB, KS><<<1, 128, smem>>>(dA, dB, dO, 1, nullptr);
+  CK(cudaFuncSetAttribute(ts_kernel<S, NT, DB, KS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  ts_kernel<S, NT, DB, KS, MODE><<<1, 128, smem>>>(dA, dB, dO, 1, nullptr);
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(got.data(), dO, got.size() * 4, cudaMemcpyDeviceToHost));
   size_t bad = 0;
@@ -165,7 +169,7 @@ int run(int reps_rate, int data_mode = 0) {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0);
-  ts_kernel<S, NT, DB, KS><<<148, 128, smem>>>(dA, dB, nullptr, reps_rate, dC);
+  ts_kernel<S, NT, DB, KS, MODE><<<148, 128, smem>>>(dA, dB, nullptr, reps_rate, dC);
   cudaEventRecord(e1);
   CK(cudaDeviceSynchronize());
   float ms;
@@ -173,6 +177,7 @@ int run(int reps_rate, int data_mode = 0) {
   long long cyc[148];
   CK(cudaMemcpy(cyc, dC, sizeof cyc, cudaMemcpyDeviceToHost));
   const double ksteps = (double)reps_rate * KS;
+  if (MODE) printf("[mode %d: %s] ", MODE, MODE == 1 ? "A copied to TMEM once, MMAs only in the loop (results not comparable)" : "cp only, no MMAs");
   printf("data=%s S=%d A-slices in TMEM=%d double-buffered=%d k-steps=%d : %s (%zu / %zu mismatches) | %.0f cycles per k-step "
          "(%d MMAs + %d cp), %.1f TF-equivalent chip (FP64 flops of the 128x64x32 tile-step / time)\n",
          data_mode == 2 ? "zero" : data_mode == 1 ? "small" : "random", S, NT, DB, KS, bad ? "FAIL" : "ok", bad, got.size(), cyc[0] / ksteps, S * (S + 1) / 2, NT,
@@ -188,6 +193,9 @@ int main() {
   bad += run<7, 0, 0, 4>(200, 2);
   bad += run<7, 0, 0, 4>(2000, 0);   // 10 x longer: set-up amortised, wall-clock rate ~ cycle rate if the clock holds
   bad += run<7, 0, 0, 4>(2000, 2);
+  run<7, 7, 0, 4, 1>(200);       // pure TS-mode MMA rate
+  run<7, 7, 0, 4, 2>(200);       // pure tcgen05.cp rate
+  run<6, 6, 0, 4, 1>(200);
   bad += run<7, 7, 0, 4>(200);   // all A slices in TMEM, single buffer: relies on mma -> cp ordering
   bad += run<7, 4, 1, 4>(200);   // A_0..A_3 in TMEM, double-buffered (64 spare columns)
   bad += run<7, 4, 0, 4>(200);
