@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libautogpc_b200.so")
-SOURCES = ["gemm_nt.cu", "ozaki.cu", "chol.cu", "kbuild.cu", "ep.cu", "score.cu", "capi.cu"]
+SOURCES = ["gemm_nt.cu", "ozaki.cu", "chol.cu", "kbuild.cu", "ep.cu", "score.cu", "optim.cu", "capi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

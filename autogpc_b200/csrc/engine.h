@@ -37,3 +37,10 @@ struct agpc_ctx {
   int ensure_arena(size_t bytes);
   size_t workspace_budget();
 };
+
+// score.cu: the scoring path with explicit per-item row lists (agpc_score_batch_dev = adjacent lists); used by optim.cu
+int score_items_dev(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, const agpc_program* programs,
+                    const double* theta_dev, int32_t theta_stride, const int32_t* rows_dev, const int64_t* row_start,
+                    const int32_t* row_len, const agpc_ep_options* opt, double* tau_dev, double* nu_dev,
+                    int32_t site_stride, double* nlml_dev, double* grad_dev, double* bic_dev, double* nlml_gauss_dev,
+                    int32_t* sweeps_dev, int32_t* status_dev, void* stream);

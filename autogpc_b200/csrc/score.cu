@@ -399,23 +399,24 @@ int laplace_chunk(agpc_ctx* ctx, Launch& L, Chunk& c, const agpc_ep_options* opt
 
 }  // namespace
 
-extern "C" {
-
-int agpc_score_batch_dev(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, const agpc_program* programs,
-                         const double* theta_dev, int32_t theta_stride, const int32_t* rows_dev,
-                         const int64_t* row_off, const agpc_ep_options* opt, double* tau_dev, double* nu_dev,
-                         int32_t site_stride, double* nlml_dev, double* grad_dev, double* bic_dev,
-                         double* nlml_gauss_dev, int32_t* sweeps_dev, int32_t* status_dev, void* stream) {
+// The scoring path proper.  Item b reads the row list rows_dev[row_start[b] .. row_start[b] + row_len[b]) -- the lists need
+// not be adjacent or ordered, which is what lets the on-device optimiser (optim.cu) pass the still-running subset of a
+// resident batch without re-packing its rows.
+int score_items_dev(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, const agpc_program* programs,
+                    const double* theta_dev, int32_t theta_stride, const int32_t* rows_dev, const int64_t* row_start,
+                    const int32_t* row_len, const agpc_ep_options* opt, double* tau_dev, double* nu_dev,
+                    int32_t site_stride, double* nlml_dev, double* grad_dev, double* bic_dev, double* nlml_gauss_dev,
+                    int32_t* sweeps_dev, int32_t* status_dev, void* stream) {
   if (!ctx) return AGPC_E_ARG;
   if (dataset_id < 0 || dataset_id >= (int)ctx->datasets.size() || !ctx->datasets[dataset_id].X)
     return fail(ctx, AGPC_E_ARG, "score_batch: bad dataset id");
-  if (n_items <= 0 || !programs || !theta_dev || !rows_dev || !row_off || !opt || !nlml_dev || !status_dev)
+  if (n_items <= 0 || !programs || !theta_dev || !rows_dev || !row_start || !row_len || !opt || !nlml_dev || !status_dev)
     return fail(ctx, AGPC_E_ARG, "score_batch: null argument");
   if (theta_stride <= 0 || theta_stride > 4096) return fail(ctx, AGPC_E_ARG, "score_batch: bad theta_stride");
   const Dataset& ds = ctx->datasets[dataset_id];
   int n_max = 0;
   for (int b = 0; b < n_items; ++b) {
-    const long long n = row_off[b + 1] - row_off[b];
+    const long long n = row_len[b];
     if (n <= 0 || n > ds.N * 4LL) return fail(ctx, AGPC_E_ARG, "score_batch: bad row_off");
     n_max = std::max<int>(n_max, (int)n);
     const agpc_program& p = programs[b];
@@ -456,11 +457,11 @@ int agpc_score_batch_dev(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, con
     std::vector<int> n_of(nb);
     std::vector<long long> off(nb + 1);
     for (int b = 0; b < nb; ++b) {
-      n_of[b] = (int)(row_off[first + b + 1] - row_off[first + b]);
-      off[b] = row_off[first + b];
+      n_of[b] = row_len[first + b];
+      off[b] = row_start[first + b];
       np = std::max(np, n_of[b]);
     }
-    off[nb] = row_off[first + nb];
+    off[nb] = off[nb - 1] + n_of[nb - 1];
     np = (int)align_up((size_t)np, TILE);
     Chunk c;
     c.carve((char*)ctx->arena, nb, np, ds.D, theta_stride, false, ctx->oz_S);
@@ -522,6 +523,26 @@ int agpc_score_batch_dev(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, con
     if (first + chunk_cap < n_items) CK(cudaStreamSynchronize(L.stream));  // arena is reused by the next chunk
   }
   return AGPC_OK;
+}
+
+extern "C" {
+
+int agpc_score_batch_dev(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, const agpc_program* programs,
+                         const double* theta_dev, int32_t theta_stride, const int32_t* rows_dev,
+                         const int64_t* row_off, const agpc_ep_options* opt, double* tau_dev, double* nu_dev,
+                         int32_t site_stride, double* nlml_dev, double* grad_dev, double* bic_dev,
+                         double* nlml_gauss_dev, int32_t* sweeps_dev, int32_t* status_dev, void* stream) {
+  if (!ctx) return AGPC_E_ARG;
+  if (n_items <= 0 || !row_off) return fail(ctx, AGPC_E_ARG, "score_batch: null argument");
+  std::vector<int32_t> len(n_items);
+  for (int b = 0; b < n_items; ++b) {
+    const long long n = row_off[b + 1] - row_off[b];
+    if (n <= 0 || n > 0x7fffffffLL) return fail(ctx, AGPC_E_ARG, "score_batch: bad row_off");
+    len[b] = (int32_t)n;
+  }
+  return score_items_dev(ctx, dataset_id, n_items, programs, theta_dev, theta_stride, rows_dev, row_off, len.data(), opt,
+                         tau_dev, nu_dev, site_stride, nlml_dev, grad_dev, bic_dev, nlml_gauss_dev, sweeps_dev, status_dev,
+                         stream);
 }
 
 int agpc_score_batch(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, const agpc_program* programs,

@@ -68,6 +68,18 @@ class EPOptions(C.Structure):
                 ("inference", C.c_int32), ("reserved", C.c_int32)]
 
 
+class LBFGSOptions(C.Structure):
+    """Mirror of ``agpc_lbfgs_options`` (defaults = paramz opt_lbfgsb / SciPy fmin_l_bfgs_b)."""
+    _fields_ = [("m", C.c_int32), ("max_evals", C.c_int32), ("maxiter", C.c_int32), ("maxls", C.c_int32),
+                ("factr", C.c_double), ("pgtol", C.c_double)]
+
+
+KIND_FREE, KIND_POSITIVE, KIND_BOUNDED = 0, 1, 2
+OPT_TASKS = {0: "running", 1: "CONVERGENCE: NORM_OF_PROJECTED_GRADIENT_<=_PGTOL",
+             2: "CONVERGENCE: REL_REDUCTION_OF_F_<=_FACTR*EPSMCH", 3: "STOP: TOTAL NO. of f AND g EVALUATIONS EXCEEDS LIMIT",
+             4: "STOP: TOTAL NO. of ITERATIONS REACHED LIMIT", 5: "ABNORMAL_TERMINATION_IN_LNSRCH",
+             6: "too many failed evaluations"}
+
 _lib = None
 
 
@@ -193,6 +205,53 @@ class Engine:
                                              _dp(grad) if want_grad else None, _dp(bic), _dp(gauss), _ip(sweeps),
                                              _ip(status)))
         return dict(nlml=nlml, grad=grad, bic=bic, nlml_gauss=gauss, sweeps=sweeps, status=status,
+                    tau=[tau_a[b, :len(rows[b])].copy() for b in range(B)],
+                    nu=[nu_a[b, :len(rows[b])].copy() for b in range(B)])
+
+    def optimize_batch(self, dataset: int, programs: Sequence[Program], thetas: Sequence[np.ndarray],
+                       kinds: Sequence[np.ndarray], lows: Sequence[np.ndarray], highs: Sequence[np.ndarray],
+                       rows: Sequence[np.ndarray], epsilon: float = 1e-6, damping: float = 1.0, max_sweeps: int = 100,
+                       max_evals: int = 1000, m: int = 10, factr: float = 1e7, pgtol: float = 1e-5, maxls: int = 20,
+                       maxiter: int = 15000) -> dict:
+        """``agpc_optimize_batch``: m.optimize() for B models in lock-step with the optimiser state on the device.
+        kinds[b][i] in (KIND_FREE, KIND_POSITIVE, KIND_BOUNDED) is the paramz constraint of parameter i of item b
+        (lows / highs only matter for KIND_BOUNDED).  Returns score_batch's dict at the optimum plus theta, evals,
+        iters and task (index into OPT_TASKS)."""
+        B = len(programs)
+        if not (B == len(thetas) == len(rows) == len(kinds) == len(lows) == len(highs)) or B == 0:
+            raise EngineError("programs, thetas, kinds, lows, highs and rows must have the same non-zero length")
+        stride = max(int(p.n_theta) for p in programs)
+        th = np.zeros((B, stride))
+        kd = np.zeros((B, stride), dtype=np.int32)
+        lo = np.zeros((B, stride))
+        hi = np.ones((B, stride))
+        for b in range(B):
+            n = int(programs[b].n_theta)
+            t = np.asarray(thetas[b], float).reshape(-1)
+            if t.shape[0] != n:
+                raise EngineError("theta length %d != program n_theta %d" % (t.shape[0], n))
+            th[b, :n] = t
+            kd[b, :n] = np.asarray(kinds[b], dtype=np.int32).reshape(-1)
+            lo[b, :n] = np.asarray(lows[b], float).reshape(-1)
+            hi[b, :n] = np.asarray(highs[b], float).reshape(-1)
+        row_off = np.zeros(B + 1, dtype=np.int64)
+        row_off[1:] = np.cumsum([len(r) for r in rows])
+        rows_cat = np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.int32) for r in rows]))
+        n_max = int(max(len(r) for r in rows))
+        ep = EPOptions(float(epsilon), float(damping), int(max_sweeps), 0, INFER_EP, 0)
+        lb = LBFGSOptions(int(m), int(max_evals), int(maxiter), int(maxls), float(factr), float(pgtol))
+        progs = (Program * B)(*programs)
+        tau_a, nu_a = np.zeros((B, n_max)), np.zeros((B, n_max))
+        nlml, bic, gauss = np.zeros(B), np.zeros(B), np.zeros(B)
+        grad = np.zeros((B, stride))
+        sweeps, status = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+        evals, iters, task = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+        self._check(self._L.agpc_optimize_batch(self._ctx, int(dataset), B, progs, _dp(th), stride, _ip(kd), _dp(lo), _dp(hi),
+                                                _ip(rows_cat), _lp(row_off), C.byref(ep), C.byref(lb), _dp(tau_a), _dp(nu_a),
+                                                n_max, _dp(nlml), _dp(grad), _dp(bic), _dp(gauss), _ip(sweeps), _ip(status),
+                                                _ip(evals), _ip(iters), _ip(task)))
+        return dict(theta=[th[b, :int(programs[b].n_theta)].copy() for b in range(B)], nlml=nlml, grad=grad, bic=bic,
+                    nlml_gauss=gauss, sweeps=sweeps, status=status, evals=evals, iters=iters, task=task,
                     tau=[tau_a[b, :len(rows[b])].copy() for b in range(B)],
                     nu=[nu_a[b, :len(rows[b])].copy() for b in range(B)])
 

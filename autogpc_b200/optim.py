@@ -10,6 +10,7 @@ models in wake-up storms -- more than the GPU needed for the evaluations at n = 
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, List, Sequence, Tuple
 
 import numpy as np
@@ -133,12 +134,61 @@ def _single_threaded_blas():
         return contextlib.nullcontext()
 
 
-def optimize_models(models, max_evals: int = 1000, warm_start: bool = True):
+_KIND = {"free": 0, "positive": 1, "bounded": 2}
+
+
+def device_optimizer_default(models) -> bool:
+    """The on-device optimiser is the default wherever it applies (EP inference, an engine that has it); AGPC_DEVICE_OPT=0
+    keeps every ``optimize_models`` call on the SciPy driver (bit-for-bit SciPy trajectories), =1 insists on the device."""
+    env = os.environ.get("AGPC_DEVICE_OPT", "")
+    if env == "0":
+        return False
+    able = hasattr(models[0].engine, "optimize_batch") and all(m.ep.get("inference", "ep") == "ep" for m in models)
+    if env not in ("", "0") and not able and hasattr(models[0].engine, "optimize_batch"):
+        raise ValueError("AGPC_DEVICE_OPT=1: the on-device optimiser runs EP inference only")
+    return able
+
+
+def optimize_models_device(models, max_evals: int = 1000):
+    """``optimize_models`` with the L-BFGS state on the device (``agpc_optimize_batch``, csrc/optim.cu): the iterates, the
+    limited-memory pairs, the line searches and the EP sites of all models stay in HBM; per round the host only reads
+    the "still running" flags.  Same algorithm and stopping rules as the SciPy driver below, not the same rounding."""
+    engine = models[0].engine
+    by_ds = {}
+    for mdl in models:
+        if mdl.ep.get("inference", "ep") != "ep":
+            raise ValueError("the on-device optimiser runs EP inference only")
+        by_ds.setdefault(mdl._dataset, []).append(mdl)
+    for ds, group in by_ds.items():
+        params = [m.kern.flat_params() for m in group]
+        ep = {k: v for k, v in group[0].ep.items() if k != "inference"}
+        r = engine.optimize_batch(
+            ds, [m._program for m in group], [m.kern.param_array for m in group],
+            [[_KIND[p.kind] for p in ps] for ps in params],
+            [[0.0 if p.lo is None else p.lo for p in ps] for ps in params],
+            [[1.0 if p.hi is None else p.hi for p in ps] for ps in params],
+            [m._rows for m in group], max_evals=max_evals, **ep)
+        for b, mdl in enumerate(group):
+            mdl.kern.set_param_array(r["theta"][b])
+            mdl._absorb(r, b)
+            task = int(r["task"][b])
+            warnflag = 0 if task in (1, 2) else 1 if task in (3, 4) else 2
+            mdl.optimization_info = dict(funcalls=int(r["evals"][b]), evals=int(r["evals"][b]), nit=int(r["iters"][b]),
+                                         warnflag=warnflag, task=task, device=True)
+            if task == 6:
+                mdl.optimization_error = np.linalg.LinAlgError("too many failed evaluations")
+
+
+def optimize_models(models, max_evals: int = 1000, warm_start: bool = True, device: bool = None):
     """Optimise GPClassification shims in lock-step.  Each evaluation of every live model is one item of one
     ``score_batch``; EP is warm-started from the model's previous sites.  Models must share an engine; they may
-    live on different datasets only if the engine call is split, so they are grouped by dataset id."""
+    live on different datasets only if the engine call is split, so they are grouped by dataset id.
+    By default the optimiser state lives on the GPU (``optimize_models_device``, csrc/optim.cu); ``device=False`` or
+    AGPC_DEVICE_OPT=0 selects this host driver, which steps SciPy's own L-BFGS-B."""
     if not models:
         return
+    if device_optimizer_default(models) if device is None else device:
+        return optimize_models_device(models, max_evals=max_evals)
     engine = models[0].engine
     fails = [0] * len(models)
     evals = [0] * len(models)

@@ -154,6 +154,34 @@ int agpc_score_batch_dev(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, con
                          int32_t site_stride, double* nlml_dev, double* grad_dev, double* bic_dev,
                          double* nlml_gauss_dev, int32_t* sweeps_dev, int32_t* status_dev, void* stream);
 
+/* ---- m.optimize() (gpckernel.py:246) for a whole batch, on the device ------------------------
+ * paramz opt_lbfgsb = SciPy L-BFGS-B over the transformed parameters; here the limited-memory pairs, the Moré-Thuente
+ * line search state, the iterates and the EP sites of every model stay in HBM, one round = one scoring pass over the
+ * models still running + one kernel that advances every model to its next trial point.  theta (host, in/out): start
+ * values in, optimum out.  kinds / lo / hi (host, [n_items][theta_stride]): the parameter's paramz constraint -- 0 free,
+ * 1 positive (Logexp), 2 bounded (Logistic on [lo, hi]).  Outputs as agpc_score_batch at the optimum, plus per item the
+ * number of objective evaluations, L-BFGS iterations and the reason it stopped (AGPC_OPT_*). */
+typedef struct agpc_lbfgs_options {
+  int32_t m;         /* limited-memory pairs, 1..10 (paramz: 10)                                   */
+  int32_t max_evals; /* SciPy maxfun: stop at the first new iterate after this many evaluations    */
+  int32_t maxiter;   /* SciPy maxiter (<= 0: 15000)                                                */
+  int32_t maxls;     /* evaluations per line search before it is abandoned (SciPy: 20)             */
+  double factr;      /* stop when (f_old - f) <= factr * eps * max(|f_old|, |f|, 1)  (paramz: 1e7) */
+  double pgtol;      /* stop when max |g| <= pgtol                                   (paramz: 1e-5) */
+} agpc_lbfgs_options;
+#define AGPC_OPT_CONV_PGTOL 1
+#define AGPC_OPT_CONV_FACTR 2
+#define AGPC_OPT_STOP_MAXFUN 3
+#define AGPC_OPT_STOP_MAXITER 4
+#define AGPC_OPT_ABNORMAL_LINESEARCH 5
+#define AGPC_OPT_TOO_MANY_FAILURES 6
+int agpc_optimize_batch(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, const agpc_program* programs,
+                        double* theta, int32_t theta_stride, const int32_t* kinds, const double* lo, const double* hi,
+                        const int32_t* rows, const int64_t* row_off, const agpc_ep_options* ep,
+                        const agpc_lbfgs_options* lb, double* tau, double* nu, int32_t site_stride, double* nlml,
+                        double* grad, double* bic, double* nlml_gauss, int32_t* sweeps, int32_t* status,
+                        int32_t* evals, int32_t* iters, int32_t* task);
+
 /* ---- m.predict(XT) (gpckernel.py:832): p* = Phi(mu* / sqrt(1 + v*)) per test row ------------------------------
  * test rows are dataset rows `test_rows[test_off[b] .. test_off[b+1])`; p_out is laid out the same way.
  * Optionally also returns the latent mean / variance (m._raw_predict, gpcplot.py:110-114). */

@@ -961,3 +961,87 @@ print(json.dumps(out))
             assert res[oz][n][0] <= 1e-12 and res[oz][n][1] <= 1e-12 and res[oz][n][2] <= 1e-12, (oz, n, res[oz][n])
         assert abs(res["7"][n][3] - res["0"][n][3]) <= 1e-10 * abs(res["0"][n][3])
         assert abs(res["7"][n][4] - res["0"][n][4]) <= 1e-10 * abs(res["0"][n][4])
+
+
+@pytest.mark.gpu
+def test_device_optimizer_matches_host_driver(engine):
+    """m.optimize() (gpckernel.py:246) with the L-BFGS state on the device (agpc_optimize_batch) against the
+    host driver that steps SciPy's own L-BFGS-B (optim.lbfgsb_lockstep).  Same algorithm and stopping rules, different
+    rounding, so the trajectories agree to optimiser tolerance, not bit for bit: every model must end at the same
+    optimum (NLML to 1e-4 relative -- factr = 1e7 stops at 2e-9 relative decrease per iteration --, hyper-parameters to
+    2 %), with a comparable number of evaluations, and leave consistent sites behind (re-scoring at theta* from the
+    returned sites reproduces the returned NLML)."""
+    from autogpc_b200 import engine as eng_mod
+    from autogpc_b200 import gpy_compat as GPy
+    from autogpc_b200 import optim
+
+    X, y = synth(260, 3, 31)
+    eng_mod.set_default_engine(engine)
+    did = engine.dataset(X, y)
+    rng = np.random.default_rng(12)
+
+    def kernels():
+        k = []
+        k.append(GPy.kern.RBF(1, variance=1.3, lengthscale=0.7, active_dims=[0]))
+        k.append(GPy.kern.Prod([GPy.kern.RBF(1, variance=0.8, lengthscale=1.5, active_dims=[0]),
+                                GPy.kern.RBF(1, variance=1.1, lengthscale=0.9, active_dims=[1])]))
+        k.append(GPy.kern.Add([GPy.kern.RBF(1, variance=0.6, lengthscale=2.0, active_dims=[2]),
+                               GPy.kern.Bias(3, variance=0.5)]))
+        per = GPy.kern.StdPeriodic(1, variance=1.0, period=2.5, lengthscale=1.2, active_dims=[1])
+        per["period"].constrain_bounded(0.5, 6.0, warning=False)      # a Logistic-transformed parameter
+        k.append(GPy.kern.Add([per, GPy.kern.RBF(1, variance=0.9, lengthscale=1.1, active_dims=[0])]))
+        k.append(GPy.kern.Linear(1, variance=0.7, location=0.2, active_dims=[0]))    # a free (untransformed) parameter
+        return k
+
+    folds = [np.sort(rng.choice(260, size=200 + 10 * i, replace=False)).astype(np.int32) for i in range(5)]
+
+    def models():
+        return [GPy.models.GPClassification(kernel=k, engine=engine, _dataset=did, _rows=r, _infer=False)
+                for k, r in zip(kernels(), folds)]
+
+    host, dev = models(), models()
+    optim.optimize_models(host, max_evals=200, device=False)
+    optim.optimize_models(dev, max_evals=200, device=True)
+    for i, (h, d) in enumerate(zip(host, dev)):
+        assert d.optimization_info["device"] and d.status in (0, 1), (i, d.status)
+        assert d._nlml == pytest.approx(h._nlml, rel=1e-4, abs=1e-4), (i, h._nlml, d._nlml, h.optimization_info, d.optimization_info)
+        assert np.allclose(d.kern.param_array, h.kern.param_array, rtol=2e-2, atol=1e-3), (i, h.kern.param_array, d.kern.param_array)
+        assert d.optimization_info["warnflag"] == h.optimization_info["warnflag"], (i, h.optimization_info, d.optimization_info)
+        assert abs(d.optimization_info["evals"] - h.optimization_info["evals"]) <= max(6, 0.5 * h.optimization_info["evals"])
+        # the sites that came back belong to theta*: a warm-started re-evaluation stays put
+        again = engine.score_batch(did, [d._program], [d.kern.param_array], [d._rows], tau=[d._tau], nu=[d._nu], **d.ep)
+        assert again["nlml"][0] == pytest.approx(d._nlml, rel=1e-7)
+    engine.dataset_free(did)
+
+
+@pytest.mark.gpu
+def test_device_optimizer_keeps_search_selection(engine):
+    """north_star for N1: routing gpcsearch's training through the on-device optimiser must not change which structure is
+    selected at any depth (same twin-search set-up as test_search_selects_identical_structures_as_oracle)."""
+    from autogpc_b200 import engine as eng_mod
+    from autogpc_b200 import gpckernel
+    from autogpc_b200.gpcdata import GPCData
+    from autogpc_b200.gpcsearch import GPCSearch
+
+    X, y = synth(150, 3, 8)
+
+    def run(device):
+        old = os.environ.get("AGPC_DEVICE_OPT")
+        os.environ["AGPC_DEVICE_OPT"] = "1" if device else "0"
+        try:
+            eng_mod.set_default_engine(engine)
+            gpckernel.set_rng(5)
+            d = GPCData(X, y.reshape(-1, 1), seed=1)
+            s = GPCSearch(d, base_kernels="SE,Lin,Per", max_depth=2, beam_width=1, criterion="bic", n_folds=3, max_evals=60)
+            best, _ = s.search()
+            return [k.kernel.structure() for k in best], [s.score(k) for k in best]
+        finally:
+            if old is None:
+                os.environ.pop("AGPC_DEVICE_OPT", None)
+            else:
+                os.environ["AGPC_DEVICE_OPT"] = old
+
+    names_h, scores_h = run(False)
+    names_d, scores_d = run(True)
+    assert names_h == names_d, (names_h, names_d)
+    assert np.allclose(scores_h, scores_d, rtol=1e-3), (scores_h, scores_d)
