@@ -104,6 +104,7 @@ int agpc_destroy(agpc_ctx* ctx) {
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->stage) cudaFree(ctx->stage);
+  if (ctx->opt_stage) cudaFree(ctx->opt_stage);
   if (ctx->prof.base) cudaEventDestroy(ctx->prof.base);
   for (auto& r : ctx->prof.recs) {
     cudaEventDestroy(r.e0);

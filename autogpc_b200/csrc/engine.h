@@ -29,6 +29,8 @@ struct agpc_ctx {
   void* scratch = nullptr;  // 64 KB device scratch: program + theta of the building-block entry points
   void* stage = nullptr;    // grow-only device staging of the host-buffer entry point (cudaMalloc / cudaFree per
   size_t stage_bytes = 0;   // call cost 0.5-350 ms on a box with > 100 GB allocated: profiles/r01_summary.md)
+  void* opt_stage = nullptr;  // the same for agpc_optimize_batch (optimiser state, compact staging of the running subset)
+  size_t opt_stage_bytes = 0;
   std::vector<Dataset> datasets;
   std::vector<Dataset> dataset_pool;  // buffers of destroyed datasets kept for re-use (at most 4): no cudaMalloc /
                                       // cudaFree when a caller re-uploads a same-shaped dataset per step

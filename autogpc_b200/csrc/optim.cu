@@ -501,17 +501,15 @@ int fail(agpc_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess)
     if (_e != cudaSuccess) return fail(ctx, AGPC_E_CUDA, #expr, _e);  \
   } while (0)
 
-struct DevBuf {  // RAII for the call's device buffers
-  std::vector<void*> ptrs;
-  ~DevBuf() {
-    for (void* p : ptrs) cudaFree(p);
-  }
+struct Carve {  // bump allocator over one grow-only device buffer (base == nullptr: size pass)
+  char* base;
+  size_t off = 0;
   template <class T>
   T* get(size_t n) {
-    void* p = nullptr;
-    if (cudaMalloc(&p, sizeof(T) * (n ? n : 1)) != cudaSuccess) return nullptr;
-    ptrs.push_back(p);
-    return static_cast<T*>(p);
+    off = (off + 255) / 256 * 256;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += sizeof(T) * (n ? n : 1);
+    return p;
   }
 };
 
@@ -548,31 +546,31 @@ extern "C" int agpc_optimize_batch(agpc_ctx* ctx, int32_t dataset_id, int32_t n_
   const int ss = n_max;  // internal site pitch
   const size_t nth = (size_t)n_items * theta_stride, n_rows = (size_t)row_off[n_items];
 
-  DevBuf D;
-  ItemState* d_st = D.get<ItemState>(n_items);
-  double* d_theta0 = D.get<double>(nth);
-  int* d_kinds = D.get<int>(nth);
-  double* d_lo = D.get<double>(nth);
-  double* d_hi = D.get<double>(nth);
-  int* d_nth = D.get<int>(n_items);
-  int* d_rows = D.get<int>(n_rows);
-  double* d_tau = D.get<double>((size_t)n_items * ss);
-  double* d_nu = D.get<double>((size_t)n_items * ss);
-  int* d_idx = D.get<int>(n_items);
-  int* d_live = D.get<int>(n_items);
-  double* c_theta = D.get<double>(nth);
-  double* c_tau = D.get<double>((size_t)n_items * ss);
-  double* c_nu = D.get<double>((size_t)n_items * ss);
-  double* c_nlml = D.get<double>(n_items);
-  double* c_grad = D.get<double>(nth);
-  double* c_bic = D.get<double>(n_items);
-  double* c_gauss = D.get<double>(n_items);
-  int* c_sweeps = D.get<int>(n_items);
-  int* c_status = D.get<int>(n_items);
-  int* d_rep = D.get<int>(3 * (size_t)n_items);
-  if (!d_st || !d_theta0 || !d_kinds || !d_lo || !d_hi || !d_nth || !d_rows || !d_tau || !d_nu || !d_idx || !d_live ||
-      !c_theta || !c_tau || !c_nu || !c_nlml || !c_grad || !c_bic || !c_gauss || !c_sweeps || !c_status || !d_rep)
-    return fail(ctx, AGPC_E_NOMEM, "optimize_batch: cudaMalloc");
+  ItemState* d_st;
+  double *d_theta0, *d_lo, *d_hi, *d_tau, *d_nu, *c_theta, *c_tau, *c_nu, *c_nlml, *c_grad, *c_bic, *c_gauss;
+  int *d_kinds, *d_nth, *d_rows, *d_idx, *d_live, *c_sweeps, *c_status, *d_rep;
+  auto carve = [&](char* base) {
+    Carve D{base};
+    d_st = D.get<ItemState>(n_items);
+    d_theta0 = D.get<double>(nth); d_kinds = D.get<int>(nth); d_lo = D.get<double>(nth); d_hi = D.get<double>(nth);
+    d_nth = D.get<int>(n_items); d_rows = D.get<int>(n_rows);
+    d_tau = D.get<double>((size_t)n_items * ss); d_nu = D.get<double>((size_t)n_items * ss);
+    d_idx = D.get<int>(n_items); d_live = D.get<int>(n_items);
+    c_theta = D.get<double>(nth); c_tau = D.get<double>((size_t)n_items * ss); c_nu = D.get<double>((size_t)n_items * ss);
+    c_nlml = D.get<double>(n_items); c_grad = D.get<double>(nth); c_bic = D.get<double>(n_items); c_gauss = D.get<double>(n_items);
+    c_sweeps = D.get<int>(n_items); c_status = D.get<int>(n_items); d_rep = D.get<int>(3 * (size_t)n_items);
+    return D.off + 256;
+  };
+  const size_t total = carve(nullptr);
+  if (ctx->opt_stage_bytes < total) {  // grow-only: no cudaMalloc / cudaFree on the steady-state path
+    if (ctx->opt_stage) cudaFree(ctx->opt_stage);
+    ctx->opt_stage = nullptr;
+    ctx->opt_stage_bytes = 0;
+    const size_t want = total + total / 4;
+    if (cudaMalloc(&ctx->opt_stage, want) != cudaSuccess) return fail(ctx, AGPC_E_NOMEM, "optimize_batch: cudaMalloc");
+    ctx->opt_stage_bytes = want;
+  }
+  carve(static_cast<char*>(ctx->opt_stage));
 
   std::vector<int> h_nth(n_items);
   for (int b = 0; b < n_items; ++b) h_nth[b] = programs[b].n_theta;

@@ -593,6 +593,8 @@ def main():
         train = {"value": len(cands) / dt, "unit": UNIT, "seconds": dt, "evals_budget_per_fold": args.train_evals,
                  "folds": N_FOLDS, "candidates": len(cands), "evaluations_this_rank": evals,
                  "gpu_launches": int(eng.launches - l0),
+                 "optimizer": "device (agpc_optimize_batch, csrc/optim.cu)" if os.environ.get("AGPC_DEVICE_OPT", "") != "0"
+                              else "host (SciPy setulb stepped per model, optim.py)",
                  "ranking": [(c.kernel.structure(), round(float(c.bic()), 3), round(float(c.error()), 4))
                              for c in sorted(cands, key=lambda k: (k.bic(), k.kernel.structure()))][:8],
                  "note": "gpckernel.train_kernels(mode='full', n_folds=5, max_evals=%d): every (candidate, fold) model "
@@ -628,9 +630,14 @@ def main():
             bf16 = peaks.get("bf16_tflops_sustained") or 1400.0
             peak = 2.0 * bf16
             achieved = oz["work"] / (oz["ms"] * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "ozaki_gemm_kernel<S> (tcgen05.mma kind::i8, accumulators in TMEM, bulk-copy "
-                                                 "fed; sliced-integer FP64 GEMM behind potrf trailing updates, trtri, lauum)",
-                    "achieved": achieved, "peak": peak, "unit": "TOP/s (int8)", "frac": achieved / peak, "traffic": None,
+            roof = {"bound": "tensor", "kernel": "ozaki_gemm_stream_kernel<S> (persistent CTAs, tcgen05.mma kind::i8, rotating "
+                                                 "accumulator slots in TMEM, bulk-copy fed; sliced-integer FP64 GEMM behind potrf "
+                                                 "updates, trtri, lauum)",
+                    "achieved": achieved, "peak": peak, "unit": "TOP/s (int8)", "frac": achieved / peak,
+                    "traffic": 1.554e9,
+                    "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 5 launches of this kernel "
+                                    "in profiles/r02_stream_kb_ncu_raw.csv (ncu --set full of this command with --kernels-only; "
+                                    "1.34-2.01 GB per launch: operand slices read once + the C tiles read and written once)",
                     "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (%s); the same kernel's MMA loop on "
                                    "resident operands sustains 4.4-4.5 POP/s at N >= 128 and 2.9 POP/s at its own N = 64 tile "
                                    "(TMEM holds S x 64 accumulator columns), profiles/r02_i8mma_probe.txt"
