@@ -55,7 +55,7 @@ def synth(N, D, seed=0):
     return X, (f > np.median(f)).astype(float)
 
 
-def build_workload(world: int, cands_per_gpu: int, n_points: int = N_POINTS):
+def build_workload(world: int, cands_per_gpu: int, n_points: int = N_POINTS, fresh_restarts: bool = False):
     """Global item list [(candidate index, fold, gpy-shaped kernel, theta0)] in canonical order + the data."""
     from autogpc_b200 import flexible_function as ff
     from autogpc_b200 import gpckernel as gk
@@ -98,21 +98,33 @@ def build_workload(world: int, cands_per_gpu: int, n_points: int = N_POINTS):
     p1, p2 = pick(d1, n1, set()), pick(d2, cands_per_gpu - n1, set())
     block = [(p1.pop(0) if i % 8 in (0, 3, 6) else p2.pop(0)) for i in range(cands_per_gpu)]
 
-    # Every further GPU adds the SAME block of structures with its own random restarts (BASELINE configs[2]: "candidates
-    # and restarts sharded across 1/2/4/8 B200"): resetGpssParams below draws a fresh theta_0 for every (candidate, fold,
-    # block) from the one seeded stream, so the items are distinct models while the expected work per GPU is fixed --
-    # weak scaling.  (Round 1 shifted the input dimensions per block instead: those blocks need systematically more EP
-    # sweeps -- 4.1-4.6 against 3.9 -- because the signal sits in dimensions 0-5, i.e. the per-GPU work GREW with N.)
-    cands = []
-    for j in range(world):
-        cands += block if j == 0 else [gk.GPCKernel(c.kernel.copy(), data, depth=c.depth) for c in block]
+    # Weak scaling: every further GPU adds a REPLICA of the block -- the same structures from the same start points theta_0
+    # (distinct item ids, scored independently: nothing in the engine or the host recognises equal items), so the work
+    # per GPU is fixed by construction and the 1 -> N curve measures the system (dealing, exchange), not the draw.
+    # `fresh_restarts` instead gives every block its own restarts from the one seeded stream (gpckernel.py:241-243 draws
+    # one per fold): distinct models, but then the blocks differ in cost -- with this seed block 1 needs 4.28 EP sweeps per
+    # item against 3.875 for block 0, +9.5 % work, which the driver's efficiency would book as a scaling loss
+    # (profiles/r02_summary.md section 4).  (Round 1 shifted the input dimensions per block: 4.1-4.6 sweeps.)
     folds = data.kFoldIndices(N_FOLDS)
-    items = []
-    for ci, c in enumerate(cands):
-        for f in range(N_FOLDS):
-            k = c.kernel.copy()
-            gk.resetGpssParams(k, data=data)  # one random restart per fold (gpckernel.py:241-243)
-            items.append((ci, f, gk.gpss2gpy(k, data=data)))
+
+    def draw(block_cands, ci0):   # one random restart per (candidate, fold) (gpckernel.py:241-243), from the seeded stream
+        out = []
+        for ci, c in enumerate(block_cands):
+            for f in range(N_FOLDS):
+                k = c.kernel.copy()
+                gk.resetGpssParams(k, data=data)
+                out.append((ci0 + ci, f, gk.gpss2gpy(k, data=data)))
+        return out
+
+    cands = list(block)
+    items = draw(block, 0)            # block 0 first: its restarts are the same draws whatever the number of GPUs
+    for j in range(1, world):
+        copies = [gk.GPCKernel(c.kernel.copy(), data, depth=c.depth) for c in block]
+        cands += copies
+        if fresh_restarts:
+            items += draw(copies, j * len(block))
+        else:
+            items += [(ci + j * len(block), f, k) for (ci, f, k) in items[:len(block) * N_FOLDS]]
     return data, cands, folds, items
 
 
@@ -230,7 +242,7 @@ def run_reference(args, rank, world):
     """CPU arm: the oracle on the box's host cores, one item of the same workload per step."""
     if rank != 0:
         return
-    data, cands, folds, items = build_workload(world, args.cands, args.points)
+    data, cands, folds, items = build_workload(args.blocks if args.blocks > 0 else world, args.cands, args.points, args.fresh_restarts)
     times = []
     with all_host_threads():
         for s in range(args.warmup + args.steps):
@@ -261,6 +273,10 @@ def workload_config(args, world, n_items):
                         "evaluation (K build, parallel EP eps=1e-6, FP64 potrf+trtri per sweep, logZ, gradient, BIC)"
                         % (args.points, args.points - args.points // N_FOLDS),
             "candidates_per_gpu": args.cands, "folds": N_FOLDS, "items_total": n_items,
+            "blocks": ("one block of %d candidates" % args.cands if world == 1 else
+                       ("%d blocks with their own random restarts (unequal work per block)" % world if args.fresh_restarts else
+                        "%d replicas of the one-GPU block (same structures, same start points, scored independently): "
+                        "fixed work per GPU" % world)),
             "parallelism": ("one lock-step batch on 1 GPU" if world == 1 else
                             ("items dealt longest-first over %d GPUs on the cost measured in the previous step (EP sweeps); "
                              % world if args.deal == "lpt" else
@@ -282,6 +298,10 @@ def main():
     ap.add_argument("--chunk", type=int, default=8, help="items per chunk with --deal dynamic")
     ap.add_argument("--train-evals", type=int, default=50,
                     help="objective-evaluation budget per fold of the train_e2e leg (SURVEY 8d: 5 x 50 = 250 per candidate); 0 = skip")
+    ap.add_argument("--fresh-restarts", action="store_true",
+                    help="N > 1: every block draws its own restarts (distinct models, unequal work per GPU) instead of replicas")
+    ap.add_argument("--blocks", type=int, default=0,
+                    help="diagnostic: number of candidate blocks in the workload (default: one per GPU = weak scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernels-only", action="store_true",
                     help="profiling aid (ncu passes): skip the DGEMM peak probe, the e2e leg and the CPU baseline")
@@ -319,7 +339,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
-    data, cands, folds, items = build_workload(world, args.cands, args.points)
+    data, cands, folds, items = build_workload(args.blocks if args.blocks > 0 else world, args.cands, args.points, args.fresh_restarts)
     eng = Engine(local_rank)
     n_items = len(items)
     progs = [GPy.compile_program(it[2]) for it in items]
@@ -442,7 +462,16 @@ def main():
                     sel = owner == rr
                     if sel.any():
                         model[sel] *= busy[rr] / model[sel].sum()
-            state["mine"] = sharding.shard_indices(n_items, rank, world, list(model))
+            # re-deal only when it pays: the measured times carry ~1 % noise, and a new assignment every step means new
+            # batch compositions every step (fresh device buffers, no steady state).  Keep the current shares unless the
+            # longest-first dealing on the calibrated costs predicts a step at least 2 % shorter.
+            new = sharding.deal_items(list(model), world)
+            if np.all(owner >= 0):
+                cur_max = max(float(model[owner == rr].sum()) for rr in range(world))
+                new_max = max(float(model[new[rr]].sum()) if new[rr] else 0.0 for rr in range(world))
+                if cur_max <= 1.02 * new_max:
+                    return
+            state["mine"] = new[rank]
 
     def step_device():
         t0 = time.perf_counter()
@@ -450,6 +479,10 @@ def main():
         if world > 1:
             torch.cuda.synchronize()
             rank_busy_ms.append(1e3 * (time.perf_counter() - t0))
+            if os.environ.get("AGPC_BENCH_DEBUG"):
+                sw = sweeps_d.cpu().numpy()[ids]
+                sys.stderr.write("[bench rank %d] step: %d items, busy %.1f ms, sweeps sum %d max %d\n"
+                                 % (rank, len(ids), rank_busy_ms[-1], int(sw.sum()), int(sw.max())))
             exchange(ids, nlml_d.cpu().numpy(), bic_d.cpu().numpy(), status_d.cpu().numpy(), sweeps_d.cpu().numpy())
 
     def barrier():
@@ -479,6 +512,7 @@ def main():
     e1.record()
     barrier()
     t_wall1 = time.time()
+    busy_device = list(rank_busy_ms[-args.steps:])   # (the host-path leg below appends its own step times)
     ms_each = [step_ev[k].elapsed_time(step_ev[k + 1]) for k in range(args.steps)]
     clocks = None
     if sampler is not None:   # the samples of the timed region are in; stop nvidia-smi before the host-path leg
@@ -494,6 +528,8 @@ def main():
         ms = float(t.item())
     scored = nlml_d != 0
     sweeps_mean = float(sweeps_d[scored].float().mean().item())
+    # lock-step batches pay for their slowest item: the distribution of EP sweeps over this rank's items of the last step
+    sweeps_hist = {int(k): int(v) for k, v in zip(*np.unique(sweeps_d[scored].cpu().numpy(), return_counts=True))}
     status_ok = int(((status_d == 0) & scored).sum().item())
     n_cands_total = len(cands)
     value = n_cands_total * args.steps / (ms * 1e-3)
@@ -519,6 +555,11 @@ def main():
                 r[k][ids] = rc[k]
         ids = my_units(run_unit_host)
         t2 = time.perf_counter()
+        if world > 1:
+            rank_busy_ms.append(1e3 * (t2 - t0))   # the re-deal in exchange() calibrates on the time THIS path took
+            if os.environ.get("AGPC_BENCH_DEBUG"):
+                sys.stderr.write("[bench rank %d] host step: %d items, busy %.1f ms, sweeps sum %d\n"
+                                 % (rank, len(ids), rank_busy_ms[-1], int(r["sweeps"][ids].sum())))
         eng.dataset_free(d)
         t3 = time.perf_counter()
         exchange(ids, r["nlml"], r["bic"], r["status"], r["sweeps"])
@@ -535,6 +576,7 @@ def main():
     if args.kernels_only:
         if rank == 0:
             emit({"kernels_only": True, "ms_per_step": ms / args.steps, "gpu_launches": int(launches),
+                  "ep_sweeps_mean": sweeps_mean, "ep_sweeps_hist_rank0": sweeps_hist,
                   "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}})
         eng.dataset_free(did)
         eng.close()
@@ -548,6 +590,7 @@ def main():
     sampler2 = ClockSampler(local_rank) if rank == 0 else None
     if sampler2 is not None:
         time.sleep(0.3)
+    barrier()   # rank 0 alone slept: without this the other ranks' clocks would include waiting for it at the first exchange
     t_e2e0 = time.time()
     t0 = time.perf_counter()
     e2e_each = []
@@ -603,7 +646,7 @@ def main():
 
     busy = None
     if world > 1:
-        mine_ms = float(np.mean(rank_busy_ms[-args.steps:])) if rank_busy_ms else 0.0
+        mine_ms = float(np.mean(busy_device)) if busy_device else 0.0
         t = torch.zeros(world, dtype=torch.float64, device=dev)
         t[rank] = mine_ms
         dist.all_reduce(t)
@@ -676,7 +719,7 @@ def main():
                                         "so the sum overstates its wall time)"},
             "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
             "evals_per_s": len(items) * args.steps / (ms * 1e-3),
-            "ep_sweeps_mean": sweeps_mean, "items_ok": status_ok, "items_per_gpu": n_items // world,
+            "ep_sweeps_mean": sweeps_mean, "ep_sweeps_hist_rank0": sweeps_hist, "items_ok": status_ok, "items_per_gpu": n_items // world,
             "batches_this_rank_per_step": units_run[0] / float(args.warmup + args.steps + e2e_steps + 1),
             "dealing": "one batch" if world == 1 else args.deal,
             "int8_slices": int(os.environ.get("AGPC_OZAKI", "7") or 0),
