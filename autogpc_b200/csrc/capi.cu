@@ -75,6 +75,7 @@ int agpc_create(int device, agpc_ctx** out) {
     const int v = atoi(e);
     c->oz_S = (v == 6 || v == 7) ? v : 0;
   }
+  if (const char* e = getenv("AGPC_OZ_MIN_N")) c->oz_min_np = atoi(e);
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // the look-ahead (panel) stream outranks the bulk updates
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||

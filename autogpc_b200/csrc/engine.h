@@ -16,6 +16,11 @@ struct agpc_ctx {
   int sm_count = 148;
   int jitter = 1;  // jitchol's jitter ladder on a failed factorisation (AGPC_JITTER=0 disables: failures stay NOT_PD)
   int oz_S = 7;  // digit slices of the int8 tensor-core GEMM path (ozaki.cu); 0 = FP64 DMMA kernel only.  AGPC_OZAKI=0|6|7
+  int oz_min_np = 1536;  // scoring path: padded matrix size from which the int8 path is used (AGPC_OZ_MIN_N).  Below it the
+                         // slicing passes cost more than the tensor core saves: 4096 models at n = 1024 run 8 % faster on the
+                         // FP64 DMMA kernel (0.75 s against 0.81 s), from n = 1536 on the int8 path wins by 20 % and more
+                         // (profiles/r02_summary.md section 3).  The building-block entry points are not affected.
+  int oz_slices(int np) const { return np >= oz_min_np ? oz_S : 0; }
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;  // look-ahead stream of potrf_blocked
   cudaEvent_t ev_panel = nullptr, ev_rest = nullptr;

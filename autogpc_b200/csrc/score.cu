@@ -441,13 +441,13 @@ int score_items_dev(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, const ag
 
   // chunking: consecutive items, as many as the arena budget allows at the padded size of the largest item
   const int np_all = (int)align_up((size_t)n_max, TILE);
-  const size_t per_item = per_item_bytes(np_all, ds.D, theta_stride, ctx->oz_S);
+  const size_t per_item = per_item_bytes(np_all, ds.D, theta_stride, ctx->oz_slices(np_all));
   const size_t budget = ctx->workspace_budget();
   int chunk_cap = (int)std::min<size_t>((size_t)n_items, std::max<size_t>(1, budget / per_item));
   chunk_cap = std::min(chunk_cap, 65535);  // the batch index is gridDim.y / gridDim.z of most launches
   if (per_item > budget) return fail(ctx, AGPC_E_NOMEM, "score_batch: one item does not fit the workspace budget");
   Chunk probe;
-  const size_t need = probe.carve(nullptr, chunk_cap, np_all, ds.D, theta_stride, false, ctx->oz_S);
+  const size_t need = probe.carve(nullptr, chunk_cap, np_all, ds.D, theta_stride, false, ctx->oz_slices(np_all));
   int rc = ctx->ensure_arena(need);
   if (rc) return rc;
 
@@ -464,7 +464,7 @@ int score_items_dev(agpc_ctx* ctx, int32_t dataset_id, int32_t n_items, const ag
     off[nb] = off[nb - 1] + n_of[nb - 1];
     np = (int)align_up((size_t)np, TILE);
     Chunk c;
-    c.carve((char*)ctx->arena, nb, np, ds.D, theta_stride, false, ctx->oz_S);
+    c.carve((char*)ctx->arena, nb, np, ds.D, theta_stride, false, ctx->oz_slices(np_all));
     if (c.make_maps()) return fail(ctx, AGPC_E_CUDA, "cuTensorMapEncodeTiled failed");
     const int tb = 256;
     dim3 gvec((np + tb - 1) / tb, nb);

@@ -356,7 +356,16 @@ def test_chunked_batches_equal_one_chunk(engine):
     one = engine.score_batch(did, progs, thetas, rows, damping=0.0)
     engine.dataset_free(did)
     per_item = 5 * 384 * 384 * 8 + 64 * 1024          # five padded n x n matrices + vectors
-    small = Engine(0, workspace_limit_bytes=int(3.5 * per_item))
+    saved = {k: os.environ.get(k) for k in engine.test_env}
+    os.environ.update(engine.test_env)          # same kernel-selection rule as the fixture's engine
+    try:
+        small = Engine(0, workspace_limit_bytes=int(3.5 * per_item))
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     try:
         did2 = small.dataset(X, y)
         many = small.score_batch(did2, progs, thetas, rows, damping=0.0)

@@ -138,10 +138,17 @@ elif mode == "small":
     r = eng.score_batch(did, progs, thetas, rows)
     dt = time.time() - t0
     prof = eng.profile_read()
+    eng.profile_enable(False)
+    rep = []
+    for _ in range(3):   # steady state: arena and staging allocated, no per-launch events
+        t0 = time.time()
+        eng.score_batch(did, progs, thetas, rows)
+        rep.append(time.time() - t0)
     g = prof["gemm"]
     print(json.dumps({"config": "configs[4] batched small: %d models (%d structures x %d restarts) at n=%d"
                                 % (len(progs), len(pool), n_restart, n),
-                      "seconds": dt, "models_per_s": len(progs) / dt, "ep_sweeps_mean": float(np.mean(r["sweeps"])),
+                      "seconds": dt, "models_per_s": len(progs) / dt, "seconds_repeat": rep,
+                      "models_per_s_steady": len(progs) / min(rep), "ep_sweeps_mean": float(np.mean(r["sweeps"])),
                       "status_ok": int(np.sum(r["status"] == 0)),
                       "not_ok": [{"item": int(i), "structure": pool[i // n_restart].kernel.structure(), "status": int(r["status"][i]),
                                   "sweeps": int(r["sweeps"][i]), "nlml": float(r["nlml"][i]),
