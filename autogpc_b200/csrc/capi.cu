@@ -114,6 +114,8 @@ int agpc_destroy(agpc_ctx* ctx) {
   cudaStreamSynchronize(ctx->side);
   cudaEventDestroy(ctx->ev_panel);
   cudaEventDestroy(ctx->ev_rest);
+  agpc::oz_release_stream(ctx->side);
+  agpc::oz_release_stream(ctx->stream);
   cudaStreamDestroy(ctx->side);
   cudaStreamDestroy(ctx->stream);
   delete ctx;

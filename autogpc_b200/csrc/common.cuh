@@ -160,6 +160,7 @@ struct OzSliceArgs {
 struct Launch;
 cudaError_t oz_gemm_launch(const Launch& L, const OzGemmArgs& a, int tiles128, int groups, int batch, int S);
 cudaError_t oz_slice_launch(const Launch& L, const OzSliceArgs& a, int row_blocks, int groups, int batch, int S);
+void oz_release_stream(cudaStream_t st);  // persistent kernel's per-stream tile counter: give it back before destroying st
 // scale[b][i] = 2^(e_i - 8) with 2^e_i > 4 sqrt(A_ii): |L_ik| <= sqrt(A_ii) for every entry of row i of the Cholesky factor
 cudaError_t oz_row_bound_launch(const Launch& L, const double* A, long long ld, long long a_batch, int n, int batch,
                                 double* scale, long long sc_batch, const int* active);

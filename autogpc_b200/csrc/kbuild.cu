@@ -1146,6 +1146,310 @@ grad_contract_kernel(const GradArgs a) {
   }
 }
 
+// ---- the same contraction, register micro-tiled (round 2) --------------------------------------------------------------
+// grad_contract_kernel above walks the kernel program once per PAIR and keeps its dk[] in a theta-indexed array, i.e. in
+// local memory: 337 instructions per pair, 0.09 of the HBM rate of the B^-1 tiles it reads.  Here a thread owns 2 x 4
+// pairs per pass (two passes per 64 x 64 tile, as build_K_tiled_kernel), the program is walked once per pass, and what
+// has to be summed over pairs is, per product term t, S0_t = sum w v_t (every variance: dk/dvar_p = v_t / var_p) and per
+// leaf one or two more sums (SE: sum w v r^2; PER: sum w v sin cos r and sum w v sin^2; LIN: sum w v/(factor) d factor/dc).
+// Each is reduced over the warp as soon as its 8 pairs are done and added by lane 0 into the warp's own row of a
+// shared [8 warps][theta] table: no atomics, fixed order, so the result is deterministic.  PER leaves use the same
+// per-tile sincospi tables as the K build.
+__global__ void __launch_bounds__(KT_THREADS, 2)
+grad_contract_tiled_kernel(const GradArgs a) {
+  const int b = blockIdx.y;
+  if (a.active != nullptr && a.active[b] == 0) return;
+  extern __shared__ double smem[];
+  __shared__ ProgShared P;
+  __shared__ double exp_tab[32];
+  __shared__ double th_s[AGPC_MAX_THETA];
+  __shared__ int per_slot[AGPC_MAX_LEAVES];
+  __shared__ int per_leaf[KT_PER];
+  __shared__ int n_per_s;
+  if (threadIdx.x < 32) exp_tab[threadIdx.x] = EXP_T[threadIdx.x];
+  const int D = a.D;
+  double* xr = smem;                          // [D][KT]
+  double* xc = smem + D * KT;                 // [D][KT]
+  double* trg_r = xc + D * KT;                // [KT_PER][2][KT]  (sin, cos)(pi x_i / T)
+  double* trg_c = trg_r + KT_PER * 2 * KT;    // [KT_PER][2][KT]
+  double* red = trg_c + KT_PER * 2 * KT;      // [8 warps][AGPC_MAX_THETA]
+  const int nt = a.np / KT;
+  int ti, tj;
+  if (a.mode == 0) {
+    const int t = blockIdx.x;
+    ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while (ti * (ti + 1) / 2 > t) --ti;
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    tj = t - ti * (ti + 1) / 2;
+  } else {
+    ti = blockIdx.x / nt;
+    tj = blockIdx.x % nt;
+  }
+  const int n = a.n_of ? a.n_of[b] : a.n_fixed;
+  const int row0 = ti * KT, col0 = tj * KT;
+  const double* Xf = a.Xf + (long long)b * a.np * D;
+  load_x_tiles_async<KT>(xr, xc, Xf, Xf, row0, col0, a.np, a.np, D);
+  load_program_raw(P, th_s, a.progs[b], a.theta + (long long)b * a.theta_stride, a.theta_stride);
+  for (int i = threadIdx.x; i < 8 * AGPC_MAX_THETA; i += KT_THREADS) red[i] = 0.0;
+  cp_async_wait_all();
+  __syncthreads();
+  derive_leaf_consts(P, th_s);
+  if (threadIdx.x == KT_THREADS - 1) {
+    int np = 0;
+    for (int l = 0; l < P.n_leaves; ++l) {
+      const bool tab = P.leaf[l].type == AGPC_LEAF_PER && np < KT_PER;
+      per_slot[l] = tab ? np : -1;
+      if (tab) per_leaf[np++] = l;
+    }
+    n_per_s = np;
+  }
+  __syncthreads();
+  const int n_per = n_per_s;
+  for (int idx = threadIdx.x; idx < 2 * n_per * KT; idx += KT_THREADS) {
+    const int side = idx / (n_per * KT), rem = idx % (n_per * KT);
+    const int sl = rem >> 6, r = rem & (KT - 1);
+    const LeafConst& lc = P.leaf[per_leaf[sl]];
+    double sn, cs;
+    sincospi((side ? xc : xr)[lc.dim * KT + r] * lc.a, &sn, &cs);
+    double* dst = side ? trg_c : trg_r;
+    dst[(sl * 2 + 0) * KT + r] = sn;
+    dst[(sl * 2 + 1) * KT + r] = cs;
+  }
+  __syncthreads();
+
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* myred = red + warp * AGPC_MAX_THETA;
+  const double* Gb = a.G + (long long)b * a.g_batch;
+  const double* al = a.alpha ? a.alpha + (long long)b * a.np : nullptr;
+  const double* sv = a.s ? a.s + (long long)b * a.np : nullptr;
+  const double* ru = a.ru ? a.ru + (long long)b * a.np : nullptr;
+  const double* rv = a.rv ? a.rv + (long long)b * a.np : nullptr;
+  auto warp_add = [&](int slot, double v) {   // sum over the warp, lane 0 accumulates into the warp's own row
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) myred[slot] += v;
+  };
+
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    // ---- weights of the 2 x 4 pairs of this pass ----
+    double w[2][4];
+    int gi[2], gj[4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) gi[r] = row0 + ty + 16 * (2 * h + r);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) gj[c] = col0 + tx + 16 * c;
+    // every index lies inside the padded matrix, so all loads are issued unconditionally and together (one memory round
+    // trip per pass; a branch per pair made them 8 dependent round trips: 50 % of the first version's stall samples) and
+    // the pairs outside the valid triangle are masked afterwards
+    double g[2][4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) g[r][c] = Gb[(long long)gi[r] * a.ld + gj[c]];
+    if (a.mode == 0) {
+      double ali[2], svi[2], alj[4], svj[4], rui[2] = {0.0, 0.0}, rvi[2] = {0.0, 0.0}, ruj[4] = {0.0, 0.0, 0.0, 0.0}, rvj[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        ali[r] = al[gi[r]];
+        svi[r] = sv[gi[r]];
+        if (ru != nullptr) { rui[r] = ru[gi[r]]; rvi[r] = rv[gi[r]]; }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        alj[c] = al[gj[c]];
+        svj[c] = sv[gj[c]];
+        if (ru != nullptr) { ruj[c] = ru[gj[c]]; rvj[c] = rv[gj[c]]; }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          double wv = 0.5 * (ali[r] * alj[c] - svi[r] * g[r][c] * svj[c]);
+          if (ru != nullptr) wv += 0.5 * (rui[r] * rvj[c] + ruj[c] * rvi[r]);
+          if (gj[c] < gi[r]) wv *= 2.0;
+          const bool ok = gi[r] < n && gj[c] < n && gj[c] <= gi[r];
+          w[r][c] = ok ? wv : 0.0;
+        }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) w[r][c] = (gi[r] < n && gj[c] < n) ? g[r][c] : 0.0;
+    }
+    const int n_terms = P.n_terms;
+    for (int t = 0; t < n_terms; ++t) {
+      const int len = P.term_len[t];
+      double arg[2][4];
+      double mr[2] = {1.0, 1.0}, mc[4] = {1.0, 1.0, 1.0, 1.0};
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) arg[r][c] = 0.0;
+      double scale = 1.0;
+      bool has_exp = false;
+      // ---- pass A over the leaves: the term's value ----
+      for (int p = 0; p < len; ++p) {
+        const int leaf_id = P.term_leaf[t][p];
+        const LeafConst& lc = P.leaf[leaf_id];
+        scale *= lc.var;
+        if (lc.type == AGPC_LEAF_CONST) continue;
+        if (lc.type == AGPC_LEAF_PER && per_slot[leaf_id] >= 0) {
+          has_exp = true;
+          const double* tr = trg_r + per_slot[leaf_id] * 2 * KT;
+          const double* tc = trg_c + per_slot[leaf_id] * 2 * KT;
+          const double hb = 0.5 * lc.b;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const double sr = tr[ty + 16 * (2 * h + r)], cr = tr[KT + ty + 16 * (2 * h + r)];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const double sn = sr * tc[KT + tx + 16 * c] - cr * tc[tx + 16 * c];
+              arg[r][c] -= hb * sn * sn;
+            }
+          }
+          continue;
+        }
+        double xi[2], xj[4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) xi[r] = xr[lc.dim * KT + ty + 16 * (2 * h + r)];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) xj[c] = xc[lc.dim * KT + tx + 16 * c];
+        if (lc.type == AGPC_LEAF_SE) {
+          has_exp = true;
+          const double ha = 0.5 * lc.a;
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const double d = xi[r] - xj[c];
+              arg[r][c] -= ha * d * d;
+            }
+        } else if (lc.type == AGPC_LEAF_PER) {
+          has_exp = true;
+          const double wq = M_PI * lc.a, hb = 0.5 * lc.b;
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const double sn = sin(wq * (xi[r] - xj[c]));
+              arg[r][c] -= hb * sn * sn;
+            }
+        } else {  // LIN
+#pragma unroll
+          for (int r = 0; r < 2; ++r) mr[r] *= xi[r] - lc.a;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) mc[c] *= xj[c] - lc.a;
+        }
+      }
+      if (has_exp) exp_nonpos_n<8>(reinterpret_cast<double(&)[8]>(arg), exp_tab);
+      // arg <- w * (scale * exp part): what every derivative of this term starts from (the LIN factors are separable)
+      double s0 = 0.0;
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const double e = has_exp ? arg[r][c] : 1.0;
+          arg[r][c] = w[r][c] * scale * e;
+          s0 = fma(arg[r][c], mr[r] * mc[c], s0);
+        }
+      // S0_t = sum w v_t, booked to every variance of the term
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      // ---- pass B over the leaves: the per-leaf sums ----
+      for (int p = 0; p < len; ++p) {
+        const int leaf_id = P.term_leaf[t][p];
+        const LeafConst& lc = P.leaf[leaf_id];
+        const int o = P.leaf_off[leaf_id];
+        if (lane == 0) myred[o] += s0 / lc.var;
+        if (lc.type == AGPC_LEAF_CONST) continue;
+        if (lc.type == AGPC_LEAF_PER && per_slot[leaf_id] >= 0) {
+          const double* tr = trg_r + per_slot[leaf_id] * 2 * KT;
+          const double* tc = trg_c + per_slot[leaf_id] * 2 * KT;
+          const double* xrd = xr + lc.dim * KT;
+          const double* xcd = xc + lc.dim * KT;
+          double sT = 0.0, sL = 0.0;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int lr = ty + 16 * (2 * h + r);
+            const double sr = tr[lr], cr = tr[KT + lr], xi = xrd[lr];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int lc4 = tx + 16 * c;
+              const double sc = tc[lc4], cc = tc[KT + lc4];
+              const double sn = sr * cc - cr * sc, cs = cr * cc + sr * sc;
+              const double wv = arg[r][c] * (mr[r] * mc[c]);
+              sT = fma(wv * sn * cs, xi - xcd[lc4], sT);
+              sL = fma(wv * sn, sn, sL);
+            }
+          }
+          // dk/dT = k sin b cos b (b / T) / l^2 with b = pi r / T;  dk/dl = k sin^2 b / l^3
+          warp_add(o + 1, sT * (M_PI * lc.a * lc.a) * lc.b);
+          warp_add(o + 2, sL * lc.d);
+          continue;
+        }
+        double xi[2], xj[4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) xi[r] = xr[lc.dim * KT + ty + 16 * (2 * h + r)];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) xj[c] = xc[lc.dim * KT + tx + 16 * c];
+        if (lc.type == AGPC_LEAF_SE) {
+          double sL = 0.0;
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const double d = xi[r] - xj[c];
+              sL = fma(arg[r][c] * (mr[r] * mc[c]), d * d, sL);
+            }
+          warp_add(o + 1, sL * lc.b);   // dk/dl = k r^2 / l^3
+        } else if (lc.type == AGPC_LEAF_PER) {
+          const double wq = M_PI * lc.a;
+          double sT = 0.0, sL = 0.0;
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              double sn, cs;
+              const double d = xi[r] - xj[c];
+              sincos(wq * d, &sn, &cs);
+              const double wv = arg[r][c] * (mr[r] * mc[c]);
+              sT = fma(wv * sn * cs, d, sT);
+              sL = fma(wv * sn, sn, sL);
+            }
+          warp_add(o + 1, sT * (M_PI * lc.a * lc.a) * lc.b);
+          warp_add(o + 2, sL * lc.d);
+        } else {  // LIN: d/dc of var (x_i - c)(x_j - c) = -var (x_i + x_j - 2c), times the term without this leaf's own factor
+          double exr[2] = {1.0, 1.0}, exc[4] = {1.0, 1.0, 1.0, 1.0};
+          for (int q = 0; q < len; ++q) {
+            if (q == p) continue;
+            const LeafConst& lq = P.leaf[P.term_leaf[t][q]];
+            if (lq.type != AGPC_LEAF_LIN) continue;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) exr[r] *= xr[lq.dim * KT + ty + 16 * (2 * h + r)] - lq.a;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) exc[c] *= xc[lq.dim * KT + tx + 16 * c] - lq.a;
+          }
+          double sC = 0.0;
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              sC = fma(arg[r][c] * (exr[r] * exc[c]), -(xi[r] + xj[c] - 2.0 * lc.a), sC);
+          warp_add(o + 1, sC);   // (arg already carries every variance of the term, this leaf's included)
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < P.n_theta) {
+    double v = 0.0;
+    for (int w8 = 0; w8 < 8; ++w8) v += red[w8 * AGPC_MAX_THETA + threadIdx.x];
+    a.partial[((long long)b * a.tiles_per_item + blockIdx.x) * AGPC_MAX_THETA + threadIdx.x] = v;
+  }
+}
+
 // grad[b][q] = scale * sum_tiles partial[b][tile][q]   (one warp per (b, q), fixed summation order)
 __global__ void grad_finalize_kernel(const double* __restrict__ partial, int tiles, const agpc_program* progs,
                                      double scale, double* __restrict__ grad, int grad_stride,
@@ -1166,9 +1470,21 @@ cudaError_t grad_contract_launch(const Launch& L, const GradArgs& a, int batch, 
   ProfScope prof_scope(L, CLS_GRAD);
   const int nt = a.np / GT;
   const int tiles = a.mode == 0 ? nt * (nt + 1) / 2 : nt * nt;
-  const size_t smem = sizeof(double) * (2 * a.D * GT + 8 * AGPC_MAX_THETA);
   dim3 grid(tiles, batch);
-  grad_contract_kernel<<<grid, 256, smem, L.stream>>>(a);
+  static const bool generic = getenv("AGPC_GRAD_GENERIC") && atoi(getenv("AGPC_GRAD_GENERIC")) != 0;   // round-1 kernel, for A/B
+  if (generic) {
+    const size_t smem = sizeof(double) * (2 * a.D * GT + 8 * AGPC_MAX_THETA);
+    grad_contract_kernel<<<grid, 256, smem, L.stream>>>(a);
+  } else {
+    const size_t smem = sizeof(double) * (2 * (size_t)a.D * KT + 2 * KT_PER * 2 * KT + 8 * AGPC_MAX_THETA);
+    bool& configured = func_attr_done(__LINE__);
+    if (!configured || smem > 48 * 1024) {
+      AGPC_CUDA_TRY(cudaFuncSetAttribute(grad_contract_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(smem > 100 * 1024 ? smem : 100 * 1024)));
+      configured = true;
+    }
+    grad_contract_tiled_kernel<<<grid, KT_THREADS, smem, L.stream>>>(a);
+  }
   L.bump();
   AGPC_CUDA_TRY(cudaGetLastError());
   grad_finalize_kernel<<<dim3(batch, AGPC_MAX_THETA), 32, 0, L.stream>>>(a.partial, tiles, a.progs, scale, grad, grad_stride,

@@ -1151,36 +1151,48 @@ static cudaError_t oz_gemm128_launch_t(const Launch& L, const OzGemmArgs& a, int
 
 // Tile counters of the persistent kernel: {next tile, CTAs finished} per stream.  Launches on one stream run one after the
 // other and the last CTA of each re-arms its pair, so one pair per (device, stream) is enough.
-constexpr int OZP_STREAM_SLOTS = 64;
+constexpr int OZP_STREAM_SLOTS = 1024;
 __device__ int oz_tile_counters[OZP_STREAM_SLOTS][2];
 
+namespace {
+struct OzpSlot {
+  int dev;
+  cudaStream_t st;
+  bool used;
+};
+OzpSlot ozp_slots[OZP_STREAM_SLOTS];
+int* ozp_base[64] = {};
+std::mutex ozp_mu;
+}  // namespace
+
 static int* ozp_counter_for(cudaStream_t st) {
-  struct Slot {
-    int dev;
-    cudaStream_t st;
-  };
-  static Slot slots[OZP_STREAM_SLOTS];
-  static int used = 0;
-  static int* base[64] = {};
-  static std::mutex mu;
-  std::lock_guard<std::mutex> lock(mu);
+  std::lock_guard<std::mutex> lock(ozp_mu);
   int dev = 0;
   cudaGetDevice(&dev);
-  if (base[dev & 63] == nullptr) {
+  if (ozp_base[dev & 63] == nullptr) {
     void* p = nullptr;
     if (cudaGetSymbolAddress(&p, oz_tile_counters) != cudaSuccess) return nullptr;
     if (cudaMemset(p, 0, sizeof(int) * 2 * OZP_STREAM_SLOTS) != cudaSuccess) return nullptr;
-    base[dev & 63] = static_cast<int*>(p);
+    ozp_base[dev & 63] = static_cast<int*>(p);
   }
-  int per_dev = 0;
-  for (int i = 0; i < used; ++i) {
-    if (slots[i].dev != dev) continue;
-    if (slots[i].st == st) return base[dev & 63] + 2 * per_dev;
-    ++per_dev;
+  int free_slot = -1;
+  for (int i = 0; i < OZP_STREAM_SLOTS; ++i) {
+    if (ozp_slots[i].used && ozp_slots[i].dev == dev && ozp_slots[i].st == st) return ozp_base[dev & 63] + 2 * i;
+    if (!ozp_slots[i].used && free_slot < 0) free_slot = i;
   }
-  if (used == OZP_STREAM_SLOTS || per_dev == OZP_STREAM_SLOTS) return nullptr;
-  slots[used++] = Slot{dev, st};
-  return base[dev & 63] + 2 * per_dev;
+  if (free_slot < 0) return nullptr;  // table full: the caller falls back to the one-tile-per-CTA kernel
+  ozp_slots[free_slot] = OzpSlot{dev, st, true};
+  return ozp_base[dev & 63] + 2 * free_slot;
+}
+
+// A stream that is about to be destroyed gives its counter pair back (agpc_destroy; the stream must be idle: its last
+// launch re-armed the pair to zero).
+void oz_release_stream(cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(ozp_mu);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (int i = 0; i < OZP_STREAM_SLOTS; ++i)
+    if (ozp_slots[i].used && ozp_slots[i].dev == dev && ozp_slots[i].st == st) ozp_slots[i].used = false;
 }
 
 template <int S>
