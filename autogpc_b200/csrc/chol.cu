@@ -306,14 +306,15 @@ constexpr int THIN_CTA_LIMIT = 160;
 // the operands are re-sliced from their FP64 source right before each product (row scale = exact row maximum over the
 // K range that product uses), SA serves the A operand and SB the B operand.
 static inline bool oz_on(const MatSet& ms) { return ms.oz_S > 0 && ms.SA != nullptr; }
-static inline OzOperand oz_operand(const MatSet& ms, bool second) {
-  return OzOperand{second ? ms.SB : ms.SA, second ? ms.scB : ms.scA, (long long)ms.oz_S * ms.np * ms.np, (long long)ms.np,
-                   ms.np / OZ_KB};
+// which: 0 = SA, 1 = SB, 2 = SC
+static inline OzOperand oz_operand(const MatSet& ms, int which) {
+  return OzOperand{which == 2 ? ms.SC : which ? ms.SB : ms.SA, which == 2 ? ms.scC : which ? ms.scB : ms.scA,
+                   (long long)ms.oz_S * ms.np * ms.np, (long long)ms.np, ms.np / OZ_KB};
 }
-static inline OzSliceArgs oz_slice_args(const MatSet& ms, const double* X, bool second, const int* active) {
+static inline OzSliceArgs oz_slice_args(const MatSet& ms, const double* X, int which, const int* active) {
   OzSliceArgs a{};
   a.X = X; a.ld = ms.np; a.x_batch = ms.stride;
-  a.S = second ? ms.SB : ms.SA; a.scale = second ? ms.scB : ms.scA;
+  a.S = which == 2 ? ms.SC : which ? ms.SB : ms.SA; a.scale = which == 2 ? ms.scC : which ? ms.scB : ms.scA;
   a.s_batch = (long long)ms.oz_S * ms.np * ms.np; a.sc_batch = ms.np; a.nkc = ms.np / OZ_KB;
   a.active = active;
   return a;
@@ -325,7 +326,7 @@ constexpr int OZ_TRTRI_MIN_H = 2;      // trtri levels below this half-size (K =
 static cudaError_t potrf_slice_panel(const Launch& L, const MatSet& ms, const int* active, int k0, int kb, int r0) {
   const int nblk = ms.np / TILE;
   if (nblk - r0 <= 0) return cudaSuccess;
-  OzSliceArgs a = oz_slice_args(ms, ms.A, false, active);
+  OzSliceArgs a = oz_slice_args(ms, ms.A, 0, active);
   a.row0 = r0 * TILE; a.col0 = k0 * TILE; a.row_blocks = nblk - r0; a.col_chunks = kb * OZ_CPB;
   a.fixed_scale = ms.scA;  // row scales from |L_ik| <= sqrt(B_ii) (oz_row_bound_launch): every panel of L shares them
   L.add_work(CLS_SLICE, 8.0 * (double)(nblk - r0) * TILE * kb * TILE * L.work_items);
@@ -345,7 +346,7 @@ static cudaError_t potrf_update_oz(const Launch& L, const MatSet& ms, const int*
   const int rows = nblk - k0;
   if (rows <= 0 || kcb <= 0) return cudaSuccess;
   OzGemmArgs z{};
-  z.A = oz_operand(ms, false); z.B = z.A;
+  z.A = oz_operand(ms, 0); z.B = z.A;
   z.C = ms.A; z.Ct = nullptr; z.ldc = ms.np; z.c_batch = ms.stride;
   z.a_row0 = k0 * TILE; z.a_col0 = kc0 * TILE; z.b_row0 = k0 * TILE; z.b_col0 = kc0 * TILE;
   z.c_row0 = k0 * TILE; z.c_col0 = k0 * TILE;
@@ -365,6 +366,7 @@ static cudaError_t potrf_update_oz(const Launch& L, const MatSet& ms, const int*
 // K = 512) on the chain itself.
 //   hi:  part2(j) [after part1(j)] | panels(j) | slice(j) | part2(j+1) ...
 //   lo:  part1(j+1) [after slice(j-1)]                     | part1(j+2) ...
+static int potrf_outer_oz(int nblk);
 static cudaError_t potrf_blocked_oz(const Launch& L, const MatSet& ms, const int* active, int* info) {
   const int nblk = ms.np / TILE;
   static const int ob_env = getenv("AGPC_POTRF_OUTER") ? atoi(getenv("AGPC_POTRF_OUTER")) : 0;
@@ -373,7 +375,8 @@ static cudaError_t potrf_blocked_oz(const Launch& L, const MatSet& ms, const int
   // launches beside the panel chain: n = 16384 28.1 ms against 30.2).  A function of n ONLY: the blocking fixes the
   // summation order, and results must not depend on how many other matrices share the batch
   // (tests/test_gpu_parity.py::test_chunked_batches_equal_one_chunk).  profiles/r02_summary.md section 7
-  const int OB = ob_env > 0 ? ob_env : (nblk < 96 ? 2 : POTRF_OUTER);
+  const int OB = potrf_outer_oz(nblk);
+  (void)ob_env;
   AGPC_CUDA_TRY(oz_row_bound_launch(L, ms.A, ms.np, ms.stride, ms.np, ms.batch, ms.scA, ms.np, active));
   const bool lookahead = L.side != nullptr && nblk > 2 * OB;
   if (!lookahead) {
@@ -421,6 +424,11 @@ static cudaError_t potrf_blocked_oz(const Launch& L, const MatSet& ms, const int
   AGPC_CUDA_TRY(cudaEventRecord(L.ev_panel, H.stream));  // join: the caller's stream continues after the chain
   AGPC_CUDA_TRY(cudaStreamWaitEvent(L.stream, L.ev_panel, 0));
   return cudaSuccess;
+}
+
+static int potrf_outer_oz(int nblk) {
+  static const int ob_env = getenv("AGPC_POTRF_OUTER") ? atoi(getenv("AGPC_POTRF_OUTER")) : 0;
+  return ob_env > 0 ? ob_env : (nblk < 96 ? 2 : POTRF_OUTER);
 }
 
 // panels k0 .. k0 + kb of one outer block: in-block left-looking update, diagonal block, panel solve
@@ -485,7 +493,7 @@ static cudaError_t potrf_trailing(const Launch& L, const MatSet& ms, const int* 
   if (rows <= 0 || ncols == 0) return cudaSuccess;
   if (oz_on(ms)) {  // the panel was sliced into SA by potrf_slice_panel
     OzGemmArgs z{};
-    z.A = oz_operand(ms, false); z.B = z.A;
+    z.A = oz_operand(ms, 0); z.B = z.A;
     z.C = ms.A; z.Ct = nullptr; z.ldc = ms.np; z.c_batch = ms.stride;
     z.a_row0 = r0 * TILE; z.a_col0 = k0 * TILE; z.b_row0 = r0 * TILE; z.b_col0 = k0 * TILE;
     z.c_row0 = r0 * TILE; z.c_col0 = r0 * TILE;
@@ -584,23 +592,34 @@ cudaError_t trtri_blocked(const Launch& L, const MatSet& ms, const int* active) 
   L.add_work(CLS_GEMM_TRTRI, (double)L.work_items * wn * wn * wn / 3.0);  // dtrtri
   Launch Lt = L;
   Lt.gemm_cls = CLS_GEMM_TRTRI;
+  static const bool right_looking = getenv("AGPC_OZ_RIGHT") && atoi(getenv("AGPC_OZ_RIGHT")) != 0;
+  static const bool keep_env = !(getenv("AGPC_OZ_KEEP_L") && atoi(getenv("AGPC_OZ_KEEP_L")) == 0);
+  const bool keep_L = oz_on(ms) && ms.SC != nullptr && !right_looking && keep_env;
+  const int OBp = potrf_outer_oz(nblk);
   for (int h = 1; h < nblk; h *= 2) {
     const int G = 2 * h;
     const int groups = (nblk + G - 1) / G;
     if (oz_on(ms) && h >= OZ_TRTRI_MIN_H) {
       const double blk = (double)TILE * TILE * 8.0 * Lt.work_items;
       // step 1: T[left rows, right cols] = U11 * L21^T  (U11 upper triangular: K from the tile row on)
-      OzSliceArgs su = oz_slice_args(ms, ms.U, false, active);
+      // L21 (rows of the right half, columns of the left half) lies below the outer blocks of its columns whenever h is a
+      // multiple of the potrf outer block: the left-looking potrf has already sliced it into SA (static row scales), and
+      // with a third image for trtri's own A operands those slices survive -- a third of this level's slicing traffic
+      const bool l_kept = keep_L && h % OBp == 0;
+      const int wa = keep_L ? 2 : 0;   // image of the A operands (U11, M22)
+      OzSliceArgs su = oz_slice_args(ms, ms.U, wa, active);
       su.row0 = 0; su.col0 = 0; su.row_blocks = h; su.col_chunks = h * OZ_CPB; su.tri = 2;
       su.grp_blocks = G; su.half_blocks = h; su.nblk = nblk; su.need_h2 = 1;
       AGPC_CUDA_TRY(oz_slice_launch(Lt, su, h, groups, ms.batch, ms.oz_S));
-      OzSliceArgs sl = oz_slice_args(ms, ms.A, true, active);
-      sl.row0 = h * TILE; sl.col0 = 0; sl.rows_kind = EXT_H2; sl.col_chunks = h * OZ_CPB;
-      sl.grp_blocks = G; sl.half_blocks = h; sl.nblk = nblk; sl.need_h2 = 1;
-      AGPC_CUDA_TRY(oz_slice_launch(Lt, sl, h, groups, ms.batch, ms.oz_S));
-      Lt.add_work(CLS_SLICE, blk * 1.5 * h * h * groups);
+      if (!l_kept) {
+        OzSliceArgs sl = oz_slice_args(ms, ms.A, 1, active);
+        sl.row0 = h * TILE; sl.col0 = 0; sl.rows_kind = EXT_H2; sl.col_chunks = h * OZ_CPB;
+        sl.grp_blocks = G; sl.half_blocks = h; sl.nblk = nblk; sl.need_h2 = 1;
+        AGPC_CUDA_TRY(oz_slice_launch(Lt, sl, h, groups, ms.batch, ms.oz_S));
+      }
+      Lt.add_work(CLS_SLICE, blk * (l_kept ? 0.5 : 1.5) * h * h * groups);
       OzGemmArgs a{};
-      a.A = oz_operand(ms, false); a.B = oz_operand(ms, true);
+      a.A = oz_operand(ms, wa); a.B = oz_operand(ms, l_kept ? 0 : 1);
       a.C = ms.T; a.Ct = nullptr; a.ldc = ms.np; a.c_batch = ms.stride;
       a.a_row0 = 0; a.a_col0 = 0; a.b_row0 = h * TILE; a.b_col0 = 0; a.c_row0 = 0; a.c_col0 = h * TILE;
       a.m_tiles = h; a.n_tiles = 0; a.k_chunks = h * OZ_CPB;
@@ -609,17 +628,17 @@ cudaError_t trtri_blocked(const Launch& L, const MatSet& ms, const int* active) 
       a.k_rule = KRULE_BEGIN_AT_ROW; a.alpha = 1.0; a.beta = 0.0; a.active = active;
       AGPC_CUDA_TRY(oz_gemm_launch(Lt, a, h * h, groups, ms.batch, ms.oz_S));
       // step 2: M21 = -M22 * T^T ; U12 = M21^T  (M22 lower triangular: K up to the tile row)
-      OzSliceArgs sm = oz_slice_args(ms, ms.M, false, active);
+      OzSliceArgs sm = oz_slice_args(ms, ms.M, wa, active);
       sm.row0 = h * TILE; sm.col0 = h * TILE; sm.rows_kind = EXT_H2; sm.cols_kind = EXT_H2; sm.tri = 1;
       sm.grp_blocks = G; sm.half_blocks = h; sm.nblk = nblk; sm.need_h2 = 1;
       AGPC_CUDA_TRY(oz_slice_launch(Lt, sm, h, groups, ms.batch, ms.oz_S));
-      OzSliceArgs st = oz_slice_args(ms, ms.T, true, active);
+      OzSliceArgs st = oz_slice_args(ms, ms.T, 1, active);
       st.row0 = 0; st.col0 = h * TILE; st.row_blocks = h; st.cols_kind = EXT_H2;
       st.grp_blocks = G; st.half_blocks = h; st.nblk = nblk; st.need_h2 = 1;
       AGPC_CUDA_TRY(oz_slice_launch(Lt, st, h, groups, ms.batch, ms.oz_S));
       Lt.add_work(CLS_SLICE, blk * 1.5 * h * h * groups);
       OzGemmArgs c{};
-      c.A = oz_operand(ms, false); c.B = oz_operand(ms, true);
+      c.A = oz_operand(ms, wa); c.B = oz_operand(ms, 1);
       c.C = ms.M; c.Ct = ms.U; c.ldc = ms.np; c.c_batch = ms.stride;
       c.a_row0 = h * TILE; c.a_col0 = h * TILE; c.b_row0 = 0; c.b_col0 = h * TILE;
       c.c_row0 = h * TILE; c.c_col0 = 0; c.ct_row0 = 0; c.ct_col0 = h * TILE;
@@ -665,12 +684,12 @@ cudaError_t lauum_blocked(const Launch& L, const MatSet& ms, double* dst, const 
   Launch Ll = L;
   Ll.gemm_cls = CLS_GEMM_LAUUM;
   if (oz_on(ms)) {
-    OzSliceArgs su = oz_slice_args(ms, ms.U, false, active);
+    OzSliceArgs su = oz_slice_args(ms, ms.U, 0, active);
     su.row_blocks = nblk; su.col_chunks = nblk * OZ_CPB; su.tri = 2;
     Ll.add_work(CLS_SLICE, 4.0 * wn * wn * Ll.work_items);
     AGPC_CUDA_TRY(oz_slice_launch(Ll, su, nblk, 1, ms.batch, ms.oz_S));
     OzGemmArgs z{};
-    z.A = oz_operand(ms, false); z.B = z.A;
+    z.A = oz_operand(ms, 0); z.B = z.A;
     z.C = dst; z.Ct = nullptr; z.ldc = ms.np; z.c_batch = ms.stride;
     z.m_tiles = nblk; z.n_tiles = nblk; z.k_chunks = nblk * OZ_CPB;
     z.k_rule = KRULE_BEGIN_AT_ROW; z.lower_only = 1; z.alpha = 1.0; z.beta = 0.0; z.active = active;

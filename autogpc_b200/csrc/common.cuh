@@ -178,6 +178,10 @@ struct MatSet {
   int oz_S = 0;
   int8_t *SA = nullptr, *SB = nullptr;
   double *scA = nullptr, *scB = nullptr;
+  // optional third image: when present, trtri puts its A operands (U11, M22) here and takes L21 from the slices of L that
+  // the left-looking potrf left in SA (statically scaled) instead of slicing L a second time
+  int8_t* SC = nullptr;
+  double* scC = nullptr;
   CUtensorMap mapA, mapM, mapU, mapT;
   CUtensorMap mapA32, mapM32;  // 32-row boxes: B operands of the thin GEMM variant
 };

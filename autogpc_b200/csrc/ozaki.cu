@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzGemmA
 constexpr int OZP_RING = 4;      // tile records in flight between producer, MMA issuer and epilogue
 constexpr int OZS_EPI_WARPS = 16;
 constexpr int OZS_THREADS = 64 + 32 * OZS_EPI_WARPS;  // warp 0: producer, warp 1: TMEM owner + MMA issuer, warps 2-17: epilogue
-constexpr int OZP_MAX_BATCH = 1024;
+constexpr int OZP_MAX_BATCH = 4096;  // compact list of active items in shared memory (2 B each)
 struct OzTileRec {
   int b, a_row, b_row, a_kc, b_kc, n_iter;  // a_kc / b_kc: first K chunk in each operand's own columns; n_iter < 0: no more tiles
   int c_row, c_col, t_row, t_col;
