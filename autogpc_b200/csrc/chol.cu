@@ -369,14 +369,12 @@ static cudaError_t potrf_update_oz(const Launch& L, const MatSet& ms, const int*
 static int potrf_outer_oz(int nblk);
 static cudaError_t potrf_blocked_oz(const Launch& L, const MatSet& ms, const int* active, int* info) {
   const int nblk = ms.np / TILE;
-  static const int ob_env = getenv("AGPC_POTRF_OUTER") ? atoi(getenv("AGPC_POTRF_OUTER")) : 0;
   // panels per outer block of the left-looking form: 2 up to n = 12 k (the persistent int8 kernel makes K = 256 passes cheap
   // and fewer in-block updates stay on the FP64 pipe: -3 % at n = 6400 x 40, -4 % x 8), 4 above (one big matrix: fewer, larger
   // launches beside the panel chain: n = 16384 28.1 ms against 30.2).  A function of n ONLY: the blocking fixes the
   // summation order, and results must not depend on how many other matrices share the batch
   // (tests/test_gpu_parity.py::test_chunked_batches_equal_one_chunk).  profiles/r02_summary.md section 7
   const int OB = potrf_outer_oz(nblk);
-  (void)ob_env;
   AGPC_CUDA_TRY(oz_row_bound_launch(L, ms.A, ms.np, ms.stride, ms.np, ms.batch, ms.scA, ms.np, active));
   const bool lookahead = L.side != nullptr && nblk > 2 * OB;
   if (!lookahead) {

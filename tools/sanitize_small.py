@@ -1,6 +1,7 @@
 """Small end-to-end exercise of the int8 GEMM (persistent and one-tile forms), potrf / trtri / lauum on it, score_batch and
 the on-device optimiser, sized for compute-sanitizer (memcheck / racecheck / synccheck), run under gpurun:
-    compute-sanitizer --tool memcheck python tools/sanitize_small.py"""
+    compute-sanitizer --tool memcheck python tools/sanitize_small.py
+(compute-sanitizer is closed on the round-2 GPU pool; without it the script is a quick end-to-end check with asserts.)"""
 import ctypes
 import os
 import sys
