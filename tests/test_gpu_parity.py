@@ -1054,3 +1054,34 @@ def test_device_optimizer_keeps_search_selection(engine):
     names_d, scores_d = run(True)
     assert names_h == names_d, (names_h, names_d)
     assert np.allclose(scores_h, scores_d, rtol=1e-3), (scores_h, scores_d)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_evals", [1, 3, 7])
+def test_device_optimizer_stopping_rules_match_scipy(engine, max_evals):
+    """SciPy's maxfun semantics (the run stops at the first NEW iterate after more than maxfun evaluations, so it may
+    overshoot inside a line search) and its warnflag, reproduced by the device loop: same number of objective evaluations,
+    same warnflag, same final objective as the SciPy-stepped host driver under a tight budget."""
+    from autogpc_b200 import engine as eng_mod
+    from autogpc_b200 import gpy_compat as GPy
+    from autogpc_b200 import optim
+
+    X, y = synth(180, 2, 44)
+    eng_mod.set_default_engine(engine)
+    did = engine.dataset(X, y)
+    rows = [np.arange(150, dtype=np.int32), np.arange(20, 180, dtype=np.int32)]
+
+    def models():
+        ks = [GPy.kern.RBF(1, variance=2.0, lengthscale=0.3, active_dims=[0]),
+              GPy.kern.Add([GPy.kern.RBF(1, variance=0.5, lengthscale=1.7, active_dims=[1]), GPy.kern.Bias(2, variance=1.5)])]
+        return [GPy.models.GPClassification(kernel=k, engine=engine, _dataset=did, _rows=r, _infer=False) for k, r in zip(ks, rows)]
+
+    host, dev = models(), models()
+    optim.optimize_models(host, max_evals=max_evals, device=False)
+    optim.optimize_models(dev, max_evals=max_evals, device=True)
+    for h, d in zip(host, dev):
+        assert d.optimization_info["evals"] == h.optimization_info["evals"], (h.optimization_info, d.optimization_info)
+        assert d.optimization_info["warnflag"] == h.optimization_info["warnflag"], (h.optimization_info, d.optimization_info)
+        assert d._nlml == pytest.approx(h._nlml, rel=1e-9)
+        assert np.allclose(d.kern.param_array, h.kern.param_array, rtol=1e-7)
+    engine.dataset_free(did)
