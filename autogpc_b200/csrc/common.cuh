@@ -286,7 +286,9 @@ cudaError_t predict_prob_launch(const Launch& L, const double* mu_s, const doubl
 namespace agpc {
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device context: one "done" flag per (call site, device), so
 // a second Engine(device = k) in the same process configures its own context instead of failing at launch
-inline bool& func_attr_done(int site) {
+// (internal linkage on purpose: every translation unit gets its own table, so the call sites -- identified by their line
+// number -- of different files can never alias)
+static inline bool& func_attr_done(int site) {
   static bool done[64][2048] = {};
   int dev = 0;
   cudaGetDevice(&dev);
