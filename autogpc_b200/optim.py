@@ -187,7 +187,7 @@ def optimize_models(models, max_evals: int = 1000, warm_start: bool = True, devi
     AGPC_DEVICE_OPT=0 selects this host driver, which steps SciPy's own L-BFGS-B."""
     if not models:
         return
-    if device_optimizer_default(models) if device is None else device:
+    if (device_optimizer_default(models) if device is None else device) and warm_start:   # (the device loop always warm-starts EP)
         return optimize_models_device(models, max_evals=max_evals)
     engine = models[0].engine
     fails = [0] * len(models)
