@@ -594,6 +594,7 @@ cudaError_t trtri_blocked(const Launch& L, const MatSet& ms, const int* active) 
   static const bool keep_env = !(getenv("AGPC_OZ_KEEP_L") && atoi(getenv("AGPC_OZ_KEEP_L")) == 0);
   const bool keep_L = oz_on(ms) && ms.SC != nullptr && !right_looking && keep_env;
   const int OBp = potrf_outer_oz(nblk);
+  static const bool rowmax_env = !(getenv("AGPC_OZ_ROWMAX") && atoi(getenv("AGPC_OZ_ROWMAX")) == 0);
   for (int h = 1; h < nblk; h *= 2) {
     const int G = 2 * h;
     const int groups = (nblk + G - 1) / G;
@@ -624,6 +625,12 @@ cudaError_t trtri_blocked(const Launch& L, const MatSet& ms, const int* active) 
       a.m_kind = EXT_FIXED; a.n_kind = EXT_H2; a.k_kind = EXT_FIXED;
       a.grp_blocks = G; a.half_blocks = h; a.nblk = nblk;
       a.k_rule = KRULE_BEGIN_AT_ROW; a.alpha = 1.0; a.beta = 0.0; a.active = active;
+      // the epilogue collects max |T_ij| per row, so the slicing of T below needs no row-maximum pass over T
+      const bool t_max = ms.rmax != nullptr && rowmax_env && oz_gemm_rowmax_supported();
+      if (t_max) {
+        AGPC_CUDA_TRY(cudaMemsetAsync(ms.rmax, 0, sizeof(double) * (size_t)ms.np * ms.batch, Lt.stream));
+        a.row_absmax = ms.rmax; a.absmax_batch = ms.np;
+      }
       AGPC_CUDA_TRY(oz_gemm_launch(Lt, a, h * h, groups, ms.batch, ms.oz_S));
       // step 2: M21 = -M22 * T^T ; U12 = M21^T  (M22 lower triangular: K up to the tile row)
       OzSliceArgs sm = oz_slice_args(ms, ms.M, wa, active);
@@ -631,6 +638,7 @@ cudaError_t trtri_blocked(const Launch& L, const MatSet& ms, const int* active) 
       sm.grp_blocks = G; sm.half_blocks = h; sm.nblk = nblk; sm.need_h2 = 1;
       AGPC_CUDA_TRY(oz_slice_launch(Lt, sm, h, groups, ms.batch, ms.oz_S));
       OzSliceArgs st = oz_slice_args(ms, ms.T, 1, active);
+      if (t_max) st.given_max = ms.rmax;
       st.row0 = 0; st.col0 = h * TILE; st.row_blocks = h; st.cols_kind = EXT_H2;
       st.grp_blocks = G; st.half_blocks = h; st.nblk = nblk; st.need_h2 = 1;
       AGPC_CUDA_TRY(oz_slice_launch(Lt, st, h, groups, ms.batch, ms.oz_S));

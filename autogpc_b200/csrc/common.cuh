@@ -135,6 +135,9 @@ struct OzGemmArgs {  // same tile / group / K-range semantics as GemmArgs; n_til
   int k_rule, lower_only, skip_upper;
   double alpha, beta;
   const int* active;
+  double* row_absmax;      // optional: max |C_ij| over each row of the output region (what is STORED, beta included), by
+  long long absmax_batch;  //   atomic max into row_absmax[b * absmax_batch + row]; the caller zeroes it first.  NaN wins
+                           //   (bit pattern above every finite value), so a non-finite entry poisons its row as in FP64
   int concurrent;  // host hint: this launch shares the GPU with a latency-bound chain on another stream (look-ahead)
   int dbg;  // measurement aid (AGPC_OZ_DBG): 1 = main loop without MMAs (data movement only), 2 = without loads (MMAs on
             // whatever the ring holds); results are garbage in both
@@ -151,6 +154,8 @@ struct OzSliceArgs {
   int rows_kind, cols_kind;    // EXT_H2: right-half size of trtri group g
   int grp_blocks, half_blocks, nblk;
   int need_h2;  // grouped launches: skip groups without a right half (their left half may lie outside the matrix)
+  const double* given_max;    // non-null: max |x| of every row over the sliced range is GIVEN (indexed like scale[], e.g.
+                              // OzGemmArgs::row_absmax of the product that wrote X): no row-maximum pass over the data
   const double* fixed_scale;  // non-null: the row scales are GIVEN (scale[] already holds 2^(e - 8) from a bound on the row):
                               // no row-maximum pass, slices made with different calls share their scales
   int tri;  // 0: whole rectangle; 1: chunks up to the end of the row block's own diagonal block (lower triangular
@@ -160,6 +165,7 @@ struct OzSliceArgs {
 struct Launch;
 cudaError_t oz_gemm_launch(const Launch& L, const OzGemmArgs& a, int tiles128, int groups, int batch, int S);
 cudaError_t oz_slice_launch(const Launch& L, const OzSliceArgs& a, int row_blocks, int groups, int batch, int S);
+bool oz_gemm_rowmax_supported();  // false when an experimental kernel form without the row_absmax epilogue is selected
 void oz_release_stream(cudaStream_t st);  // persistent kernel's per-stream tile counter: give it back before destroying st
 // scale[b][i] = 2^(e_i - 8) with 2^e_i > 4 sqrt(A_ii): |L_ik| <= sqrt(A_ii) for every entry of row i of the Cholesky factor
 cudaError_t oz_row_bound_launch(const Launch& L, const double* A, long long ld, long long a_batch, int n, int batch,
@@ -182,6 +188,7 @@ struct MatSet {
   // the left-looking potrf left in SA (statically scaled) instead of slicing L a second time
   int8_t* SC = nullptr;
   double* scC = nullptr;
+  double* rmax = nullptr;  // optional [batch][np]: row maxima collected by a GEMM epilogue for the slicing of its output
   CUtensorMap mapA, mapM, mapU, mapT;
   CUtensorMap mapA32, mapM32;  // 32-row boxes: B operands of the thin GEMM variant
 };

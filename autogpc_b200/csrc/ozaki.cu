@@ -112,6 +112,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
                : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// max |v| into *dst (non-negative doubles order like their bit patterns; `bad` = a non-finite value was seen: NaN is stored)
+__device__ __forceinline__ void absmax_commit(double* dst, double m, bool bad) {
+  const unsigned long long bits = bad ? 0x7ff8000000000000ull : (unsigned long long)__double_as_longlong(m);
+  atomicMax(reinterpret_cast<unsigned long long*>(dst), bits);
+}
 // exact int32 -> double without the conversion pipe: 2^52 + 2^31 + v has v in its low mantissa bits
 __device__ __forceinline__ double i32_to_f64(uint32_t v) {
   return __hiloint2double(0x43300000, (int)(v ^ 0x80000000u)) - 4503601774854144.0;
@@ -312,6 +317,16 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzGemmA
         v.y = fma(beta, old.y, v.y);
       }
       *dst = v;
+      if (args.row_absmax != nullptr) {
+        double m = fmax(fabs(v.x), fabs(v.y));
+        int bad = !(fabs(v.x) + fabs(v.y) <= 1.7976931348623157e308);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+          bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+        }
+        if (lane == 0) absmax_commit(args.row_absmax + (long long)b * args.absmax_batch + c_row + rr, m, bad != 0);
+      }
     }
     if (args.Ct != nullptr) {
       const long long t_row = (long long)args.ct_row0 + shift + tj * TILE + half * OZ_BN;
@@ -639,12 +654,22 @@ ozaki_gemm_stream_kernel(const OzGemmArgs args, const int gx, const int gy, cons
       for (int i = 0; i < 16; ++i) sum[i] = (sum[i] * sa) * __ldg(sbp + i);
       if (beta != 0.0) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 4)
-          st_global_v4(crow + i, fma(beta, old[i], sum[i]), fma(beta, old[i + 1], sum[i + 1]), fma(beta, old[i + 2], sum[i + 2]),
-                       fma(beta, old[i + 3], sum[i + 3]));
+        for (int i = 0; i < 16; ++i) old[i] = fma(beta, old[i], sum[i]);
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) st_global_v4(crow + i, old[i], old[i + 1], old[i + 2], old[i + 3]);
       } else {
 #pragma unroll
         for (int i = 0; i < 16; i += 4) st_global_v4(crow + i, sum[i], sum[i + 1], sum[i + 2], sum[i + 3]);
+      }
+      if (args.row_absmax != nullptr) {
+        double m = 0.0, t = 0.0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const double v = fabs(beta != 0.0 ? old[i] : sum[i]);
+          m = fmax(m, v);
+          t += v;
+        }
+        absmax_commit(args.row_absmax + (long long)b * args.absmax_batch + c_row + row, m, !(t <= 1.7976931348623157e308));
       }
       if (args.Ct != nullptr) {  // transposed copy (alpha A B^T alone, as in the one-tile kernel): lanes = consecutive columns of Ct
         double* Tb = args.Ct + (long long)b * args.c_batch + (long long)(t_row + cgp * 16) * args.ldc + t_col + row;
@@ -951,6 +976,15 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const OzSliceArgs a) {
   if (a.fixed_scale != nullptr) {
     // given scales 2^(e - 8): multiplier 2^(8S - e) = 2^(8S - 8) / scale, exact
     if (tid < TILE) s_mult[tid] = scalbn(1.0, 8 * S - 8) / a.fixed_scale[(long long)b * a.sc_batch + row_base + tid];
+  } else if (a.given_max != nullptr) {
+    // row maxima collected by the epilogue of the product that wrote X: no pass over the data for them
+    if (tid < TILE) {
+      const double amax = a.given_max[(long long)b * a.sc_batch + row_base + tid];
+      const bool bad = !(amax <= 1.7976931348623157e308);
+      const int e = amax > 0.0 && !bad ? ilogb(amax) + 3 : 0;
+      s_mult[tid] = bad ? 0.0 : scalbn(1.0, 8 * S - e);
+      a.scale[(long long)b * a.sc_batch + row_base + tid] = bad ? __longlong_as_double(0x7ff8000000000000LL) : scalbn(1.0, e - 8);
+    }
   } else
   for (int rr = 0; rr < 16; ++rr) {
     const int r = warp * 16 + rr;
@@ -1255,6 +1289,12 @@ cudaError_t oz_gemm_launch(const Launch& L, const OzGemmArgs& a, int tiles128, i
   const bool pair = pair_env && a.k_rule != KRULE_END_AT_COL;
   if (S == 6) return pair ? oz_gemm_launch_t<6, true>(L, a, tiles128, groups, batch) : oz_gemm_launch_t<6, false>(L, a, tiles128, groups, batch);
   return pair ? oz_gemm_launch_t<7, true>(L, a, tiles128, groups, batch) : oz_gemm_launch_t<7, false>(L, a, tiles128, groups, batch);
+}
+
+bool oz_gemm_rowmax_supported() {
+  static const int tile_env = getenv("AGPC_OZ_TILE") ? atoi(getenv("AGPC_OZ_TILE")) : 64;
+  static const int dbg_env = getenv("AGPC_OZ_DBG") ? atoi(getenv("AGPC_OZ_DBG")) : 0;
+  return tile_env != 128 && tile_env != 129 && dbg_env == 0;
 }
 
 cudaError_t oz_slice_launch(const Launch& L, const OzSliceArgs& a, int row_blocks, int groups, int batch, int S) {
