@@ -677,10 +677,10 @@ def main():
                                                  "accumulator slots in TMEM, bulk-copy fed; sliced-integer FP64 GEMM behind potrf "
                                                  "updates, trtri, lauum)",
                     "achieved": achieved, "peak": peak, "unit": "TOP/s (int8)", "frac": achieved / peak,
-                    "traffic": 1.554e9,
+                    "traffic": 1.566e9,
                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 5 launches of this kernel "
-                                    "in profiles/r02_stream_kb_ncu_raw.csv (ncu --set full of this command with --kernels-only; "
-                                    "1.34-2.01 GB per launch: operand slices read once + the C tiles read and written once)",
+                                    "in profiles/r02_final_stream_kb_ncu_raw.csv (ncu --set full of this command with --kernels-only; "
+                                    "1.35-2.03 GB per launch: operand slices read once + the C tiles read and written once)",
                     "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (%s); the same kernel's MMA loop on "
                                    "resident operands sustains 4.4-4.5 POP/s at N >= 128 and 2.9 POP/s at its own N = 64 tile "
                                    "(TMEM holds S x 64 accumulator columns), profiles/r02_i8mma_probe.txt"
