@@ -57,3 +57,30 @@ def test_product_path_never_imports_the_oracle():
     for f in os.listdir(pkg):
         if f.endswith(".py"):
             assert "oracle" not in re.sub(r'""".*?"""', "", open(os.path.join(pkg, f)).read(), flags=re.S), f
+
+
+def _header_struct_fields(name):
+    """[(c type, field name)] of ``typedef struct <name> {...}`` in the public header, comments stripped."""
+    import re
+    text = open(HEADER).read()
+    body = re.search(r"typedef\s+struct\s+%s\s*\{(.*?)\}\s*%s\s*;" % (name, name), text, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    out = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:
+            parts = decl.split()
+            out.append((" ".join(parts[:-1]), parts[-1]))
+    return out
+
+
+def test_option_structs_mirror_the_header_field_by_field():
+    """``EPOptions`` / ``LBFGSOptions`` are passed by pointer: a reordered or retyped field would be read as garbage by the
+    library without any error, so the ctypes mirrors are checked against the header's declarations."""
+    import ctypes
+    from autogpc_b200 import engine
+    ctype = {"double": ctypes.c_double, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64}
+    for cname, mirror in (("agpc_ep_options", engine.EPOptions), ("agpc_lbfgs_options", engine.LBFGSOptions)):
+        fields = _header_struct_fields(cname)
+        assert [f for _, f in fields] == [f for f, _ in mirror._fields_], cname
+        assert [ctype[t] for t, _ in fields] == [t for _, t in mirror._fields_], cname

@@ -239,3 +239,28 @@ def test_failed_evaluations_are_tolerated_like_paramz(fake):
         assert np.isfinite(m._nlml) and m._nlml <= f0 and m.status == 0
     finally:
         eng_mod.set_default_engine(None)
+
+
+def test_device_optimizer_selection_rules(monkeypatch):
+    """Which driver ``optimize_models`` picks: the device loop wherever the engine has it and every model runs EP, unless
+    AGPC_DEVICE_OPT=0; an engine without ``optimize_batch`` (the oracle-backed test double) or a Laplace model stays on the
+    SciPy driver; AGPC_DEVICE_OPT=1 with a Laplace model is an error rather than a silent fallback."""
+    from types import SimpleNamespace
+    from autogpc_b200 import optim
+
+    with_dev = SimpleNamespace(optimize_batch=lambda *a, **k: None)
+    without = SimpleNamespace()
+    ep = lambda e: SimpleNamespace(engine=e, ep=dict(epsilon=1e-6, damping=0.0, max_sweeps=100))
+    lap = lambda e: SimpleNamespace(engine=e, ep=dict(epsilon=1e-10, damping=0.0, max_sweeps=50, inference="laplace"))
+    monkeypatch.delenv("AGPC_DEVICE_OPT", raising=False)
+    assert optim.device_optimizer_default([ep(with_dev), ep(with_dev)]) is True
+    assert optim.device_optimizer_default([ep(without)]) is False
+    assert optim.device_optimizer_default([ep(with_dev), lap(with_dev)]) is False
+    monkeypatch.setenv("AGPC_DEVICE_OPT", "0")
+    assert optim.device_optimizer_default([ep(with_dev)]) is False
+    monkeypatch.setenv("AGPC_DEVICE_OPT", "1")
+    assert optim.device_optimizer_default([ep(with_dev)]) is True
+    assert optim.device_optimizer_default([ep(without)]) is False
+    import pytest
+    with pytest.raises(ValueError):
+        optim.device_optimizer_default([lap(with_dev)])
