@@ -154,6 +154,8 @@ struct OzSliceArgs {
   int rows_kind, cols_kind;    // EXT_H2: right-half size of trtri group g
   int grp_blocks, half_blocks, nblk;
   int need_h2;  // grouped launches: skip groups without a right half (their left half may lie outside the matrix)
+  int col_split;              // > 1 (only with fixed_scale / given_max, i.e. no row-maximum pass): the chunk range of a row
+  int grid_rows;              //   block is cut into col_split parts, one CTA each: blockIdx.x = part * grid_rows + row block
   const double* given_max;    // non-null: max |x| of every row over the sliced range is GIVEN (indexed like scale[], e.g.
                               // OzGemmArgs::row_absmax of the product that wrote X): no row-maximum pass over the data
   const double* fixed_scale;  // non-null: the row scales are GIVEN (scale[] already holds 2^(e - 8) from a bound on the row):

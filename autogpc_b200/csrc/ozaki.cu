@@ -954,7 +954,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm128_kernel(const OzGe
 template <int S>
 __global__ void __launch_bounds__(256) ozaki_slice_kernel(const OzSliceArgs a) {
   constexpr int CPB = TILE / OZ_KB;
-  const int rbi = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
+  const int split = a.col_split > 1 ? a.col_split : 1;
+  const int rbi = split > 1 ? (int)blockIdx.x % a.grid_rows : (int)blockIdx.x, part = split > 1 ? (int)blockIdx.x / a.grid_rows : 0;
+  const int g = blockIdx.y, b = blockIdx.z;
   if (a.active != nullptr && a.active[b] == 0) return;
   int h2 = 0;
   if (a.grp_blocks > 0) {
@@ -969,6 +971,12 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const OzSliceArgs a) {
   int c_lo = 0, c_hi = ncc;
   if (a.tri == 1) c_hi = min(ncc, (rbi + 1) * CPB);
   if (a.tri == 2) c_lo = min(ncc, rbi * CPB);
+  if (split > 1) {  // this CTA's share of the chunk range (the scales are given: no pass needs the whole row)
+    const int per = (c_hi - c_lo + split - 1) / split;
+    c_lo = min(c_hi, c_lo + part * per);
+    c_hi = min(c_hi, c_lo + per);
+    if (c_lo >= c_hi && part > 0) return;
+  }
   const int row_base = a.row0 + shift + rbi * TILE, col_base = a.col0 + shift;
   const double* Xb = a.X + (long long)b * a.x_batch;
   __shared__ double s_mult[TILE];
@@ -983,7 +991,7 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const OzSliceArgs a) {
       const bool bad = !(amax <= 1.7976931348623157e308);
       const int e = amax > 0.0 && !bad ? ilogb(amax) + 3 : 0;
       s_mult[tid] = bad ? 0.0 : scalbn(1.0, 8 * S - e);
-      a.scale[(long long)b * a.sc_batch + row_base + tid] = bad ? __longlong_as_double(0x7ff8000000000000LL) : scalbn(1.0, e - 8);
+      if (part == 0) a.scale[(long long)b * a.sc_batch + row_base + tid] = bad ? __longlong_as_double(0x7ff8000000000000LL) : scalbn(1.0, e - 8);
     }
   } else
   for (int rr = 0; rr < 16; ++rr) {
@@ -1300,11 +1308,25 @@ bool oz_gemm_rowmax_supported() {
 cudaError_t oz_slice_launch(const Launch& L, const OzSliceArgs& a, int row_blocks, int groups, int batch, int S) {
   ProfScope prof_scope(L, CLS_SLICE);
   if (row_blocks <= 0 || groups <= 0 || batch <= 0) return cudaSuccess;
-  dim3 grid(row_blocks, groups, batch);
+  // Launches without a row-maximum pass are a chain of load -> convert -> store rounds per CTA, one per 32-column chunk:
+  // with few CTAs they are latency-bound (a 256-column potrf panel: 30 us whatever the number of active items), so the
+  // chunk range is cut into parts of >= 2 chunks until the grid has a few CTAs per SM slot.
+  OzSliceArgs b = a;
+  b.col_split = 0;
+  static const bool split_env = !(getenv("AGPC_OZ_SLICE_SPLIT") && atoi(getenv("AGPC_OZ_SLICE_SPLIT")) == 0);
+  if (split_env && (a.fixed_scale != nullptr || a.given_max != nullptr) && a.cols_kind == EXT_FIXED && a.col_chunks >= 4) {
+    int split = 1;
+    while (split * 2 * 2 <= a.col_chunks && (long long)row_blocks * groups * batch * split < 148LL * 3 * 4) split *= 2;
+    if (split > 1) {
+      b.col_split = split;
+      b.grid_rows = row_blocks;
+    }
+  }
+  dim3 grid(row_blocks * (b.col_split > 1 ? b.col_split : 1), groups, batch);
   if (S == 6)
-    ozaki_slice_kernel<6><<<grid, 256, 0, L.stream>>>(a);
+    ozaki_slice_kernel<6><<<grid, 256, 0, L.stream>>>(b);
   else
-    ozaki_slice_kernel<7><<<grid, 256, 0, L.stream>>>(a);
+    ozaki_slice_kernel<7><<<grid, 256, 0, L.stream>>>(b);
   L.bump();
   return cudaGetLastError();
 }
