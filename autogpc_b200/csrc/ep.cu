@@ -34,7 +34,7 @@ rowdot_kernel(const double* __restrict__ A, const double* __restrict__ x, double
   // align the start down to a multiple of 2 so double2 loads are 16-byte aligned (ncols is even)
   const int ka = k0 & ~1;
   double s = 0.0, q = 0.0;
-  for (int k = ka + 2 * lane; k < k1; k += 64) {
+  auto edge = [&](int k) {   // one masked step: the first 64 columns (may start below k0) and the last ones (may end at k1)
     const double2 a2 = *reinterpret_cast<const double2*>(row + k);
     const double2 x2 = *reinterpret_cast<const double2*>(xb + k);
     if (k >= k0) {
@@ -45,7 +45,35 @@ rowdot_kernel(const double* __restrict__ A, const double* __restrict__ x, double
       s += a2.y * x2.y;
       if (SQ && !(STRICT && k + 1 == i)) q += a2.y * a2.y;
     }
+  };
+  int k = ka + 2 * lane;
+  if (k < k1) edge(k);
+  k += 64;
+  // interior: four loads of the row in flight per lane, no masks.  k >= k0 after the first step; the bound keeps every
+  // element inside the range AND, for a lower row (k1 = i + 1), below the diagonal, which the strict sum of squares must
+  // leave out (an upper row has its diagonal in the first step).  One load per step left the kernel at 71 % of the DRAM
+  // rate (profiles/r02_rowdot_kernel_ncu_raw.csv: 96 % of the stall samples on the first use of the load).
+  const int k_in = k1 - 1;   // last index the interior may touch is k_in - 1
+  double s1 = 0.0, s2 = 0.0, s3 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+  for (; k + 193 < k_in; k += 256) {
+    const double2 a0 = *reinterpret_cast<const double2*>(row + k), a1 = *reinterpret_cast<const double2*>(row + k + 64);
+    const double2 a2 = *reinterpret_cast<const double2*>(row + k + 128), a3 = *reinterpret_cast<const double2*>(row + k + 192);
+    const double2 x0 = *reinterpret_cast<const double2*>(xb + k), x1 = *reinterpret_cast<const double2*>(xb + k + 64);
+    const double2 x2 = *reinterpret_cast<const double2*>(xb + k + 128), x3 = *reinterpret_cast<const double2*>(xb + k + 192);
+    s = fma(a0.x, x0.x, s); s = fma(a0.y, x0.y, s);
+    s1 = fma(a1.x, x1.x, s1); s1 = fma(a1.y, x1.y, s1);
+    s2 = fma(a2.x, x2.x, s2); s2 = fma(a2.y, x2.y, s2);
+    s3 = fma(a3.x, x3.x, s3); s3 = fma(a3.y, x3.y, s3);
+    if (SQ) {
+      q = fma(a0.x, a0.x, q); q = fma(a0.y, a0.y, q);
+      q1 = fma(a1.x, a1.x, q1); q1 = fma(a1.y, a1.y, q1);
+      q2 = fma(a2.x, a2.x, q2); q2 = fma(a2.y, a2.y, q2);
+      q3 = fma(a3.x, a3.x, q3); q3 = fma(a3.y, a3.y, q3);
+    }
   }
+  for (; k < k1; k += 64) edge(k);
+  s += (s1 + s2) + s3;
+  if (SQ) q += (q1 + q2) + q3;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
