@@ -308,7 +308,7 @@ int agpc_potrf(agpc_ctx* ctx, double* A, int32_t n, int32_t batch, double* Minv,
   if (want_inv) need += mat;  // T
   const int oz_S = ctx->oz_S;
   const size_t oz_bytes = (size_t)oz_S * n * n * batch, sc_bytes = sizeof(double) * (size_t)n * batch;
-  if (oz_S) need += 3 * (oz_bytes + 1024) + 4 * sc_bytes;
+  if (oz_S) need += 3 * (oz_bytes + 1024) + 6 * sc_bytes;
   int rc = ctx->ensure_arena(need + 4096);
   if (rc) return rc;
   char* p = (char*)ctx->arena;
@@ -325,6 +325,8 @@ int agpc_potrf(agpc_ctx* ctx, double* A, int32_t n, int32_t batch, double* Minv,
     ms.scB = (double*)p; p += sc_bytes;
     ms.scC = (double*)p; p += sc_bytes;
     ms.rmax = (double*)p; p += sc_bytes;
+    ms.rmM = (double*)p; p += sc_bytes;
+    ms.rmU = (double*)p; p += sc_bytes;
     p = (char*)(((uintptr_t)p + 1023) & ~(uintptr_t)1023);
     ms.SA = (int8_t*)p; p += (oz_bytes + 1023) / 1024 * 1024;
     ms.SB = (int8_t*)p; p += (oz_bytes + 1023) / 1024 * 1024;

@@ -595,6 +595,15 @@ cudaError_t trtri_blocked(const Launch& L, const MatSet& ms, const int* active) 
   const bool keep_L = oz_on(ms) && ms.SC != nullptr && !right_looking && keep_env;
   const int OBp = potrf_outer_oz(nblk);
   static const bool rowmax_env = !(getenv("AGPC_OZ_ROWMAX") && atoi(getenv("AGPC_OZ_ROWMAX")) == 0);
+  // Running row maxima of M and U (rmM, rmU): every entry of row i of U (of M) that exists when level h slices U11 (M22) lies
+  // inside that level's range -- the earlier levels' groups are sub-groups of the half the row belongs to -- so the maximum
+  // over everything produced so far IS the maximum of the range, and the slice launches of U11 / M22 need no pass of their
+  // own over the data (AGPC_OZ_ROWMAX=2 turns this part off).  Producers: oz_rowmax_init_launch after the FP64 levels
+  // (diagonal blocks + level h = 1), then the step-2 epilogue of every int8 level (rows of M21, columns of it for U12).
+  static const bool run_env = !(getenv("AGPC_OZ_ROWMAX") && atoi(getenv("AGPC_OZ_ROWMAX")) == 2);
+  const bool running = oz_on(ms) && ms.rmM != nullptr && ms.rmU != nullptr && rowmax_env && run_env && oz_gemm_rowmax_supported() &&
+                       nblk > OZ_TRTRI_MIN_H;
+  bool running_ready = false;
   for (int h = 1; h < nblk; h *= 2) {
     const int G = 2 * h;
     const int groups = (nblk + G - 1) / G;
@@ -606,7 +615,12 @@ cudaError_t trtri_blocked(const Launch& L, const MatSet& ms, const int* active) 
       // with a third image for trtri's own A operands those slices survive -- a third of this level's slicing traffic
       const bool l_kept = keep_L && h % OBp == 0;
       const int wa = keep_L ? 2 : 0;   // image of the A operands (U11, M22)
+      if (running && !running_ready) {  // first int8 level: the state the FP64 levels left behind
+        AGPC_CUDA_TRY(oz_rowmax_init_launch(Lt, ms.M, ms.U, ms.np, ms.stride, ms.np, h * TILE, ms.rmM, ms.rmU, ms.batch, active));
+        running_ready = true;
+      }
       OzSliceArgs su = oz_slice_args(ms, ms.U, wa, active);
+      if (running) su.given_max = ms.rmU;
       su.row0 = 0; su.col0 = 0; su.row_blocks = h; su.col_chunks = h * OZ_CPB; su.tri = 2;
       su.grp_blocks = G; su.half_blocks = h; su.nblk = nblk; su.need_h2 = 1;
       AGPC_CUDA_TRY(oz_slice_launch(Lt, su, h, groups, ms.batch, ms.oz_S));
@@ -634,6 +648,7 @@ cudaError_t trtri_blocked(const Launch& L, const MatSet& ms, const int* active) 
       AGPC_CUDA_TRY(oz_gemm_launch(Lt, a, h * h, groups, ms.batch, ms.oz_S));
       // step 2: M21 = -M22 * T^T ; U12 = M21^T  (M22 lower triangular: K up to the tile row)
       OzSliceArgs sm = oz_slice_args(ms, ms.M, wa, active);
+      if (running) sm.given_max = ms.rmM;
       sm.row0 = h * TILE; sm.col0 = h * TILE; sm.rows_kind = EXT_H2; sm.cols_kind = EXT_H2; sm.tri = 1;
       sm.grp_blocks = G; sm.half_blocks = h; sm.nblk = nblk; sm.need_h2 = 1;
       AGPC_CUDA_TRY(oz_slice_launch(Lt, sm, h, groups, ms.batch, ms.oz_S));
@@ -652,6 +667,9 @@ cudaError_t trtri_blocked(const Launch& L, const MatSet& ms, const int* active) 
       c.m_kind = EXT_H2; c.n_kind = EXT_FIXED; c.k_kind = EXT_H2;
       c.grp_blocks = G; c.half_blocks = h; c.nblk = nblk;
       c.k_rule = KRULE_END_AT_ROW; c.alpha = -1.0; c.beta = 0.0; c.active = active;
+      if (running) {  // the new blocks M21 (rows) and U12 = M21^T (columns of the product) enter the running maxima
+        c.row_absmax = ms.rmM; c.col_absmax = ms.rmU; c.absmax_batch = ms.np;
+      }
       AGPC_CUDA_TRY(oz_gemm_launch(Lt, c, h * h, groups, ms.batch, ms.oz_S));
       continue;
     }

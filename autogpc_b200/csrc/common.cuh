@@ -138,6 +138,7 @@ struct OzGemmArgs {  // same tile / group / K-range semantics as GemmArgs; n_til
   double* row_absmax;      // optional: max |C_ij| over each row of the output region (what is STORED, beta included), by
   long long absmax_batch;  //   atomic max into row_absmax[b * absmax_batch + row]; the caller zeroes it first.  NaN wins
                            //   (bit pattern above every finite value), so a non-finite entry poisons its row as in FP64
+  double* col_absmax;      // optional, with Ct: max |Ct_row| (= column maxima of the product), same indexing by Ct row
   int concurrent;  // host hint: this launch shares the GPU with a latency-bound chain on another stream (look-ahead)
   int dbg;  // measurement aid (AGPC_OZ_DBG): 1 = main loop without MMAs (data movement only), 2 = without loads (MMAs on
             // whatever the ring holds); results are garbage in both
@@ -167,6 +168,10 @@ struct OzSliceArgs {
 struct Launch;
 cudaError_t oz_gemm_launch(const Launch& L, const OzGemmArgs& a, int tiles128, int groups, int batch, int S);
 cudaError_t oz_slice_launch(const Launch& L, const OzSliceArgs& a, int row_blocks, int groups, int batch, int S);
+// rmM[i] = max_{k in [G0 * (i / G0), i]} |M[i][k]|, rmU[i] = max_{k in [i, G0 * (i / G0) + G0)} |U[i][k]|: the state of the running
+// maxima after the levels that ran without the epilogue hooks (diagonal blocks + FP64 levels; G0 = their group width)
+cudaError_t oz_rowmax_init_launch(const Launch& L, const double* M, const double* U, long long ld, long long batch_stride, int np,
+                                  int G0, double* rmM, double* rmU, int batch, const int* active);
 bool oz_gemm_rowmax_supported();  // false when an experimental kernel form without the row_absmax epilogue is selected
 void oz_release_stream(cudaStream_t st);  // persistent kernel's per-stream tile counter: give it back before destroying st
 // scale[b][i] = 2^(e_i - 8) with 2^e_i > 4 sqrt(A_ii): |L_ik| <= sqrt(A_ii) for every entry of row i of the Cholesky factor
@@ -191,6 +196,8 @@ struct MatSet {
   int8_t* SC = nullptr;
   double* scC = nullptr;
   double* rmax = nullptr;  // optional [batch][np]: row maxima collected by a GEMM epilogue for the slicing of its output
+  double *rmM = nullptr, *rmU = nullptr;  // optional [batch][np]: running max |M_ik| / |U_ik| over the part of row i that trtri has
+                                          // produced so far (kept by its producers): exactly the range the next level slices
   CUtensorMap mapA, mapM, mapU, mapT;
   CUtensorMap mapA32, mapM32;  // 32-row boxes: B operands of the thin GEMM variant
 };

@@ -334,8 +334,23 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzGemmA
       double* Tb = args.Ct + (long long)b * args.c_batch;
       for (int cc = ew; cc < OZ_BN; cc += 8) {
         const double sbc = args.B.scale[(long long)b * args.B.sc_batch + b_row + cc];
+        double m = 0.0, t = 0.0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) Tb[(t_row + cc) * args.ldc + t_col + lane + 32 * i] = stage[(lane + 32 * i) * OZ_EPI_LD + cc] * sbc;
+        for (int i = 0; i < 4; ++i) {
+          const double v = stage[(lane + 32 * i) * OZ_EPI_LD + cc] * sbc;
+          Tb[(t_row + cc) * args.ldc + t_col + lane + 32 * i] = v;
+          m = fmax(m, fabs(v));
+          t += fabs(v);
+        }
+        if (args.col_absmax != nullptr) {
+          int bad = !(t <= 1.7976931348623157e308);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+            bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+          }
+          if (lane == 0) absmax_commit(args.col_absmax + (long long)b * args.absmax_batch + t_row + cc, m, bad != 0);
+        }
       }
     }
   }
@@ -675,6 +690,21 @@ ozaki_gemm_stream_kernel(const OzGemmArgs args, const int gx, const int gy, cons
         double* Tb = args.Ct + (long long)b * args.c_batch + (long long)(t_row + cgp * 16) * args.ldc + t_col + row;
 #pragma unroll
         for (int i = 0; i < 16; ++i) Tb[(long long)i * args.ldc] = sum[i];
+        if (args.col_absmax != nullptr) {  // rows of Ct = columns of this tile: maximum over the warp's 32 rows, one atomic each
+          double* cm = args.col_absmax + (long long)b * args.absmax_batch + t_row + cgp * 16;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const double v = fabs(sum[i]);
+            int bad = !(v <= 1.7976931348623157e308);
+            double m = bad ? 0.0 : v;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+              bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+            }
+            if (lane == 0) absmax_commit(cm + i, m, bad != 0);
+          }
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * r);
@@ -1297,6 +1327,54 @@ cudaError_t oz_gemm_launch(const Launch& L, const OzGemmArgs& a, int tiles128, i
   const bool pair = pair_env && a.k_rule != KRULE_END_AT_COL;
   if (S == 6) return pair ? oz_gemm_launch_t<6, true>(L, a, tiles128, groups, batch) : oz_gemm_launch_t<6, false>(L, a, tiles128, groups, batch);
   return pair ? oz_gemm_launch_t<7, true>(L, a, tiles128, groups, batch) : oz_gemm_launch_t<7, false>(L, a, tiles128, groups, batch);
+}
+
+// one warp per row: the extent of row i inside its G0-wide diagonal group (lower part for M, upper part for U)
+__global__ void __launch_bounds__(256)
+oz_rowmax_init_kernel(const double* __restrict__ M, const double* __restrict__ U, long long ld, long long batch_stride, int np,
+                      int G0, double* __restrict__ rmM, double* __restrict__ rmU, const int* __restrict__ active) {
+  const int b = blockIdx.y;
+  if (active != nullptr && active[b] == 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + warp;
+  if (i >= np) return;
+  const int g0 = (i / G0) * G0, g1 = min(g0 + G0, np);
+  const double* mrow = M + (long long)b * batch_stride + (long long)i * ld;
+  const double* urow = U + (long long)b * batch_stride + (long long)i * ld;
+  double mm = 0.0, mu = 0.0, t = 0.0;
+  for (int k = g0 + lane; k <= i; k += 32) {
+    const double v = fabs(mrow[k]);
+    mm = fmax(mm, v);
+    t += v;
+  }
+  int bad_m = !(t <= 1.7976931348623157e308);
+  t = 0.0;
+  for (int k = i + lane; k < g1; k += 32) {
+    const double v = fabs(urow[k]);
+    mu = fmax(mu, v);
+    t += v;
+  }
+  int bad_u = !(t <= 1.7976931348623157e308);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mm = fmax(mm, __shfl_xor_sync(0xffffffffu, mm, o));
+    mu = fmax(mu, __shfl_xor_sync(0xffffffffu, mu, o));
+    bad_m |= __shfl_xor_sync(0xffffffffu, bad_m, o);
+    bad_u |= __shfl_xor_sync(0xffffffffu, bad_u, o);
+  }
+  if (lane == 0) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    rmM[(long long)b * np + i] = bad_m ? nan : mm;
+    rmU[(long long)b * np + i] = bad_u ? nan : mu;
+  }
+}
+cudaError_t oz_rowmax_init_launch(const Launch& L, const double* M, const double* U, long long ld, long long batch_stride, int np,
+                                  int G0, double* rmM, double* rmU, int batch, const int* active) {
+  ProfScope prof_scope(L, CLS_SLICE);
+  dim3 grid((np + 7) / 8, batch);
+  oz_rowmax_init_kernel<<<grid, 256, 0, L.stream>>>(M, U, ld, batch_stride, np, G0, rmM, rmU, active);
+  L.bump();
+  return cudaGetLastError();
 }
 
 bool oz_gemm_rowmax_supported() {

@@ -72,6 +72,7 @@ struct Chunk {
     if (oz_S > 0) {  // digit-slice images of the two operands of the int8 tensor-core GEMM + their row scales
       ms.SA = c.take<int8_t>(mat * oz_S); ms.SB = c.take<int8_t>(mat * oz_S); ms.SC = c.take<int8_t>(mat * oz_S);
       ms.scA = c.take<double>(vec); ms.scB = c.take<double>(vec); ms.scC = c.take<double>(vec); ms.rmax = c.take<double>(vec);
+      ms.rmM = c.take<double>(vec); ms.rmU = c.take<double>(vec);
     }
     tau = c.take<double>(vec); nu = c.take<double>(vec); s = c.take<double>(vec); sig = c.take<double>(vec);
     mu = c.take<double>(vec); w = c.take<double>(vec); u = c.take<double>(vec); t = c.take<double>(vec);
