@@ -692,17 +692,43 @@ ozaki_gemm_stream_kernel(const OzGemmArgs args, const int gx, const int gy, cons
         for (int i = 0; i < 16; ++i) Tb[(long long)i * args.ldc] = sum[i];
         if (args.col_absmax != nullptr) {  // rows of Ct = columns of this tile: maximum over the warp's 32 rows, one atomic each
           double* cm = args.col_absmax + (long long)b * args.absmax_batch + t_row + cgp * 16;
+          // 16 column maxima over 32 lanes by a halving butterfly: at distance 16 / 8 / 4 / 2 every lane hands the half of its
+          // columns that its partner keeps to the partner (8 + 4 + 2 + 1 exchanges), then one exchange at distance 1; lane l
+          // ends with column 8 b4 + 4 b3 + 2 b2 + b1 of its bits (31 shuffles instead of 16 x 5).  Non-finite values travel
+          // as +inf (fmax would drop a NaN) and are stored as NaN.
+          double v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const double v = fabs(sum[i]);
-            int bad = !(v <= 1.7976931348623157e308);
-            double m = bad ? 0.0 : v;
+            const double t = fabs(sum[i]);
+            v[i] = t <= 1.7976931348623157e308 ? t : __longlong_as_double(0x7ff0000000000000LL);
+          }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-              bad |= __shfl_xor_sync(0xffffffffu, bad, o);
-            }
-            if (lane == 0) absmax_commit(cm + i, m, bad != 0);
+          for (int i = 0; i < 8; ++i) {
+            const bool up = (lane & 16) != 0;
+            const double give = up ? v[i] : v[i + 8], keep = up ? v[i + 8] : v[i];
+            v[i] = fmax(keep, __shfl_xor_sync(0xffffffffu, give, 16));
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const bool up = (lane & 8) != 0;
+            const double give = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
+            v[i] = fmax(keep, __shfl_xor_sync(0xffffffffu, give, 8));
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const bool up = (lane & 4) != 0;
+            const double give = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i];
+            v[i] = fmax(keep, __shfl_xor_sync(0xffffffffu, give, 4));
+          }
+          {
+            const bool up = (lane & 2) != 0;
+            const double give = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+            v[0] = fmax(keep, __shfl_xor_sync(0xffffffffu, give, 2));
+          }
+          v[0] = fmax(v[0], __shfl_xor_sync(0xffffffffu, v[0], 1));
+          if ((lane & 1) == 0) {
+            const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            absmax_commit(cm + col, v[0], !(v[0] <= 1.7976931348623157e308));
           }
         }
       }
