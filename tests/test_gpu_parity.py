@@ -1085,3 +1085,48 @@ def test_device_optimizer_stopping_rules_match_scipy(engine, max_evals):
         assert d._nlml == pytest.approx(h._nlml, rel=1e-9)
         assert np.allclose(d.kern.param_array, h.kern.param_array, rtol=1e-7)
     engine.dataset_free(did)
+
+
+@pytest.mark.gpu
+def test_slicing_shortcuts_do_not_change_a_single_bit():
+    """trtri's slice launches take their row scales from maxima that the producers of the data collect (T: the epilogue of
+    the product that writes it; U11 / M22: running row maxima of U and M) instead of a pass of their own over the data.
+    Those maxima are exact, so L^-1 and L^-T must come out bit-identical with the shortcuts switched off (AGPC_OZ_ROWMAX=0);
+    the split of the given-scale slice launches over several CTAs (AGPC_OZ_SLICE_SPLIT=0) must not change anything either."""
+    import hashlib
+    import json
+    import subprocess
+    import sys
+    code = r'''
+import hashlib, json, os, sys
+import numpy as np, torch
+sys.path.insert(0, %r)
+from autogpc_b200.engine import Engine
+e = Engine(0)
+rng = np.random.default_rng(7)
+out = {}
+for n, batch in ((1536, 2), (2432, 1)):
+    G = rng.standard_normal((batch, n, n))
+    S = G @ G.transpose(0, 2, 1) / n + np.eye(n) * (1.0 + 30.0 * rng.random((batch, n, 1)))
+    S = 0.5 * (S + S.transpose(0, 2, 1))
+    A = torch.from_numpy(S.copy()).cuda()
+    Mi = torch.zeros_like(A)
+    Ui = torch.zeros_like(A)
+    torch.cuda.synchronize()
+    e.potrf(A.data_ptr(), n, batch, Mi.data_ptr(), Ui.data_ptr(), 0)
+    torch.cuda.synchronize()
+    h = hashlib.sha256()
+    for t in (A, Mi, Ui):
+        h.update(np.tril(t.cpu().numpy()).tobytes() if t is not Ui else np.triu(t.cpu().numpy()).tobytes())
+    Minv = np.linalg.inv(np.linalg.cholesky(S))
+    out[str(n)] = [h.hexdigest(), float(np.abs(np.tril(Mi.cpu().numpy()) - Minv).max())]
+print(json.dumps(out))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for tag, env in (("default", {}), ("two-pass", {"AGPC_OZ_ROWMAX": "0"}), ("no-split", {"AGPC_OZ_SLICE_SPLIT": "0"})):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[tag] = json.loads(r.stdout.strip().splitlines()[-1])
+    for n in ("1536", "2432"):
+        assert res["default"][n][1] < 1e-12
+        assert res["default"][n][0] == res["two-pass"][n][0] == res["no-split"][n][0], (n, res)
